@@ -1,0 +1,199 @@
+/* fb200.h - C ABI of libfb200.so, the B200 (sm_100a) fusion-head library.
+ *
+ * Drop-in boundary for ONE hot path of life-ufes/multimodal-model-skin-lesion-classifier:
+ * the multimodal fusion head + MLP classifier + class-weighted cross-entropy, forward and
+ * backward.  The reference has no FFI layer: its boundary is the Python class
+ *   MultimodalModel(...)            src/scripts/benchmark/models/multimodalIntraInterModal.py:13-28
+ *   MultimodalModel.forward         ... :162-416
+ *   nn.CrossEntropyLoss(weight=w)   src/scripts/benchmark/train_pad_20.py:52,111
+ * The Python host (fusion_b200.MultimodalModel) keeps that class' constructor, parameter
+ * names and fusion strings and calls the entry points below through ctypes with raw device
+ * pointers.  No torch types cross this boundary.  Every function returns an int status
+ * (0 = OK, negative = FB200_E*), never throws, never exits; there is NO CPU fallback - a
+ * host pointer or a missing GPU is FB200_EUNSUPPORTED / FB200_ECUDA.
+ *
+ * Threading: the library keeps no mutable global state besides a per-device cache of
+ * immutable kernel attributes; calls are re-entrant, launch only on the stream handed in
+ * (forward is called on the Python main thread, backward on autograd's device thread) and
+ * are CUDA-graph capturable.
+ */
+#ifndef FB200_H
+#define FB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_VERSION 100
+
+/* status codes */
+#define FB200_OK            0
+#define FB200_EBADARG      -1   /* null pointer / inconsistent descriptor                 */
+#define FB200_EUNSUPPORTED -2   /* shape / dtype / device the kernels do not cover        */
+#define FB200_EALIGN       -3   /* pointer or leading dimension breaks a 16-byte contract */
+#define FB200_ECUDA        -4   /* a CUDA runtime / driver call failed                    */
+#define FB200_EABSENT      -5   /* parameter slot does not exist in this configuration    */
+
+/* compute dtypes (fb200_desc.dtype).  Parameters and the API tensors are always fp32. */
+#define FB200_F32   0   /* fp32 storage; GEMMs either FFMA (exact fp32) or 3xTF32 on tcgen05 */
+#define FB200_BF16  1   /* bf16 operands, fp32 accumulation, fp32 LayerNorm / loss          */
+
+/* fusion strings of MultimodalModel.forward (multimodalIntraInterModal.py:205-416), in the
+ * order they are tested there.  fb200_mechanism_from_string() maps the literal strings. */
+enum fb200_mechanism {
+  FB200_NO_METADATA = 0,              /* :205 */
+  FB200_NO_METADATA_WITHOUT_MLP,      /* :208 */
+  FB200_CONCATENATION,                /* :211 */
+  FB200_CROSSATTENTION,               /* :215 */
+  FB200_WEIGHTED,                     /* :219 */
+  FB200_GFCAM,                        /* :225 */
+  FB200_CROSS_WEIGHTS_AFTER_CROSSATT, /* :231 */
+  FB200_METABLOCK,                    /* :237 */
+  FB200_RGATT2FUSEFEATURES,           /* :247 */
+  FB200_RG_ATT,                       /* :253 */
+  FB200_ATT_INTRAMODAL,               /* :265 */
+  FB200_ATT_INTRAMODAL_RESIDUAL,      /* :273 */
+  FB200_CROSS_ATTENTION_ONLY,         /* :285 */
+  FB200_RESIDUAL_CROSSATT,            /* :301 */
+  FB200_RGATT_FULL,                   /* :322 "att-intramodal+residual+cross-attention-metadados" */
+  FB200_RGATT_FULL_RGATT2FUSE,        /* :343 */
+  FB200_RGATT_FULL_METABLOCK,         /* :364 */
+  FB200_RGATT_FULL_INTRAMODAL_RES,    /* :388 */
+  FB200_NUM_MECHANISMS
+};
+
+/* fb200_desc.flags */
+#define FB200_FLAG_NEED_DIMG   1   /* backward also produces d(img_feat) (backbone unfrozen) */
+#define FB200_FLAG_NEED_DTEXT  2   /* backward also produces d(text_in) (trainable encoder)  */
+#define FB200_FLAG_FORCE_SIMT  4   /* never use the tcgen05 GEMM (exact-fp32 FFMA everywhere) */
+#define FB200_FLAG_FORCE_TC    8   /* use the tcgen05 GEMM wherever its shape rules allow     */
+
+/* dropout sites, reference call order (nn.Dropout modules reached by forward) */
+enum fb200_dropout_site {
+  FB200_DROP_IMG_RES = 0,   /* image_residual.dropout  p=0.1  [B,D]   gatedResidualBlock.py:9,14 */
+  FB200_DROP_TXT_RES,       /* text_residual.dropout   p=0.1  [B,D]                              */
+  FB200_DROP_IMG_RES2,      /* second call of image_residual (strings :343, :388)                */
+  FB200_DROP_TXT_RES2,      /* second call of text_residual  (string :388)                       */
+  FB200_DROP_FC1,           /* fc_fusion[3] p=0.5 / after-metablock MLP[3] p=0.3  [B,D]   :139,153 */
+  FB200_DROP_FC2,           /* fc_fusion[7] p=0.5 / after-metablock MLP[7] p=0.3  [B,D/2] :143,157 */
+  FB200_NUM_DROPOUT_SITES
+};
+
+/* One head instance = the reference constructor arguments that shape the path
+ * (multimodalIntraInterModal.py:14-28) plus the batch and the execution mode. */
+typedef struct fb200_desc {
+  int32_t mechanism;   /* enum fb200_mechanism  <- attention_mecanism                     */
+  int32_t B;           /* rows in this call (any B >= 1)                                  */
+  int32_t F;           /* cnn_dim_output: width of img_feat                               */
+  int32_t V;           /* vocab_size: width of the one-hot metadata (text_mode 0)         */
+  int32_t T;           /* text_encoder_dim_output (512 one-hot, 85 tab-transformer)       */
+  int32_t D;           /* common_dim (multiple of 8; the residual blocks hard-code 8 heads) */
+  int32_t H;           /* num_heads (only validated: D % H == 0, as nn.MultiheadAttention) */
+  int32_t C;           /* num_classes                                                     */
+  int32_t n;           /* ctor argument n (fc_fusion input = n*D; the six strings need 2) */
+  int32_t text_mode;   /* 0: text_in = [B,V] one-hot -> text_fc; 1: text_in = [B,T] encoder output */
+  int32_t dtype;       /* FB200_F32 | FB200_BF16                                          */
+  int32_t train;       /* 1: dropout active (masks or Philox), 0: eval                    */
+  int32_t flags;       /* FB200_FLAG_*                                                    */
+  int32_t reserved;
+} fb200_desc;
+
+/* ---- introspection (host only, no GPU needed) ------------------------------------- */
+int          fb200_version(void);
+const char*  fb200_strerror(int status);
+int          fb200_mechanism_from_string(const char* attention_mecanism); /* -1: unknown */
+const char*  fb200_mechanism_string(int mechanism);
+int          fb200_num_params(void);                 /* 78 slots, reference state_dict order */
+const char*  fb200_param_name(int slot);             /* e.g. "image_projector.weight"        */
+/* rows/cols of a slot under desc (cols = 0 for 1-D tensors); FB200_EABSENT if the slot does
+ * not exist (text_fc.* when text_mode = 1). */
+int          fb200_param_shape(const fb200_desc* d, int slot, int64_t* rows, int64_t* cols);
+/* Element offset of the slot's gradient inside the flat gradient buffer, or -1 when the
+ * reference leaves .grad = None for it under this mechanism. */
+int64_t      fb200_grad_offset(const fb200_desc* d, int slot);
+int64_t      fb200_grad_elems(const fb200_desc* d);  /* size of the flat gradient buffer (fp32 elements) */
+int          fb200_workspace_bytes(const fb200_desc* d, size_t* bytes);
+float        fb200_dropout_p(const fb200_desc* d, int site);   /* 0 when the site is unused */
+int          fb200_dropout_shape(const fb200_desc* d, int site, int64_t* rows, int64_t* cols);
+/* Algorithmic work of one train step (forward + backward) under desc: FLOPs = 6*B*MAC_live
+ * minus the dX GEMMs nobody needs, bytes = 3*P_live*4 + input/grad traffic. */
+int          fb200_algorithmic_work(const fb200_desc* d, double* flops, double* bytes, int64_t* live_params);
+/* Number of kernel launches one forward / one backward issues (for bench.py's gpu_launches). */
+int          fb200_launch_count(const fb200_desc* d, int* forward, int* backward);
+
+/* ---- the hot path ----------------------------------------------------------------- */
+/* All pointers are DEVICE pointers on the current device; `stream` is a cudaStream_t.
+ * params[slot]  : fp32 parameter tensors, contiguous, reference shapes (NULL for absent slots)
+ * img_feat      : [B,F] fp32 row-major (output of image_encoder, :167-170)
+ * text_in       : [B,V] (text_mode 0) or [B,T] (text_mode 1) fp32 row-major
+ * masks[site]   : optional uint8 keep-masks ({0,1}, row-major, fb200_dropout_shape); when
+ *                 train = 1 and masks == NULL (or masks[site] == NULL) the kernels draw the
+ *                 mask from Philox4x32-10 keyed by (seed, offset, site, element)
+ * logits        : [B,C] fp32 out
+ * ws            : fb200_workspace_bytes() bytes, 256-byte aligned; must stay untouched
+ *                 between forward and the matching backward (it holds the saved activations) */
+int fb200_head_forward(const fb200_desc* d, const void* const* params,
+                       const void* img_feat, const void* text_in,
+                       const uint8_t* const* masks, uint64_t seed, uint64_t offset,
+                       void* logits, void* ws, void* stream);
+
+/* dlogits : [B,C] fp32.  grads : flat fp32 buffer of fb200_grad_elems() elements; the call
+ * overwrites it (rows of in_proj_weight/bias that belong to W_q/W_k are written as zeros,
+ * exactly like autograd does for S=1 attention).  d_img_feat / d_text_in : [B,F] / [B,V|T]
+ * fp32 out, required iff the matching FB200_FLAG_NEED_* bit is set, else may be NULL. */
+int fb200_head_backward(const fb200_desc* d, const void* const* params,
+                        const void* img_feat, const void* text_in,
+                        const uint8_t* const* masks, uint64_t seed, uint64_t offset,
+                        const void* dlogits, void* grads, void* d_img_feat, void* d_text_in,
+                        void* ws, void* stream);
+
+/* Fused log-softmax + class-weighted NLL (nn.CrossEntropyLoss(weight, reduction='mean')),
+ * forward and dlogits in one launch pair.
+ * class_w  : [C] fp32 or NULL (all ones).
+ * denom    : device scalar holding the global sum_i w[y_i] (data-parallel runs), or NULL to
+ *            use this batch's own sum.
+ * loss_out : device float[3] = { loss, numerator, local weight sum }.
+ * dlogits  : [B,C] fp32 out, or NULL for loss only. */
+int fb200_cross_entropy(const void* logits, const int64_t* labels, const float* class_w,
+                        const float* denom, int B, int C, float* loss_out, void* dlogits,
+                        void* stream);
+
+/* forward + cross-entropy + backward in one call (what model.forward_loss / bench.py use). */
+int fb200_head_train_step(const fb200_desc* d, const void* const* params,
+                          const void* img_feat, const void* text_in,
+                          const int64_t* labels, const float* class_w, const float* denom,
+                          const uint8_t* const* masks, uint64_t seed, uint64_t offset,
+                          void* logits, float* loss_out, void* grads,
+                          void* d_img_feat, void* d_text_in, void* ws, void* stream);
+
+/* ---- primitives (exported for unit parity tests and micro-benchmarks) --------------- */
+/* C[M,N] (+)= op(A) * op(B) (+ bias) with fp32 tensors.
+ * layout: 0 = NT  C = A[M,K] * B[N,K]^T   (nn.Linear forward)
+ *         1 = NN  C = A[M,K] * B[K,N]     (dX = dY * W)
+ *         2 = TN  C = A[K,M]^T * B[K,N]   (dW = dY^T * X)
+ * engine: 0 = FFMA SIMT kernel, 1 = tcgen05 3xTF32, 2 = tcgen05 bf16 (operands rounded to bf16)
+ * bias: [N] or NULL; relu: apply max(.,0); accumulate: C += result. */
+int fb200_gemm(int layout, int engine, int M, int N, int K,
+               const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+               const float* bias, int relu, int accumulate, void* ws, size_t ws_bytes, void* stream);
+int fb200_gemm_workspace_bytes(int layout, int engine, int M, int N, int K, size_t* bytes);
+
+/* y = dropout(relu(LayerNorm(x))), rows of width N (fc_fusion[1:4], [5:8]); stats = [B,2] (mean, rstd) */
+int fb200_ln_relu_dropout_fwd(const float* x, const float* gamma, const float* beta,
+                              const uint8_t* mask, float p, int train, uint64_t seed, uint64_t offset, int site,
+                              int B, int N, float* y, float* stats, void* stream);
+int fb200_ln_relu_dropout_bwd(const float* x, const float* y, const float* gamma, const float* stats,
+                              const float* dy, float p, int train, int B, int N,
+                              float* dx, float* dgamma, float* dbeta, void* stream);
+/* MetaBlock modulation: y = sigmoid(tanh(v * LN(f)) + LN(g))  (metablock.py:22-32) */
+int fb200_metablock_fwd(const float* v, const float* f, const float* g,
+                        const float* gamma_f, const float* beta_f, const float* gamma_g, const float* beta_g,
+                        int B, int N, float* y, float* stats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FB200_H */

@@ -1,0 +1,498 @@
+// exec.cu - forward / backward executors over the op program, and the C ABI.
+#include "plan.h"
+#include "simt_gemm.cuh"
+#include "rowwise.cuh"
+#include "tc_gemm.cuh"
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace fb200 {
+
+struct DeviceInfo { int num_sms = 0; int cc_major = 0; };
+static int get_device_info(DeviceInfo& out) {
+  static std::mutex mu;
+  static DeviceInfo cache[64];
+  static bool have[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return FB200_ECUDA;
+  std::lock_guard<std::mutex> g(mu);
+  if (!have[dev]) {
+    int sms = 0, maj = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return FB200_ECUDA;
+    if (cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return FB200_ECUDA;
+    cache[dev].num_sms = sms; cache[dev].cc_major = maj; have[dev] = true;
+  }
+  out = cache[dev];
+  return FB200_OK;
+}
+
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; } } while (0)
+
+struct Ctx {
+  const Plan& p;
+  const void* const* params;
+  const void* img; const void* txt;
+  void* logits; const void* dlogits;
+  void* d_img; void* d_txt;
+  float* grads;
+  const uint8_t* const* masks; uint64_t seed, offset;
+  char* ws;
+  cudaStream_t st;
+  DeviceInfo dev;
+
+  TRef value(const View& v) const {
+    const Act& a = p.acts[v.buf];
+    if (a.ext == 1) return make_ref((float*)img + v.col0, a.cols, FMT_F32);
+    if (a.ext == 2) return make_ref((float*)txt + v.col0, a.cols, FMT_F32);
+    if (a.ext == 3) return make_ref((float*)logits + v.col0, a.cols, FMT_F32);
+    return make_ref(ws + a.off + (size_t)v.col0 * fmt_bytes(p.fmt), a.cols, p.fmt, (int64_t)p.d.B * a.cols);
+  }
+  TRef grad(const View& v) const {
+    const Act& a = p.acts[v.buf];
+    if (a.ext == 1) return make_ref(d_img ? (float*)d_img + v.col0 : nullptr, a.cols, FMT_F32);
+    if (a.ext == 2) return make_ref(d_txt ? (float*)d_txt + v.col0 : nullptr, a.cols, FMT_F32);
+    if (a.ext == 3) return make_ref((float*)dlogits + v.col0, a.cols, FMT_F32);
+    return make_ref(ws + a.goff + (size_t)v.col0 * fmt_bytes(p.fmt), a.cols, p.fmt, (int64_t)p.d.B * a.cols);
+  }
+  const float* param(int slot, int64_t elem_off = 0) const { return (const float*)params[slot] + elem_off; }
+  float* pgrad(int slot, int64_t elem_off = 0) const { return grads + p.goff[slot] + elem_off; }
+  DropSpec drop(const Op& o) const {
+    DropSpec s; s.mask = nullptr; s.seed = seed; s.offset = offset; s.p = o.p; s.site = o.site; s.active = 0;
+    if (p.d.train && o.site >= 0 && o.p > 0.f) { s.active = 1; if (masks && masks[o.site]) s.mask = masks[o.site]; }
+    return s;
+  }
+};
+
+// ------------------------------------------------------------------------------- forward
+static int run_forward(Ctx& c) {
+  const Plan& p = c.p; const int B = p.d.B;
+  for (const Op& o : p.ops) {
+    switch (o.kind) {
+      case OP_LINEAR: {
+        GemmArgs g{};
+        g.A = c.value(o.in0); g.B = make_ref((void*)c.param(o.w_slot, (int64_t)o.w_row0 * o.in0.cols), o.in0.cols, FMT_F32);
+        g.C = c.value(o.out); g.M = B; g.N = o.out.cols; g.K = o.in0.cols; g.a_kc = 1; g.b_kc = 1;
+        g.bias = c.param(o.b_slot, o.w_row0); g.relu = o.relu; g.mask_src.p = nullptr; g.accumulate = 0; g.split_k = 1; g.colsum_a = nullptr;
+        CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
+      } break;
+      case OP_LNRD: {
+        LnrdArgs a{}; a.x = c.value(o.in0); a.y = c.value(o.out); a.gamma = c.param(o.ln_w[0]); a.beta = c.param(o.ln_b[0]);
+        a.stats = (float*)(c.ws + o.stats_off); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
+        const int grid = row_grid_for(B, a.N, c.dev.num_sms);
+#define CALL(NV, TPR) lnrd_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+        FB200_ROW_DISPATCH(a.N, CALL);
+#undef CALL
+      } break;
+      case OP_GATE: {
+        GateArgs a{}; a.x = c.value(o.in0); a.z = c.value(o.in1); a.y = c.value(o.out); a.B = B; a.N = o.out.cols;
+        const int grid = row_grid_for(B, a.N, c.dev.num_sms);
+#define CALL(NV, TPR) gate_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+        FB200_ROW_DISPATCH(a.N, CALL);
+#undef CALL
+      } break;
+      case OP_GRB: {
+        GrbArgs a{}; a.q = c.value(o.in0); a.a = c.value(o.in1); a.z = c.value(o.in2); a.y = c.value(o.out);
+        a.gamma = c.param(o.ln_w[0]); a.beta = c.param(o.ln_b[0]); a.stats = (float*)(c.ws + o.stats_off);
+        a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
+        const int grid = row_grid_for(B, a.N, c.dev.num_sms);
+#define CALL(NV, TPR) grb_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+        FB200_ROW_DISPATCH(a.N, CALL);
+#undef CALL
+      } break;
+      case OP_META: {
+        MetaArgs a{}; a.v = c.value(o.in0); a.f = c.value(o.in1); a.g = c.value(o.in2); a.y = c.value(o.out);
+        a.gamma_f = c.param(o.ln_w[0]); a.beta_f = c.param(o.ln_b[0]); a.gamma_g = c.param(o.ln_w[1]); a.beta_g = c.param(o.ln_b[1]);
+        a.stats = (float*)(c.ws + o.stats_off); a.B = B; a.N = o.out.cols;
+        const int grid = row_grid_for(B, a.N, c.dev.num_sms);
+#define CALL(NV, TPR) meta_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+        FB200_ROW_DISPATCH(a.N, CALL);
+#undef CALL
+      } break;
+      default: return FB200_EBADARG;
+    }
+    CUDA_OK(cudaGetLastError());
+  }
+  return FB200_OK;
+}
+
+// ------------------------------------------------------------------------------- backward
+static int run_backward(Ctx& c) {
+  const Plan& p = c.p; const int B = p.d.B;
+  CUDA_OK(cudaMemsetAsync(c.grads, 0, (size_t)p.grad_elems * sizeof(float), c.st));
+  std::vector<char> gwritten(p.acts.size(), 0);       // has the gradient buffer been written yet?
+  std::vector<char> pwritten(NUM_SLOTS, 0);           // has this weight gradient been written yet?
+  gwritten[p.logits.buf] = 1;
+  // Views that alias one buffer (concat halves) are tracked per (buffer, col0) through a small map
+  std::vector<std::pair<long long, char>> vw;
+  auto vkey = [](const View& v) { return ((long long)v.buf << 32) | (unsigned)v.col0; };
+  auto is_written = [&](const View& v) { if (gwritten[v.buf]) return true; for (auto& e : vw) if (e.first == vkey(v)) return e.second != 0; return false; };
+  auto set_written = [&](const View& v) {
+    if (v.col0 == 0 && v.cols == p.acts[v.buf].cols) { gwritten[v.buf] = 1; return; }
+    for (auto& e : vw) if (e.first == vkey(v)) { e.second = 1; return; }
+    vw.push_back({vkey(v), 1});
+  };
+  auto grad_wanted = [&](const View& v) {
+    const int ext = p.acts[v.buf].ext;
+    if (ext == 1) return c.d_img != nullptr;
+    if (ext == 2) return c.d_txt != nullptr;
+    return true;
+  };
+
+  for (int oi = (int)p.ops.size() - 1; oi >= 0; --oi) {
+    const Op& o = p.ops[oi];
+    // the gradient of a view that lives inside a fully written buffer counts as written
+    if (!is_written(o.out)) return FB200_EBADARG;
+    switch (o.kind) {
+      case OP_LINEAR: {
+        const int N = o.out.cols, K = o.in0.cols;
+        // dW[N,K] (+)= dY^T X ; db[N] += colsum(dY)
+        GemmArgs g{};
+        g.A = c.grad(o.out); g.a_kc = 0; g.B = c.value(o.in0); g.b_kc = 0;
+        g.C = make_ref(c.pgrad(o.w_slot, (int64_t)o.w_row0 * K), K, FMT_F32);
+        g.M = N; g.N = K; g.K = B; g.bias = nullptr; g.relu = 0; g.mask_src.p = nullptr;
+        g.accumulate = pwritten[o.w_slot]; g.split_k = 0; g.colsum_a = c.pgrad(o.b_slot, o.w_row0);
+        CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
+        pwritten[o.w_slot] = 1;
+        // dX[B,K] (+)= dY W, masked by the producer's ReLU when the input came out of Linear+ReLU
+        if (grad_wanted(o.in0)) {
+          GemmArgs h{};
+          h.A = c.grad(o.out); h.a_kc = 1; h.B = make_ref((void*)c.param(o.w_slot, (int64_t)o.w_row0 * K), K, FMT_F32); h.b_kc = 0;
+          h.C = c.grad(o.in0); h.M = B; h.N = K; h.K = N; h.bias = nullptr; h.relu = 0;
+          h.mask_src.p = nullptr;
+          if (p.acts[o.in0.buf].relu_out) h.mask_src = c.value(o.in0);
+          h.accumulate = is_written(o.in0); h.split_k = 1; h.colsum_a = nullptr;
+          CUDA_OK(launch_simt_gemm(h, c.dev.num_sms, c.st));
+          set_written(o.in0);
+        }
+      } break;
+      case OP_LNRD: {
+        LnrdArgs a{}; a.x = c.value(o.in0); a.y = c.value(o.out); a.dy = c.grad(o.out); a.dx = c.grad(o.in0);
+        a.gamma = c.param(o.ln_w[0]); a.stats = (float*)(c.ws + o.stats_off);
+        a.dgamma = c.pgrad(o.ln_w[0]); a.dbeta = c.pgrad(o.ln_b[0]); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
+        if (is_written(o.in0)) return FB200_EUNSUPPORTED;     // LN input has exactly one consumer in every program
+        const int grid = row_grid_for(B, a.N, c.dev.num_sms);
+#define CALL(NV, TPR) lnrd_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+        FB200_ROW_DISPATCH(a.N, CALL);
+#undef CALL
+        set_written(o.in0);
+      } break;
+      case OP_GATE: {
+        GateArgs a{}; a.x = c.value(o.in0); a.z = c.value(o.in1); a.dy = c.grad(o.out); a.dz = c.grad(o.in1); a.dx = c.grad(o.in0);
+        a.dx_accumulate = is_written(o.in0); a.B = B; a.N = o.out.cols;
+        if (is_written(o.in1)) return FB200_EUNSUPPORTED;
+        const int grid = row_grid_for(B, a.N, c.dev.num_sms);
+#define CALL(NV, TPR) gate_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+        FB200_ROW_DISPATCH(a.N, CALL);
+#undef CALL
+        set_written(o.in0); set_written(o.in1);
+      } break;
+      case OP_GRB: {
+        GrbArgs a{}; a.q = c.value(o.in0); a.a = c.value(o.in1); a.z = c.value(o.in2); a.dy = c.grad(o.out);
+        a.da = c.grad(o.in1); a.dz = c.grad(o.in2); a.dq = c.grad(o.in0); a.dq_accumulate = is_written(o.in0);
+        a.gamma = c.param(o.ln_w[0]); a.stats = (float*)(c.ws + o.stats_off);
+        a.dgamma = c.pgrad(o.ln_w[0]); a.dbeta = c.pgrad(o.ln_b[0]); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
+        if (is_written(o.in1) || is_written(o.in2)) return FB200_EUNSUPPORTED;
+        const int grid = row_grid_for(B, a.N, c.dev.num_sms);
+#define CALL(NV, TPR) grb_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+        FB200_ROW_DISPATCH(a.N, CALL);
+#undef CALL
+        set_written(o.in0); set_written(o.in1); set_written(o.in2);
+      } break;
+      case OP_META: {
+        MetaArgs a{}; a.v = c.value(o.in0); a.f = c.value(o.in1); a.g = c.value(o.in2); a.y = c.value(o.out); a.dy = c.grad(o.out);
+        a.df = c.grad(o.in1); a.dg = c.grad(o.in2);
+        a.dv.p = nullptr;
+        if (grad_wanted(o.in0)) { a.dv = c.grad(o.in0); a.dv_accumulate = is_written(o.in0); }
+        a.gamma_f = c.param(o.ln_w[0]); a.beta_f = c.param(o.ln_b[0]); a.gamma_g = c.param(o.ln_w[1]); a.beta_g = c.param(o.ln_b[1]);
+        a.stats = (float*)(c.ws + o.stats_off);
+        a.dgamma_f = c.pgrad(o.ln_w[0]); a.dbeta_f = c.pgrad(o.ln_b[0]); a.dgamma_g = c.pgrad(o.ln_w[1]); a.dbeta_g = c.pgrad(o.ln_b[1]);
+        a.B = B; a.N = o.out.cols;
+        if (is_written(o.in1) || is_written(o.in2)) return FB200_EUNSUPPORTED;
+        const int grid = row_grid_for(B, a.N, c.dev.num_sms);
+#define CALL(NV, TPR) meta_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+        FB200_ROW_DISPATCH(a.N, CALL);
+#undef CALL
+        if (a.dv.p) set_written(o.in0);
+        set_written(o.in1); set_written(o.in2);
+      } break;
+      default: return FB200_EBADARG;
+    }
+    CUDA_OK(cudaGetLastError());
+  }
+  // inputs nobody differentiated through still owe the caller a defined gradient
+  if (c.d_img && !gwritten[0]) CUDA_OK(cudaMemsetAsync(c.d_img, 0, (size_t)B * p.d.F * sizeof(float), c.st));
+  if (c.d_txt && !gwritten[1]) CUDA_OK(cudaMemsetAsync(c.d_txt, 0, (size_t)B * p.acts[1].cols * sizeof(float), c.st));
+  return FB200_OK;
+}
+
+static int check_common(const fb200_desc* d, const void* const* params, const void* img, const void* txt, const void* ws, Plan& plan, DeviceInfo& dev) {
+  if (!d || !params || !img || !txt || !ws) return FB200_EBADARG;
+  int rc = build_plan(*d, plan);
+  if (rc != FB200_OK) return rc;
+  rc = get_device_info(dev);
+  if (rc != FB200_OK) return rc;
+  if (dev.cc_major < 10) return FB200_EUNSUPPORTED;          // sm_100a only: no other architecture is built
+  if (!is_device_ptr(img) || !is_device_ptr(ws)) return FB200_EUNSUPPORTED;   // no CPU path
+  for (int s = 0; s < NUM_SLOTS; ++s) {
+    if (!plan.live[s]) continue;
+    if (!params[s]) return FB200_EBADARG;
+    if (((uintptr_t)params[s]) & 15) return FB200_EALIGN;
+  }
+  if ((((uintptr_t)img) & 15) || (((uintptr_t)ws) & 255)) return FB200_EALIGN;
+  return FB200_OK;
+}
+
+static int ce_launch(const void* logits, const int64_t* labels, const float* class_w, const float* denom, int B, int C,
+                     float* loss_out, void* dlogits, cudaStream_t st) {
+  if (!logits || !labels || !loss_out || B < 1 || C < 1) return FB200_EBADARG;
+  CUDA_OK(cudaMemsetAsync(loss_out, 0, 3 * sizeof(float), st));
+  int rows_per_cta = 256 / 8;
+  int grid = (B + rows_per_cta - 1) / rows_per_cta; if (grid > 1184) grid = 1184;
+  ce_pass1_kernel<<<grid, 256, 0, st>>>((const float*)logits, labels, class_w, B, C, loss_out, (float*)dlogits);
+  CUDA_OK(cudaGetLastError());
+  int n = B * C; int g2 = (n + 255) / 256; if (g2 > 1184) g2 = 1184;
+  ce_pass2_kernel<<<g2, 256, 0, st>>>(denom, n, loss_out, (float*)dlogits);
+  CUDA_OK(cudaGetLastError());
+  return FB200_OK;
+}
+
+}  // namespace fb200
+
+using namespace fb200;
+
+// =================================================================================== C ABI
+extern "C" {
+
+int fb200_version(void) { return FB200_VERSION; }
+
+const char* fb200_strerror(int s) {
+  switch (s) {
+    case FB200_OK: return "ok";
+    case FB200_EBADARG: return "fb200: bad argument (null pointer or inconsistent descriptor)";
+    case FB200_EUNSUPPORTED: return "fb200: unsupported shape, dtype or device (this library is CUDA sm_100a only; there is no CPU path)";
+    case FB200_EALIGN: return "fb200: pointer or leading dimension violates the 16-byte alignment contract";
+    case FB200_ECUDA: return "fb200: CUDA runtime error";
+    case FB200_EABSENT: return "fb200: parameter slot absent in this configuration";
+    default: return "fb200: unknown status";
+  }
+}
+
+static const char* const kMechNames[FB200_NUM_MECHANISMS] = {
+  "no-metadata", "no-metadata-without-mlp", "concatenation", "crossattention", "weighted", "gfcam",
+  "cross-weights-after-crossattention", "metablock", "rg-att2fusefeatures", "rg-att", "att-intramodal",
+  "att-intramodal+residual", "cross-attention-only", "residual+cross-attention-metadados",
+  "att-intramodal+residual+cross-attention-metadados",
+  "att-intramodal+residual+cross-attention-metadados+rg-att2fusefeatures",
+  "att-intramodal+residual+cross-attention-metadados+metablock",
+  "att-intramodal+residual+cross-attention-metadados+att-intramodal+residual",
+};
+int fb200_mechanism_from_string(const char* s) {
+  if (!s) return -1;
+  for (int i = 0; i < FB200_NUM_MECHANISMS; ++i) if (std::strcmp(s, kMechNames[i]) == 0) return i;
+  return -1;
+}
+const char* fb200_mechanism_string(int m) { return (m >= 0 && m < FB200_NUM_MECHANISMS) ? kMechNames[m] : nullptr; }
+int fb200_num_params(void) { return NUM_SLOTS; }
+const char* fb200_param_name(int slot) { return (slot >= 0 && slot < NUM_SLOTS) ? kSlotNames[slot] : nullptr; }
+
+int fb200_param_shape(const fb200_desc* d, int slot, int64_t* rows, int64_t* cols) {
+  if (!d || !rows || !cols || slot < 0 || slot >= NUM_SLOTS) return FB200_EBADARG;
+  Shape s = slot_shape(*d, slot);
+  if (!s.present) return FB200_EABSENT;
+  *rows = s.rows; *cols = s.cols;
+  return FB200_OK;
+}
+int64_t fb200_grad_offset(const fb200_desc* d, int slot) {
+  if (!d || slot < 0 || slot >= NUM_SLOTS) return -1;
+  Plan p; if (build_plan(*d, p) != FB200_OK) return -1;
+  return p.goff[slot];
+}
+int64_t fb200_grad_elems(const fb200_desc* d) {
+  if (!d) return -1;
+  Plan p; if (build_plan(*d, p) != FB200_OK) return -1;
+  return p.grad_elems;
+}
+int fb200_workspace_bytes(const fb200_desc* d, size_t* bytes) {
+  if (!d || !bytes) return FB200_EBADARG;
+  Plan p; int rc = build_plan(*d, p); if (rc != FB200_OK) return rc;
+  *bytes = p.ws_bytes;
+  return FB200_OK;
+}
+float fb200_dropout_p(const fb200_desc* d, int site) {
+  if (!d || site < 0 || site >= FB200_NUM_DROPOUT_SITES) return 0.f;
+  Plan p; if (build_plan(*d, p) != FB200_OK) return 0.f;
+  return p.drop_p[site];
+}
+int fb200_dropout_shape(const fb200_desc* d, int site, int64_t* rows, int64_t* cols) {
+  if (!d || !rows || !cols || site < 0 || site >= FB200_NUM_DROPOUT_SITES) return FB200_EBADARG;
+  Plan p; int rc = build_plan(*d, p); if (rc != FB200_OK) return rc;
+  if (p.drop_p[site] == 0.f) return FB200_EABSENT;
+  *rows = d->B; *cols = p.drop_cols[site];
+  return FB200_OK;
+}
+int fb200_algorithmic_work(const fb200_desc* d, double* flops, double* bytes, int64_t* live_params) {
+  if (!d) return FB200_EBADARG;
+  Plan p; int rc = build_plan(*d, p); if (rc != FB200_OK) return rc;
+  if (flops) *flops = p.flops;
+  if (bytes) *bytes = p.bytes;
+  if (live_params) *live_params = p.live_params;
+  return FB200_OK;
+}
+int fb200_launch_count(const fb200_desc* d, int* forward, int* backward) {
+  if (!d) return FB200_EBADARG;
+  Plan p; int rc = build_plan(*d, p); if (rc != FB200_OK) return rc;
+  int f = 0, b = 0;
+  const bool need_dimg = d->flags & FB200_FLAG_NEED_DIMG, need_dtxt = d->flags & FB200_FLAG_NEED_DTEXT;
+  for (auto& o : p.ops) {
+    f += 1;
+    if (o.kind == OP_LINEAR) {
+      const int ext = p.acts[o.in0.buf].ext;
+      b += 1 + ((ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) ? 1 : 0);
+    } else b += 1;
+  }
+  if (forward) *forward = f;
+  if (backward) *backward = b;
+  return FB200_OK;
+}
+
+int fb200_head_forward(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
+                       const uint8_t* const* masks, uint64_t seed, uint64_t offset, void* logits, void* ws, void* stream) {
+  Plan plan; DeviceInfo dev;
+  int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
+  if (rc != FB200_OK) return rc;
+  if (!logits) return FB200_EBADARG;
+  Ctx c{plan, params, img_feat, text_in, logits, nullptr, nullptr, nullptr, nullptr, masks, seed, offset, (char*)ws, (cudaStream_t)stream, dev};
+  return run_forward(c);
+}
+
+int fb200_head_backward(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
+                        const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* dlogits, void* grads,
+                        void* d_img_feat, void* d_text_in, void* ws, void* stream) {
+  Plan plan; DeviceInfo dev;
+  int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
+  if (rc != FB200_OK) return rc;
+  if (!dlogits || !grads) return FB200_EBADARG;
+  if ((d->flags & FB200_FLAG_NEED_DIMG) && !d_img_feat) return FB200_EBADARG;
+  if ((d->flags & FB200_FLAG_NEED_DTEXT) && !d_text_in) return FB200_EBADARG;
+  Ctx c{plan, params, img_feat, text_in, nullptr, dlogits,
+        (d->flags & FB200_FLAG_NEED_DIMG) ? d_img_feat : nullptr, (d->flags & FB200_FLAG_NEED_DTEXT) ? d_text_in : nullptr,
+        (float*)grads, masks, seed, offset, (char*)ws, (cudaStream_t)stream, dev};
+  return run_backward(c);
+}
+
+int fb200_cross_entropy(const void* logits, const int64_t* labels, const float* class_w, const float* denom, int B, int C,
+                        float* loss_out, void* dlogits, void* stream) {
+  if (!logits || !is_device_ptr(logits)) return logits ? FB200_EUNSUPPORTED : FB200_EBADARG;
+  return ce_launch(logits, labels, class_w, denom, B, C, loss_out, dlogits, (cudaStream_t)stream);
+}
+
+int fb200_head_train_step(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
+                          const int64_t* labels, const float* class_w, const float* denom,
+                          const uint8_t* const* masks, uint64_t seed, uint64_t offset,
+                          void* logits, float* loss_out, void* grads, void* d_img_feat, void* d_text_in, void* ws, void* stream) {
+  Plan plan; DeviceInfo dev;
+  int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
+  if (rc != FB200_OK) return rc;
+  if (!logits || !labels || !loss_out || !grads) return FB200_EBADARG;
+  if ((d->flags & FB200_FLAG_NEED_DIMG) && !d_img_feat) return FB200_EBADARG;
+  if ((d->flags & FB200_FLAG_NEED_DTEXT) && !d_text_in) return FB200_EBADARG;
+  // dlogits live at the tail of the workspace (fb200_workspace_bytes reserves them)
+  char* w = (char*)ws;
+  float* dlog = (float*)(w + plan.ws_bytes - (((size_t)d->B * d->C * sizeof(float) + 255) & ~size_t(255)) - 256);
+  Ctx c{plan, params, img_feat, text_in, logits, dlog,
+        (d->flags & FB200_FLAG_NEED_DIMG) ? d_img_feat : nullptr, (d->flags & FB200_FLAG_NEED_DTEXT) ? d_text_in : nullptr,
+        (float*)grads, masks, seed, offset, w, (cudaStream_t)stream, dev};
+  rc = run_forward(c);
+  if (rc != FB200_OK) return rc;
+  rc = ce_launch(logits, labels, class_w, denom, d->B, d->C, loss_out, dlog, c.st);
+  if (rc != FB200_OK) return rc;
+  return run_backward(c);
+}
+
+// ---- primitives -----------------------------------------------------------------------
+int fb200_gemm_workspace_bytes(int layout, int engine, int M, int N, int K, size_t* bytes) {
+  if (!bytes || layout < 0 || layout > 2 || engine < 0 || engine > 2 || M < 1 || N < 1 || K < 1) return FB200_EBADARG;
+  *bytes = 256;
+  if (engine != 0) return tc_gemm_workspace_bytes(layout, engine, M, N, K, bytes);
+  return FB200_OK;
+}
+
+int fb200_gemm(int layout, int engine, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+               float* C, int ldc, const float* bias, int relu, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  if (!A || !B || !C || layout < 0 || layout > 2 || M < 1 || N < 1 || K < 1) return FB200_EBADARG;
+  if (!is_device_ptr(A) || !is_device_ptr(C)) return FB200_EUNSUPPORTED;
+  DeviceInfo dev; int rc = get_device_info(dev); if (rc != FB200_OK) return rc;
+  if (dev.cc_major < 10) return FB200_EUNSUPPORTED;
+  if (engine == 0) {
+    GemmArgs g{};
+    g.A = make_ref((void*)A, lda, FMT_F32); g.B = make_ref((void*)B, ldb, FMT_F32); g.C = make_ref(C, ldc, FMT_F32);
+    g.M = M; g.N = N; g.K = K;
+    g.a_kc = (layout == 2) ? 0 : 1;            // TN: A is [K,M]
+    g.b_kc = (layout == 0) ? 1 : 0;            // NT: B is [N,K]
+    g.bias = bias; g.relu = relu; g.mask_src.p = nullptr; g.accumulate = accumulate; g.split_k = 1; g.colsum_a = nullptr;
+    CUDA_OK(launch_simt_gemm(g, dev.num_sms, (cudaStream_t)stream));
+    return FB200_OK;
+  }
+  return tc_gemm_f32(layout, engine, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, accumulate, ws, ws_bytes, dev.num_sms, (cudaStream_t)stream);
+}
+
+int fb200_ln_relu_dropout_fwd(const float* x, const float* gamma, const float* beta, const uint8_t* mask, float p, int train,
+                              uint64_t seed, uint64_t offset, int site, int B, int N, float* y, float* stats, void* stream) {
+  if (!x || !gamma || !beta || !y || !stats || B < 1 || N < 4 || N % 4 || N > 4096) return FB200_EBADARG;
+  if (!is_device_ptr(x)) return FB200_EUNSUPPORTED;
+  DeviceInfo dev; int rc = get_device_info(dev); if (rc != FB200_OK) return rc;
+  LnrdArgs a{}; a.x = make_ref((void*)x, N); a.y = make_ref(y, N); a.gamma = gamma; a.beta = beta; a.stats = stats;
+  a.drop.mask = mask; a.drop.seed = seed; a.drop.offset = offset; a.drop.p = p; a.drop.site = site; a.drop.active = (train && p > 0.f) ? 1 : 0;
+  a.B = B; a.N = N;
+  const int grid = row_grid_for(B, N, dev.num_sms);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(NV, TPR) lnrd_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, st>>>(a)
+  FB200_ROW_DISPATCH(N, CALL);
+#undef CALL
+  CUDA_OK(cudaGetLastError());
+  return FB200_OK;
+}
+
+int fb200_ln_relu_dropout_bwd(const float* x, const float* y, const float* gamma, const float* stats, const float* dy, float p, int train,
+                              int B, int N, float* dx, float* dgamma, float* dbeta, void* stream) {
+  if (!x || !y || !gamma || !stats || !dy || !dx || !dgamma || !dbeta || B < 1 || N < 4 || N % 4 || N > 4096) return FB200_EBADARG;
+  if (!is_device_ptr(x)) return FB200_EUNSUPPORTED;
+  DeviceInfo dev; int rc = get_device_info(dev); if (rc != FB200_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaMemsetAsync(dgamma, 0, N * sizeof(float), st));
+  CUDA_OK(cudaMemsetAsync(dbeta, 0, N * sizeof(float), st));
+  LnrdArgs a{}; a.x = make_ref((void*)x, N); a.y = make_ref((void*)y, N); a.dy = make_ref((void*)dy, N); a.dx = make_ref(dx, N);
+  a.gamma = gamma; a.stats = (float*)stats; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.drop.mask = nullptr; a.drop.p = p; a.drop.active = (train && p > 0.f) ? 1 : 0; a.B = B; a.N = N;
+  const int grid = row_grid_for(B, N, dev.num_sms);
+#define CALL(NV, TPR) lnrd_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, st>>>(a)
+  FB200_ROW_DISPATCH(N, CALL);
+#undef CALL
+  CUDA_OK(cudaGetLastError());
+  return FB200_OK;
+}
+
+int fb200_metablock_fwd(const float* v, const float* f, const float* g, const float* gamma_f, const float* beta_f,
+                        const float* gamma_g, const float* beta_g, int B, int N, float* y, float* stats, void* stream) {
+  if (!v || !f || !g || !gamma_f || !beta_f || !gamma_g || !beta_g || !y || !stats || B < 1 || N < 4 || N % 4 || N > 4096) return FB200_EBADARG;
+  if (!is_device_ptr(v)) return FB200_EUNSUPPORTED;
+  DeviceInfo dev; int rc = get_device_info(dev); if (rc != FB200_OK) return rc;
+  MetaArgs a{}; a.v = make_ref((void*)v, N); a.f = make_ref((void*)f, N); a.g = make_ref((void*)g, N); a.y = make_ref(y, N);
+  a.gamma_f = gamma_f; a.beta_f = beta_f; a.gamma_g = gamma_g; a.beta_g = beta_g; a.stats = stats; a.B = B; a.N = N;
+  const int grid = row_grid_for(B, N, dev.num_sms);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(NV, TPR) meta_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, st>>>(a)
+  FB200_ROW_DISPATCH(N, CALL);
+#undef CALL
+  CUDA_OK(cudaGetLastError());
+  return FB200_OK;
+}
+
+}  // extern "C"

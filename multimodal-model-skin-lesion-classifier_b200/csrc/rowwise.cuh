@@ -1,0 +1,543 @@
+// rowwise.cuh - the HBM-bound fused kernels of the fusion head.  One warp owns one row
+// (rows are D = 512, D/2 = 256 or F <= 4096 wide), every global access is a 128-bit
+// coalesced vector, row statistics are warp-shuffle reductions held in registers, and
+// per-column parameter gradients are reduced warp -> CTA (smem) -> one atomic per column.
+//
+//   ln_relu_drop   : y = dropout(relu(LayerNorm(x)))                fc_fusion[1:4],[5:8]  (multimodalIntraInterModal.py:137-143)
+//   gate_mul       : y = sigmoid(z) * x                              img_gate / txt_gate    (:219-229)
+//   gated_residual : y = LN(g*drop(a) + (1-g)*q), g = sigmoid(z)     gatedResidualBlock.py:12-17
+//   metablock      : y = sigmoid(tanh(v*LN(f)) + LN(g))              metablock.py:22-32
+//   cross_entropy  : log-softmax + class-weighted NLL, fwd + dlogits train_pad_20.py:52,111
+#pragma once
+#include "common.cuh"
+
+namespace fb200 {
+
+constexpr int ROW_WARPS = 8;                 // warps per CTA in the row kernels
+constexpr float LN_EPS = 1e-5f;
+
+// A "group" of TPR threads owns one row: TPR = 32 (one warp, rows up to 512 wide) or
+// TPR = 256 (the whole CTA, rows up to 4096 wide).  Slot i of thread t covers columns
+// (i*TPR + t)*4 .. +3, so a warp-wide access is one contiguous 512-byte segment.
+template <int TPR>
+struct Grp {
+  int t, row0, rstep;
+  __device__ __forceinline__ Grp() {
+    if (TPR == 32) { t = threadIdx.x & 31; row0 = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); rstep = gridDim.x * ROW_WARPS; }
+    else { t = threadIdx.x; row0 = blockIdx.x; rstep = gridDim.x; }
+  }
+  // sums of a and b over the group (all threads of the group must call)
+  __device__ __forceinline__ float2 sum2(float a, float b, float2* scratch) const {
+    a = warp_sum(a); b = warp_sum(b);
+    if (TPR == 32) return make_float2(a, b);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = make_float2(a, b);
+    __syncthreads();
+    float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < ROW_WARPS; ++w) { float2 v = scratch[w]; r.x += v.x; r.y += v.y; }
+    return r;
+  }
+};
+#define COL(i) (((i) * TPR + G.t) * 4)
+
+template <int NV, int TPR>
+__device__ __forceinline__ void row_load(const Grp<TPR>& G, const TRef& t, int64_t row, int N, float4 (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int c = COL(i);
+    v[i] = (c < N) ? ld4(t, row, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int NV, int TPR>
+__device__ __forceinline__ void row_store(const Grp<TPR>& G, const TRef& t, int64_t row, int N, const float4 (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int c = COL(i);
+    if (c < N) st4(t, row, c, v[i]);
+  }
+}
+template <int NV, int TPR>
+__device__ __forceinline__ void row_load_param(const Grp<TPR>& G, const float* p, int N, float4 (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int c = COL(i);
+    v[i] = (c < N) ? __ldg((const float4*)(p + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// mean and 1/sqrt(var+eps) of one row held across the group (biased variance, two-pass)
+template <int NV, int TPR>
+__device__ __forceinline__ void row_stats(const Grp<TPR>& G, const float4 (&v)[NV], int N, float& mean, float& rstd, float2* scratch) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  mean = G.sum2(s, 0.f, scratch).x / (float)N;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int c = COL(i);
+    if (c < N) {
+      float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  rstd = rsqrtf(G.sum2(q, 0.f, scratch).x / (float)N + LN_EPS);
+}
+
+// Add per-thread column partials (accumulated over the rows this CTA visited) to a global
+// fp32 vector.  TPR = 32: the CTA's 8 warps hold partials for the same columns -> reduce in
+// smem first, one atomic per column per CTA.  TPR = 256: columns are distinct per thread.
+template <int NV, int TPR>
+__device__ __forceinline__ void cta_colsum_atomic(const Grp<TPR>& G, const float4 (&part)[NV], int N, float* dst, float* smem /*[ROW_WARPS][512]*/) {
+  if (TPR == 32) {
+    static_assert(TPR != 32 || NV <= 4, "warp-per-row kernels cover rows up to 512 wide");
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) *(float4*)(smem + warp * 512 + COL(i)) = part[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < 128 * NV && c < N; c += ROW_WARPS * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < ROW_WARPS; ++w) s += smem[w * 512 + c];
+      atomicAdd(dst + c, s);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = COL(i);
+      if (c < N) { atomicAdd(dst + c, part[i].x); atomicAdd(dst + c + 1, part[i].y); atomicAdd(dst + c + 2, part[i].z); atomicAdd(dst + c + 3, part[i].w); }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LN + ReLU + dropout
+struct LnrdArgs {
+  TRef x, y, dy, dx;
+  const float *gamma, *beta;
+  float *stats;              // [B,2] mean, rstd
+  float *dgamma, *dbeta;
+  DropSpec drop;
+  int B, N;
+};
+
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_fwd_kernel(const LnrdArgs a) {
+  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  float4 gam[NV], bet[NV];
+  row_load_param<NV, TPR>(G, a.gamma, a.N, gam);
+  row_load_param<NV, TPR>(G, a.beta, a.N, bet);
+  for (int64_t row = G.row0; row < a.B; row += G.rstep) {
+    float4 v[NV];
+    row_load<NV, TPR>(G, a.x, row, a.N, v);
+    float mean, rstd;
+    row_stats<NV, TPR>(G, v, a.N, mean, rstd, scratch);
+    if (G.t == 0) { a.stats[row * 2] = mean; a.stats[row * 2 + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = COL(i);
+      if (c < a.N) {
+        float4 m = drop_mult4(a.drop, row, c, a.N);
+        v[i].x = fmaxf((v[i].x - mean) * rstd * gam[i].x + bet[i].x, 0.f) * m.x;
+        v[i].y = fmaxf((v[i].y - mean) * rstd * gam[i].y + bet[i].y, 0.f) * m.y;
+        v[i].z = fmaxf((v[i].z - mean) * rstd * gam[i].z + bet[i].z, 0.f) * m.z;
+        v[i].w = fmaxf((v[i].w - mean) * rstd * gam[i].w + bet[i].w, 0.f) * m.w;
+      }
+    }
+    row_store<NV, TPR>(G, a.y, row, a.N, v);
+  }
+}
+
+// LayerNorm backward core for one row: given dyh = d(out)/d(LN output) (already multiplied by
+// everything downstream), returns dx in place of `g` and accumulates dgamma/dbeta partials.
+template <int NV, int TPR>
+__device__ __forceinline__ void ln_bwd_row(const Grp<TPR>& G, float2* scratch, const float4 (&xh)[NV], float4 (&g)[NV], const float4 (&gam)[NV],
+                                           float rstd, int N, float4 (&dgam)[NV], float4 (&dbet)[NV]) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    dgam[i].x += g[i].x * xh[i].x; dgam[i].y += g[i].y * xh[i].y; dgam[i].z += g[i].z * xh[i].z; dgam[i].w += g[i].w * xh[i].w;
+    dbet[i].x += g[i].x; dbet[i].y += g[i].y; dbet[i].z += g[i].z; dbet[i].w += g[i].w;
+    g[i].x *= gam[i].x; g[i].y *= gam[i].y; g[i].z *= gam[i].z; g[i].w *= gam[i].w;
+    s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+    s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+  }
+  const float2 tot = G.sum2(s1, s2, scratch);
+  s1 = tot.x / (float)N;
+  s2 = tot.y / (float)N;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g[i].x = rstd * (g[i].x - s1 - xh[i].x * s2);
+    g[i].y = rstd * (g[i].y - s1 - xh[i].y * s2);
+    g[i].z = rstd * (g[i].z - s1 - xh[i].z * s2);
+    g[i].w = rstd * (g[i].w - s1 - xh[i].w * s2);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void zero4(float4 (&v)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// xh = (x - mean) * rstd, zero outside the row
+template <int NV, int TPR>
+__device__ __forceinline__ void normalize(const Grp<TPR>& G, float4 (&v)[NV], float mean, float rstd, int N) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int c = COL(i);
+    if (c < N) { v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd; v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd; }
+    else v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_bwd_kernel(const LnrdArgs a) {
+  __shared__ __align__(16) float red[ROW_WARPS * 512];
+  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  float4 gam[NV], dgam[NV], dbet[NV];
+  row_load_param<NV, TPR>(G, a.gamma, a.N, gam);
+  zero4<NV>(dgam); zero4<NV>(dbet);
+  const float scale = a.drop.active ? 1.0f / (1.0f - a.drop.p) : 1.0f;
+  for (int64_t row = G.row0; row < a.B; row += G.rstep) {
+    float4 xh[NV], yv[NV], g[NV];
+    row_load<NV, TPR>(G, a.x, row, a.N, xh);
+    row_load<NV, TPR>(G, a.y, row, a.N, yv);
+    row_load<NV, TPR>(G, a.dy, row, a.N, g);
+    const float mean = a.stats[row * 2], rstd = a.stats[row * 2 + 1];
+    normalize<NV, TPR>(G, xh, mean, rstd, a.N);
+    // y > 0  <=>  kept by dropout AND ReLU active, so no mask is needed here
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      g[i].x = yv[i].x > 0.f ? g[i].x * scale : 0.f; g[i].y = yv[i].y > 0.f ? g[i].y * scale : 0.f;
+      g[i].z = yv[i].z > 0.f ? g[i].z * scale : 0.f; g[i].w = yv[i].w > 0.f ? g[i].w * scale : 0.f;
+    }
+    ln_bwd_row<NV, TPR>(G, scratch, xh, g, gam, rstd, a.N, dgam, dbet);
+    row_store<NV, TPR>(G, a.dx, row, a.N, g);
+  }
+  cta_colsum_atomic<NV, TPR>(G, dgam, a.N, a.dgamma, red);
+  cta_colsum_atomic<NV, TPR>(G, dbet, a.N, a.dbeta, red);
+}
+
+// ------------------------------------------------------------------ gate: y = sigmoid(z) * x
+struct GateArgs {
+  TRef x, z, y, dy, dz, dx;
+  int dx_accumulate;
+  int B, N;
+};
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) gate_fwd_kernel(const GateArgs a) {
+  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  for (int64_t row = G.row0; row < a.B; row += G.rstep) {
+    float4 x[NV], z[NV];
+    row_load<NV, TPR>(G, a.x, row, a.N, x);
+    row_load<NV, TPR>(G, a.z, row, a.N, z);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      x[i].x *= 1.f / (1.f + expf(-z[i].x)); x[i].y *= 1.f / (1.f + expf(-z[i].y));
+      x[i].z *= 1.f / (1.f + expf(-z[i].z)); x[i].w *= 1.f / (1.f + expf(-z[i].w));
+    }
+    row_store<NV, TPR>(G, a.y, row, a.N, x);
+  }
+}
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) gate_bwd_kernel(const GateArgs a) {
+  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  for (int64_t row = G.row0; row < a.B; row += G.rstep) {
+    float4 x[NV], z[NV], dy[NV], dx[NV];
+    row_load<NV, TPR>(G, a.x, row, a.N, x);
+    row_load<NV, TPR>(G, a.z, row, a.N, z);
+    row_load<NV, TPR>(G, a.dy, row, a.N, dy);
+    if (a.dx_accumulate) row_load<NV, TPR>(G, a.dx, row, a.N, dx); else zero4<NV>(dx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#define GATE1(f)                                              \
+      { float g = 1.f / (1.f + expf(-z[i].f));               \
+        dx[i].f += dy[i].f * g;                               \
+        z[i].f = dy[i].f * x[i].f * g * (1.f - g); }
+      GATE1(x) GATE1(y) GATE1(z) GATE1(w)
+#undef GATE1
+    }
+    row_store<NV, TPR>(G, a.dz, row, a.N, z);
+    row_store<NV, TPR>(G, a.dx, row, a.N, dx);
+  }
+}
+
+// ------------------------------------------------------------------ gated residual + LN
+struct GrbArgs {
+  TRef q, a, z, y;           // fwd: inputs q (residual base), a (attention out), z (gate pre-activation); out y
+  TRef dy, da, dz, dq;       // bwd
+  int dq_accumulate;
+  const float *gamma, *beta;
+  float *stats, *dgamma, *dbeta;
+  DropSpec drop;
+  int B, N;
+};
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p) {
+  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  float4 gam[NV], bet[NV];
+  row_load_param<NV, TPR>(G, p.gamma, p.N, gam);
+  row_load_param<NV, TPR>(G, p.beta, p.N, bet);
+  for (int64_t row = G.row0; row < p.B; row += G.rstep) {
+    float4 q[NV], a[NV], z[NV];
+    row_load<NV, TPR>(G, p.q, row, p.N, q);
+    row_load<NV, TPR>(G, p.a, row, p.N, a);
+    row_load<NV, TPR>(G, p.z, row, p.N, z);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = COL(i);
+      float4 m = (c < p.N) ? drop_mult4(p.drop, row, c, p.N) : make_float4(0.f, 0.f, 0.f, 0.f);
+#define GRB1(f)                                               \
+      { float g = 1.f / (1.f + expf(-z[i].f));               \
+        q[i].f = g * (a[i].f * m.f) + (1.f - g) * q[i].f; }
+      GRB1(x) GRB1(y) GRB1(z) GRB1(w)
+#undef GRB1
+    }
+    float mean, rstd;
+    row_stats<NV, TPR>(G, q, p.N, mean, rstd, scratch);
+    if (G.t == 0) { p.stats[row * 2] = mean; p.stats[row * 2 + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      q[i].x = (q[i].x - mean) * rstd * gam[i].x + bet[i].x; q[i].y = (q[i].y - mean) * rstd * gam[i].y + bet[i].y;
+      q[i].z = (q[i].z - mean) * rstd * gam[i].z + bet[i].z; q[i].w = (q[i].w - mean) * rstd * gam[i].w + bet[i].w;
+    }
+    row_store<NV, TPR>(G, p.y, row, p.N, q);
+  }
+}
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) grb_bwd_kernel(const GrbArgs p) {
+  __shared__ __align__(16) float red[ROW_WARPS * 512];
+  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  float4 gam[NV], dgam[NV], dbet[NV];
+  row_load_param<NV, TPR>(G, p.gamma, p.N, gam);
+  zero4<NV>(dgam); zero4<NV>(dbet);
+  for (int64_t row = G.row0; row < p.B; row += G.rstep) {
+    float4 q[NV], a[NV], z[NV], u[NV], du[NV];
+    row_load<NV, TPR>(G, p.q, row, p.N, q);
+    row_load<NV, TPR>(G, p.a, row, p.N, a);
+    row_load<NV, TPR>(G, p.z, row, p.N, z);
+    row_load<NV, TPR>(G, p.dy, row, p.N, du);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = COL(i);
+      float4 m = (c < p.N) ? drop_mult4(p.drop, row, c, p.N) : make_float4(0.f, 0.f, 0.f, 0.f);
+#define GRB2(f)                                               \
+      { float g = 1.f / (1.f + expf(-z[i].f));               \
+        z[i].f = g; a[i].f *= m.f;                            \
+        u[i].f = g * a[i].f + (1.f - g) * q[i].f; }
+      GRB2(x) GRB2(y) GRB2(z) GRB2(w)
+#undef GRB2
+      // keep the dropout multiplier for da in place of nothing: recomputed below
+    }
+    const float mean = p.stats[row * 2], rstd = p.stats[row * 2 + 1];
+    normalize<NV, TPR>(G, u, mean, rstd, p.N);
+    ln_bwd_row<NV, TPR>(G, scratch, u, du, gam, rstd, p.N, dgam, dbet);     // du now holds d(u)
+    float4 dq[NV];
+    if (p.dq_accumulate) row_load<NV, TPR>(G, p.dq, row, p.N, dq); else zero4<NV>(dq);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      int c = COL(i);
+      float4 m = (c < p.N) ? drop_mult4(p.drop, row, c, p.N) : make_float4(0.f, 0.f, 0.f, 0.f);
+#define GRB3(f)                                               \
+      { float g = z[i].f;                                     \
+        dq[i].f += du[i].f * (1.f - g);                       \
+        z[i].f = du[i].f * (a[i].f - q[i].f) * g * (1.f - g); \
+        a[i].f = du[i].f * g * m.f; }
+      GRB3(x) GRB3(y) GRB3(z) GRB3(w)
+#undef GRB3
+    }
+    row_store<NV, TPR>(G, p.da, row, p.N, a);
+    row_store<NV, TPR>(G, p.dz, row, p.N, z);
+    row_store<NV, TPR>(G, p.dq, row, p.N, dq);
+  }
+  cta_colsum_atomic<NV, TPR>(G, dgam, p.N, p.dgamma, red);
+  cta_colsum_atomic<NV, TPR>(G, dbet, p.N, p.dbeta, red);
+}
+
+// ------------------------------------------------------------------ MetaBlock modulation
+struct MetaArgs {
+  TRef v, f, g, y;            // v: visual features, f/g: Linear outputs of fb / gb, y: out
+  TRef dy, df, dg, dv;        // dv.p == nullptr -> not needed
+  int dv_accumulate;
+  const float *gamma_f, *beta_f, *gamma_g, *beta_g;
+  float *stats;               // [B,4] mean_f, rstd_f, mean_g, rstd_g
+  float *dgamma_f, *dbeta_f, *dgamma_g, *dbeta_g;
+  int B, N;
+};
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) meta_fwd_kernel(const MetaArgs p) {
+  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  for (int64_t row = G.row0; row < p.B; row += G.rstep) {
+    float4 f[NV], g[NV], v[NV], pr[NV];
+    row_load<NV, TPR>(G, p.f, row, p.N, f);
+    row_load<NV, TPR>(G, p.g, row, p.N, g);
+    float mf, rf, mg, rg;
+    row_stats<NV, TPR>(G, f, p.N, mf, rf, scratch);
+    row_stats<NV, TPR>(G, g, p.N, mg, rg, scratch);
+    if (G.t == 0) { float4 s = make_float4(mf, rf, mg, rg); *(float4*)(p.stats + row * 4) = s; }
+    row_load<NV, TPR>(G, p.v, row, p.N, v);
+    row_load_param<NV, TPR>(G, p.gamma_f, p.N, pr);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { f[i].x = (f[i].x - mf) * rf * pr[i].x; f[i].y = (f[i].y - mf) * rf * pr[i].y; f[i].z = (f[i].z - mf) * rf * pr[i].z; f[i].w = (f[i].w - mf) * rf * pr[i].w; }
+    row_load_param<NV, TPR>(G, p.beta_f, p.N, pr);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { f[i].x = tanhf(v[i].x * (f[i].x + pr[i].x)); f[i].y = tanhf(v[i].y * (f[i].y + pr[i].y)); f[i].z = tanhf(v[i].z * (f[i].z + pr[i].z)); f[i].w = tanhf(v[i].w * (f[i].w + pr[i].w)); }
+    row_load_param<NV, TPR>(G, p.gamma_g, p.N, pr);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { g[i].x = (g[i].x - mg) * rg * pr[i].x; g[i].y = (g[i].y - mg) * rg * pr[i].y; g[i].z = (g[i].z - mg) * rg * pr[i].z; g[i].w = (g[i].w - mg) * rg * pr[i].w; }
+    row_load_param<NV, TPR>(G, p.beta_g, p.N, pr);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      f[i].x = 1.f / (1.f + expf(-(f[i].x + g[i].x + pr[i].x))); f[i].y = 1.f / (1.f + expf(-(f[i].y + g[i].y + pr[i].y)));
+      f[i].z = 1.f / (1.f + expf(-(f[i].z + g[i].z + pr[i].z))); f[i].w = 1.f / (1.f + expf(-(f[i].w + g[i].w + pr[i].w)));
+    }
+    row_store<NV, TPR>(G, p.y, row, p.N, f);
+  }
+}
+// Backward in two sweeps per row so that at most ~6 row-vectors are live (F up to 4096).
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) meta_bwd_kernel(const MetaArgs p) {
+  __shared__ __align__(16) float red[ROW_WARPS * 512];
+  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  float4 dgf[NV], dbf[NV], dgg[NV], dbg[NV];
+  zero4<NV>(dgf); zero4<NV>(dbf); zero4<NV>(dgg); zero4<NV>(dbg);
+  for (int64_t row = G.row0; row < p.B; row += G.rstep) {
+    const float4 st = *(const float4*)(p.stats + row * 4);
+    float4 xf[NV], ds[NV], v[NV], pr[NV], pb[NV];
+    // ds = dy * y (1 - y)
+    row_load<NV, TPR>(G, p.y, row, p.N, xf);
+    row_load<NV, TPR>(G, p.dy, row, p.N, ds);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { ds[i].x *= xf[i].x * (1.f - xf[i].x); ds[i].y *= xf[i].y * (1.f - xf[i].y); ds[i].z *= xf[i].z * (1.f - xf[i].z); ds[i].w *= xf[i].w * (1.f - xf[i].w); }
+    // ---- f branch: t1 = LN_f(f); h = tanh(v t1); dt1 = ds (1-h^2) v; dv = ds (1-h^2) t1
+    row_load<NV, TPR>(G, p.f, row, p.N, xf);
+    normalize<NV, TPR>(G, xf, st.x, st.y, p.N);
+    row_load<NV, TPR>(G, p.v, row, p.N, v);
+    row_load_param<NV, TPR>(G, p.gamma_f, p.N, pr);
+    row_load_param<NV, TPR>(G, p.beta_f, p.N, pb);
+    float4 dt1[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#define MB1(c)                                                 \
+      { float t1 = xf[i].c * pr[i].c + pb[i].c;               \
+        float h = tanhf(v[i].c * t1);                         \
+        float dh = ds[i].c * (1.f - h * h);                   \
+        dt1[i].c = dh * v[i].c;                               \
+        v[i].c = dh * t1; }
+      MB1(x) MB1(y) MB1(z) MB1(w)
+#undef MB1
+    }
+    if (p.dv.p) {
+      if (p.dv_accumulate) {
+        float4 o[NV];
+        row_load<NV, TPR>(G, p.dv, row, p.N, o);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { v[i].x += o[i].x; v[i].y += o[i].y; v[i].z += o[i].z; v[i].w += o[i].w; }
+      }
+      row_store<NV, TPR>(G, p.dv, row, p.N, v);
+    }
+    ln_bwd_row<NV, TPR>(G, scratch, xf, dt1, pr, st.y, p.N, dgf, dbf);
+    row_store<NV, TPR>(G, p.df, row, p.N, dt1);
+    // ---- g branch: dt2 = ds
+    row_load<NV, TPR>(G, p.g, row, p.N, xf);
+    normalize<NV, TPR>(G, xf, st.z, st.w, p.N);
+    row_load_param<NV, TPR>(G, p.gamma_g, p.N, pr);
+    ln_bwd_row<NV, TPR>(G, scratch, xf, ds, pr, st.w, p.N, dgg, dbg);
+    row_store<NV, TPR>(G, p.dg, row, p.N, ds);
+  }
+  cta_colsum_atomic<NV, TPR>(G, dgf, p.N, p.dgamma_f, red);
+  cta_colsum_atomic<NV, TPR>(G, dbf, p.N, p.dbeta_f, red);
+  cta_colsum_atomic<NV, TPR>(G, dgg, p.N, p.dgamma_g, red);
+  cta_colsum_atomic<NV, TPR>(G, dbg, p.N, p.dbeta_g, red);
+}
+
+// ------------------------------------------------------------------ cross entropy
+// 8 lanes cooperate on one row (C <= 8 is one element per lane; larger C strides).
+// Pass 1: per-row log-sum-exp -> unnormalised gradient w[y](softmax - onehot) into dlogits,
+//         numerator / denominator reduced by shuffles then two atomics per warp.
+// Pass 2: scale by 1/denominator (this batch's, or the global one under data parallelism).
+__global__ void __launch_bounds__(256) ce_pass1_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                       const float* __restrict__ class_w, int B, int C,
+                                                       float* __restrict__ loss_out, float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & 7;
+  float num = 0.f, den = 0.f;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < (((int64_t)B + 3) & ~3LL); row += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const bool live = row < B;
+    const float* z = logits + (live ? row : 0) * C;
+    float mx = -INFINITY;
+    for (int c = sub; c < C; c += 8) mx = fmaxf(mx, z[c]);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int c = sub; c < C; c += 8) se += expf(z[c] - mx);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (live) {
+      const int y = (int)labels[row];
+      const float w = class_w ? class_w[y] : 1.f;
+      const float inv = 1.f / se;
+      if (dlogits) for (int c = sub; c < C; c += 8) dlogits[row * C + c] = w * (expf(z[c] - mx) * inv - (c == y ? 1.f : 0.f));
+      if (sub == 0) { num += w * (logf(se) + mx - z[y]); den += w; }
+    }
+  }
+  num = warp_sum(num); den = warp_sum(den);
+  if (lane == 0) { atomicAdd(loss_out + 1, num); atomicAdd(loss_out + 2, den); }
+}
+__global__ void __launch_bounds__(256) ce_pass2_kernel(const float* __restrict__ denom, int n, float* __restrict__ loss_out,
+                                                       float* __restrict__ dlogits) {
+  const float den = denom ? *denom : loss_out[2];
+  const float inv = 1.f / den;
+  if (blockIdx.x == 0 && threadIdx.x == 0) loss_out[0] = loss_out[1] * inv;
+  if (dlogits) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dlogits[i] *= inv;
+}
+
+// ------------------------------------------------------------------ format conversion
+// fp32 [rows, cols] (ld_in) -> FMT_PAIR / FMT_BF16 / FMT_F32 copy (ld_out); any alignment.
+__global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ in, int ld_in, TRef out, int64_t rows, int cols) {
+  int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols; int c = (int)(i - r * cols);
+    st1(out, r, c, in[r * ld_in + c]);
+  }
+}
+
+// column sums of a [rows, N] matrix into fp32 dst (atomic): bias gradients for the tcgen05 path
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) colsum_kernel(TRef x, int B, int N, float* dst) {
+  __shared__ __align__(16) float red[ROW_WARPS * 512];
+  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  float4 acc[NV];
+  zero4<NV>(acc);
+  for (int64_t row = G.row0; row < B; row += G.rstep) {
+    float4 v[NV];
+    row_load<NV, TPR>(G, x, row, N, v);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
+  }
+  cta_colsum_atomic<NV, TPR>(G, acc, N, dst, red);
+}
+
+// ---- launch helpers ------------------------------------------------------------------
+inline int row_grid(int B, int num_sms) {
+  int ctas = (B + ROW_WARPS * 4 - 1) / (ROW_WARPS * 4);      // aim at >= 4 rows per warp
+  int cap = num_sms * 4;
+  if (ctas > cap) ctas = cap;
+  return ctas < 1 ? 1 : ctas;
+}
+// dispatch on the row width: warp-per-row up to 512 columns, CTA-per-row up to 4096
+#define FB200_ROW_DISPATCH(N, CALL)                       \
+  do {                                                    \
+    if ((N) <= 128) { CALL(1, 32); }                      \
+    else if ((N) <= 256) { CALL(2, 32); }                 \
+    else if ((N) <= 512) { CALL(4, 32); }                 \
+    else if ((N) <= 1024) { CALL(1, 256); }               \
+    else if ((N) <= 2048) { CALL(2, 256); }               \
+    else { CALL(4, 256); }                                \
+  } while (0)
+inline int row_grid_for(int B, int N, int num_sms) {
+  if (N <= 512) return row_grid(B, num_sms);
+  int cap = num_sms * 8;
+  return B < cap ? (B < 1 ? 1 : B) : cap;
+}
+
+}  // namespace fb200

@@ -1,0 +1,15 @@
+"""fusion_b200 - B200-native (sm_100a) fusion head behind the reference's MultimodalModel API.
+
+    import sys; sys.path.insert(0, ".../multimodal-model-skin-lesion-classifier_b200")
+    from fusion_b200 import MultimodalModel, FusedCrossEntropyLoss
+
+or, keeping the reference's own import line (train_pad_20.py:6):
+
+    from models import multimodalIntraInterModal      # fusion_b200/compat adds this package
+"""
+from . import _lib
+from ._lib import Fb200Error
+from .head import FusedCrossEntropyLoss, FusedHeadFunction, cross_entropy, make_desc
+from .model import MultimodalModel
+
+__all__ = ["MultimodalModel", "FusedCrossEntropyLoss", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]

@@ -1,0 +1,121 @@
+"""Image / text encoder factory - STOCK PyTorch, outside the optimised path.
+
+Mirrors the interface of the reference's ``loadModels`` (loadImageModelClassifier.py:41-203):
+``loadModelImageEncoder(name, common_dim, backbone_train_mode) -> (module, cnn_dim_output)``.
+Pretrained weights are used when torchvision can find them locally; otherwise the
+architecture is built with random init (no network in the build/bench containers).
+Extra names for head-only work: ``"identity:<F>"`` (the "image" is already the [B,F] feature).
+"""
+from __future__ import annotations
+
+import torch.nn as nn
+
+_TORCHVISION = {  # name -> (factory attr, attribute replaced by Identity, feature width)
+    "resnet-18": ("resnet18", "fc", 512),
+    "resnet-50": ("resnet50", "fc", 2048),
+    "densenet169": ("densenet169", "classifier", 1664),
+    "mobilenet-v2": ("mobilenet_v2", "classifier", 1280),
+    "efficientnet-b0": ("efficientnet_b0", "classifier", 1280),
+    "efficientnet-b7": ("efficientnet_b7", "classifier", 2560),
+}
+
+
+def set_backbone_train_mode(model, mode="frozen_weights", last_n_layers=1):
+    """Same three modes (and the same ValueError) as loadImageModelClassifier.py:15-35."""
+    params = list(model.parameters())
+    for p in params:
+        p.requires_grad = False
+    if mode == "frozen_weights":
+        return
+    if mode == "unfrozen_weights":
+        for p in params:
+            p.requires_grad = True
+    elif mode == "last_layer_unfrozen_weights":
+        for p in params[-2 * last_n_layers:]:
+            p.requires_grad = True
+    else:
+        raise ValueError(f"Invalid backbone_train_mode: {mode}")
+
+
+def _tv_model(factory):
+    from torchvision import models
+    fn = getattr(models, factory)
+    try:
+        return fn(weights="DEFAULT")
+    except Exception:       # offline: same architecture, random init
+        return fn(weights=None)
+
+
+class loadModels:
+    @staticmethod
+    def loadModelImageEncoder(cnn_model_name, common_dim, backbone_train_mode="frozen", device="cpu"):
+        if cnn_model_name.startswith("identity:"):
+            return nn.Identity(), int(cnn_model_name.split(":", 1)[1])
+        if cnn_model_name in _TORCHVISION:
+            factory, head, width = _TORCHVISION[cnn_model_name]
+            model = _tv_model(factory)
+            setattr(model, head, nn.Identity())
+            if cnn_model_name == "densenet169" and backbone_train_mode == "partial":
+                for p in model.parameters():
+                    p.requires_grad = False
+                for p in model.features.denseblock4.parameters():
+                    p.requires_grad = True
+            else:
+                set_backbone_train_mode(model, backbone_train_mode, last_n_layers=1)
+            return model, width
+        if cnn_model_name == "vgg16":
+            model = _tv_model("vgg16")
+            model.classifier = nn.Sequential(*list(model.classifier.children())[:-1])
+            set_backbone_train_mode(model, backbone_train_mode, last_n_layers=1)
+            return model, 4096
+        try:
+            import timm
+        except ImportError:
+            timm = None
+        if timm is not None and cnn_model_name in timm.list_models():
+            try:
+                model = timm.create_model(cnn_model_name, pretrained=True)
+            except Exception:
+                model = timm.create_model(cnn_model_name, pretrained=False)
+            if hasattr(model, "reset_classifier"):
+                model.reset_classifier(0)
+            set_backbone_train_mode(model, backbone_train_mode)
+            return model, int(model.num_features)
+        raise ValueError(f"Backbone '{cnn_model_name}' não implementado.")
+
+    @staticmethod
+    def loadTextModelEncoder(text_model_encoder, train_mode="frozen_weights"):
+        if text_model_encoder == "tab-transformer":
+            return TabTransformer([10] * 82, num_continuous=4, output_dim=85), 85, 85
+        if text_model_encoder in ("bert-base-uncased", "gpt2"):
+            from transformers import AutoModel
+            model = AutoModel.from_pretrained(text_model_encoder)
+            for p in model.parameters():
+                p.requires_grad = train_mode == "unfrozen_weights"
+            return model, model.config.hidden_size, model.config.hidden_size
+        raise ValueError(f"Text encoder '{text_model_encoder}' não suportado.")
+
+
+class TabTransformer(nn.Module):
+    """Stock-PyTorch tabular encoder with the parameter names of tab_transformer.py:6-60
+    (82 embeddings -> 2-layer TransformerEncoder -> flatten + numeric projection -> MLP)."""
+
+    def __init__(self, categorical_cardinalities, num_continuous, embed_dim=32, num_heads=4,
+                 num_transformer_layers=2, hidden_dim=128, output_dim=1, dropout=0.3):
+        super().__init__()
+        self.embeddings = nn.ModuleList(nn.Embedding(c, embed_dim) for c in categorical_cardinalities)
+        self.num_categorical, self.embed_dim = len(categorical_cardinalities), embed_dim
+        layer = nn.TransformerEncoderLayer(d_model=embed_dim, nhead=num_heads, dim_feedforward=hidden_dim,
+                                           activation="relu", dropout=dropout, batch_first=True)
+        self.transformer_encoder = nn.TransformerEncoder(layer, num_layers=num_transformer_layers)
+        self.numeric_projection = nn.Linear(num_continuous, embed_dim) if num_continuous > 0 else None
+        width = self.num_categorical * embed_dim + (embed_dim if num_continuous > 0 else 0)
+        self.fc = nn.Sequential(nn.Linear(width, hidden_dim), nn.ReLU(), nn.Dropout(dropout), nn.Linear(hidden_dim, output_dim))
+
+    def forward(self, x_categorical, x_numerical):
+        import torch
+        tok = torch.stack([emb(x_categorical[:, i]) for i, emb in enumerate(self.embeddings)], dim=1)
+        feats = [self.transformer_encoder(tok).flatten(start_dim=1)]
+        if self.numeric_projection is not None:
+            feats.append(self.numeric_projection(x_numerical))
+        return self.fc(torch.cat(feats, dim=1))

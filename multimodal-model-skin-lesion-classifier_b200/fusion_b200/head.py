@@ -1,0 +1,167 @@
+"""Host-side driver of the fused fusion head: torch tensors in, raw pointers to libfb200.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; all arithmetic of
+the head runs in the CUDA kernels behind the C ABI (include/fb200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_desc(mechanism, B, F, V, T, D, H, Cn, n=2, text_mode=0, dtype="fp32", train=False, flags=0):
+    if isinstance(mechanism, str):
+        mid = _lib.mechanism_id(mechanism)
+        if mid < 0:
+            # same message as multimodalIntraInterModal.py:413-416
+            raise ValueError(f"Attention mechanism '{mechanism}' not implemented.")
+        mechanism = mid
+    dt = {"fp32": _lib.F32, "float32": _lib.F32, "bf16": _lib.BF16, "bfloat16": _lib.BF16}[dtype] if isinstance(dtype, str) else dtype
+    return _lib.Desc(mechanism=mechanism, B=B, F=F, V=V or 0, T=T, D=D, H=H, C=Cn, n=n, text_mode=text_mode,
+                     dtype=dt, train=1 if train else 0, flags=flags, reserved=0)
+
+
+def _check_input(t, name, cols):
+    if not t.is_cuda:
+        raise _lib.Fb200Error(-2, f"{name} must be a CUDA tensor (fusion_b200 has no CPU path)")
+    if t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] != cols:
+        raise ValueError(f"{name}: expected float32 [B,{cols}], got {t.dtype} {tuple(t.shape)}")
+    return t.contiguous()
+
+
+class ParamTable:
+    """Array of the 78 parameter pointers in slot order (NULL for absent slots)."""
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+        arr = (C.c_void_p * len(self.tensors))()
+        for i, t in enumerate(self.tensors):
+            if t is not None:
+                if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.Fb200Error(-2, "parameters must be contiguous float32 CUDA tensors")
+                arr[i] = t.data_ptr()
+        self.arr = arr
+
+
+def _mask_table(masks):
+    """masks: None or {site index or name: uint8 CUDA tensor} -> (ctypes array | NULL, keepalive)."""
+    if not masks:
+        return None, None
+    arr = (C.c_void_p * _lib.NUM_DROPOUT_SITES)()
+    keep = []
+    for k, t in masks.items():
+        idx = _lib.DROP_SITES.index(k) if isinstance(k, str) else int(k)
+        t = t.to(torch.uint8).contiguous()
+        if not t.is_cuda:
+            raise _lib.Fb200Error(-2, "dropout masks must be CUDA tensors")
+        arr[idx] = t.data_ptr()
+        keep.append(t)
+    return arr, keep
+
+
+class FusedHeadFunction(torch.autograd.Function):
+    """logits = head(img_feat, text_in; params) with a hand-written backward.
+
+    Once differentiable (Grad-CAM++ style double backward is not supported - SURVEY 8b)."""
+
+    @staticmethod
+    def forward(ctx, img_feat, text_in, cfg, masks, seed, offset, *params):
+        L = _lib.lib()
+        B = img_feat.shape[0]
+        need_dimg = bool(img_feat.requires_grad)
+        need_dtxt = bool(text_in.requires_grad)
+        flags = cfg["flags"] | (_lib.FLAG_NEED_DIMG if need_dimg else 0) | (_lib.FLAG_NEED_DTEXT if need_dtxt else 0)
+        desc = make_desc(cfg["mechanism"], B, cfg["F"], cfg["V"], cfg["T"], cfg["D"], cfg["H"], cfg["C"], cfg["n"],
+                         cfg["text_mode"], cfg["dtype"], cfg["train"], flags)
+        x = _check_input(img_feat.detach(), "img_feat", cfg["F"])
+        t = _check_input(text_in.detach(), "text_metadata", cfg["T"] if cfg["text_mode"] else cfg["V"])
+        table = ParamTable([p.detach() if p is not None else None for p in params])
+        ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=x.device)
+        logits = torch.empty(B, cfg["C"], dtype=torch.float32, device=x.device)
+        marr, mkeep = _mask_table(masks)
+        with torch.cuda.device(x.device):
+            _lib.check(L.fb200_head_forward(C.byref(desc), table.arr, _ptr(x), _ptr(t), marr, seed, offset,
+                                            _ptr(logits), _ptr(ws), _stream()), "fb200_head_forward")
+        ctx.desc, ctx.table, ctx.ws, ctx.x, ctx.t = desc, table, ws, x, t
+        ctx.marr, ctx.mkeep, ctx.seed, ctx.offset = marr, mkeep, seed, offset
+        ctx.need = (need_dimg, need_dtxt)
+        ctx.nparams = len(params)
+        return logits
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dlogits):
+        L = _lib.lib()
+        desc = ctx.desc
+        dl = dlogits.contiguous().float()
+        total, offs = _lib.grad_layout(desc)
+        flat = torch.empty(max(total, 1), dtype=torch.float32, device=dl.device)
+        d_img = torch.empty_like(ctx.x) if ctx.need[0] else None
+        d_txt = torch.empty_like(ctx.t) if ctx.need[1] else None
+        with torch.cuda.device(dl.device):
+            _lib.check(L.fb200_head_backward(C.byref(desc), ctx.table.arr, _ptr(ctx.x), _ptr(ctx.t), ctx.marr, ctx.seed, ctx.offset,
+                                             _ptr(dl), _ptr(flat), _ptr(d_img), _ptr(d_txt), _ptr(ctx.ws), _stream()),
+                       "fb200_head_backward")
+        grads = []
+        for s in range(ctx.nparams):
+            p = ctx.table.tensors[s]
+            if p is None or s not in offs:
+                grads.append(None)          # same None pattern as the reference's autograd
+            else:
+                grads.append(flat[offs[s]: offs[s] + p.numel()].view(p.shape))
+        ctx.ws = None
+        return (d_img, d_txt, None, None, None, None, *grads)
+
+
+def cross_entropy(logits, labels, class_w=None, denom=None, want_grad=True):
+    """Fused weighted CE through the C ABI.  Returns (loss_out[3] = loss, numerator, weight sum; dlogits)."""
+    L = _lib.lib()
+    if not logits.is_cuda:
+        raise _lib.Fb200Error(-2, "logits must be a CUDA tensor")
+    z = logits.detach().contiguous().float()
+    y = labels.to(device=z.device, dtype=torch.int64).contiguous()
+    w = None if class_w is None else class_w.to(device=z.device, dtype=torch.float32).contiguous()
+    out = torch.empty(3, dtype=torch.float32, device=z.device)
+    dl = torch.empty_like(z) if want_grad else None
+    with torch.cuda.device(z.device):
+        _lib.check(L.fb200_cross_entropy(_ptr(z), _ptr(y), _ptr(w), _ptr(denom), z.shape[0], z.shape[1], _ptr(out), _ptr(dl), _stream()),
+                   "fb200_cross_entropy")
+    return out, dl
+
+
+class _FusedCEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, class_w, denom):
+        out, dl = cross_entropy(logits, labels, class_w, denom, want_grad=True)
+        ctx.save_for_backward(dl)
+        return out[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dloss):
+        (dl,) = ctx.saved_tensors
+        return dl * dloss, None, None, None
+
+
+class FusedCrossEntropyLoss(torch.nn.Module):
+    """Drop-in for ``nn.CrossEntropyLoss(weight=class_weights)`` (train_pad_20.py:52):
+    same ``criterion(outputs, label)`` call, weighted-mean reduction, one fused kernel pair.
+    ``denom`` (device scalar) replaces this batch's weight sum by the global one under DP."""
+
+    def __init__(self, weight=None):
+        super().__init__()
+        self.register_buffer("weight", None if weight is None else weight.detach().clone().float())
+
+    def forward(self, logits, labels, denom=None):
+        return _FusedCEFunction.apply(logits, labels, self.weight, denom)

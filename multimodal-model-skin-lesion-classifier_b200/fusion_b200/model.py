@@ -1,0 +1,199 @@
+"""Drop-in ``MultimodalModel`` whose fusion head runs in libfb200 (sm_100a CUDA).
+
+Same constructor, parameter names / shapes / initialisation, fusion strings and
+``forward(image, text_metadata) -> logits`` as the reference class
+(src/scripts/benchmark/models/multimodalIntraInterModal.py:13-416), so the
+train_pad_20 / train_isic_2019 / train_isic_2020 loops, ``state_dict`` checkpoints
+(api.py:117 loads strictly) and ``.image_encoder`` users keep working.  The torch.nn
+sub-modules created here are PARAMETER CONTAINERS ONLY - their ``forward`` is never
+called; ``forward`` hands raw device pointers of their weights to the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .backbones import loadModels
+from .head import FusedHeadFunction, ParamTable, _check_input, _mask_table, _ptr, _stream, make_desc
+
+RG_ATT = "att-intramodal+residual+cross-attention-metadados"
+
+
+def _mlp_container(first_in, dim, num_classes, p):
+    # index layout 0 Linear, 1 LayerNorm, 2 ReLU, 3 Dropout, 4 Linear, 5 LayerNorm, 6 ReLU, 7 Dropout, 8 Linear
+    widths = [(first_in, dim), (dim, dim // 2)]
+    mods = []
+    for i, o in widths:
+        mods += [nn.Linear(i, o), nn.LayerNorm(o), nn.ReLU(), nn.Dropout(p)]
+    mods.append(nn.Linear(dim // 2, num_classes))
+    return nn.Sequential(*mods)
+
+
+class _GatedResidualParams(nn.Module):
+    """Parameters of GatedAlteredResidualBlock (gatedResidualBlock.py:4-10), same names."""
+
+    def __init__(self, dim, dropout=0.1):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        self.attn = nn.MultiheadAttention(embed_dim=dim, num_heads=8, batch_first=False)
+        self.dropout = nn.Dropout(dropout)
+        self.gate_linear = nn.Linear(dim, dim)
+
+
+class _MetaBlockParams(nn.Module):
+    """Parameters of MetaBlock(V_dim, U_dim) (metablock.py:9-20), same names."""
+
+    def __init__(self, v_dim, u_dim):
+        super().__init__()
+        self.fb = nn.Sequential(nn.Linear(u_dim, v_dim), nn.LayerNorm(v_dim))
+        self.gb = nn.Sequential(nn.Linear(u_dim, v_dim), nn.LayerNorm(v_dim))
+
+
+class MultimodalModel(nn.Module):
+    def __init__(self, num_classes, num_heads, device, cnn_model_name, text_model_name, batch_size=32,
+                 common_dim=512, text_encoder_dim_output=512, vocab_size=91, unfreeze_weights="frozen_weights",
+                 attention_mecanism="concatenation", n=2, compute_dtype="fp32", engine_flags=0):
+        super().__init__()
+        self.device = device
+        self.common_dim, self.num_heads, self.n = common_dim, num_heads, n
+        self.attention_mecanism = attention_mecanism
+        self.vocab_size, self.num_classes = vocab_size, num_classes
+        self.cnn_model_name, self.text_model_name = cnn_model_name, text_model_name
+        self.unfreeze_weights = unfreeze_weights
+        self.text_encoder_dim_output = text_encoder_dim_output
+        self.compute_dtype, self.engine_flags = compute_dtype, engine_flags
+        D = common_dim
+
+        # creation order == reference order, so torch.manual_seed(k) gives identical initial weights
+        self.image_encoder, self.cnn_dim_output = loadModels.loadModelImageEncoder(
+            cnn_model_name=cnn_model_name, common_dim=D, backbone_train_mode=unfreeze_weights)
+        self.image_projector = nn.Linear(self.cnn_dim_output, D)
+        if text_model_name == "one-hot-encoder":
+            self.text_fc = nn.Sequential(nn.Linear(vocab_size, 256), nn.ReLU(), nn.Linear(256, 512), nn.ReLU(),
+                                         nn.Linear(512, self.text_encoder_dim_output))
+            self.text_encoder = None
+        else:
+            self.text_encoder, self.text_encoder_dim_output, _ = loadModels.loadTextModelEncoder(
+                text_model_encoder=text_model_name, train_mode=unfreeze_weights)
+            self.text_fc = None
+        self.text_projector = nn.Linear(self.text_encoder_dim_output, D)
+        for name in ("image_self_attention", "text_self_attention", "image_cross_attention", "text_cross_attention"):
+            setattr(self, name, nn.MultiheadAttention(embed_dim=D, num_heads=num_heads, batch_first=False))
+        self.img_gate = nn.Linear(D, D)
+        self.txt_gate = nn.Linear(D, D)
+        mb_common = attention_mecanism == RG_ATT + "+metablock"
+        self.meta_block = _MetaBlockParams(
+            v_dim=D if mb_common else self.cnn_dim_output,
+            u_dim=D if attention_mecanism in (RG_ATT + "+metablock", "metablock-se") else self.text_encoder_dim_output)
+        self.image_residual = _GatedResidualParams(D)
+        self.text_residual = _GatedResidualParams(D)
+        self.fc_fusion = _mlp_container(D * (1 if attention_mecanism == "no-metadata" else n), D, num_classes, 0.5)
+        self.fc_visual_only = nn.Linear(self.cnn_dim_output, num_classes)
+        self.fc_fusion_proj_feat2output = nn.Linear(D, num_classes)
+        self.fc_mlp_module_after_metablock_fusion_module = _mlp_container(self.cnn_dim_output, D, num_classes, 0.3)
+
+        self._slot_names = _lib.param_names()
+        self._step = 0                       # Philox offset: advances once per training forward
+        self._injected_masks = None          # tests: {site: uint8 keep-mask}
+
+    # ------------------------------------------------------------------ plumbing
+    def _cfg(self, train):
+        return dict(mechanism=self.attention_mecanism, F=self.cnn_dim_output,
+                    V=self.vocab_size if self.text_model_name == "one-hot-encoder" else 0,
+                    T=self.text_encoder_dim_output, D=self.common_dim, H=self.num_heads, C=self.num_classes, n=self.n,
+                    text_mode=0 if self.text_model_name == "one-hot-encoder" else 1,
+                    dtype=self.compute_dtype, train=train, flags=self.engine_flags)
+
+    def _params_in_slot_order(self):
+        named = dict(self.named_parameters())
+        return [named.get(k) for k in self._slot_names]
+
+    def inject_dropout_masks(self, masks):
+        """Parity tests: use explicit {0,1} keep-masks instead of the in-kernel Philox stream."""
+        self._injected_masks = masks
+
+    def _encode(self, image, text_metadata):
+        image = image.to(self.device)
+        img_feat = self.image_encoder(image)
+        if img_feat.dim() == 4:
+            img_feat = img_feat.mean(dim=(-2, -1))
+        if self.text_model_name == "one-hot-encoder":
+            text_in = text_metadata.to(self.device)
+        elif isinstance(text_metadata, torch.Tensor):
+            text_in = text_metadata.to(self.device)                      # pre-computed encoder features [B,T]
+        elif isinstance(text_metadata, (tuple, list)):
+            text_in = self.text_encoder(*[t.to(self.device) for t in text_metadata])   # TabTransformer(x_cat, x_num)
+        else:                                                            # HF tokenizer dict (reference :180-183)
+            ids = text_metadata["input_ids"].squeeze(1).to(self.device)
+            att = text_metadata["attention_mask"].squeeze(1).to(self.device)
+            text_in = self.text_encoder(input_ids=ids, attention_mask=att).last_hidden_state[:, 0, :]
+        return img_feat.float(), text_in.float()
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, image, text_metadata):
+        if _lib.mechanism_id(self.attention_mecanism) < 0:
+            raise ValueError(f"Attention mechanism '{self.attention_mecanism}' not implemented.")
+        img_feat, text_in = self._encode(image, text_metadata)
+        train = bool(self.training)
+        if train:
+            self._step += 1
+        return FusedHeadFunction.apply(img_feat, text_in, self._cfg(train), self._injected_masks,
+                                       torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, self._step,
+                                       *self._params_in_slot_order())
+
+    # ------------------------------------------------------------------ fused train step (opt-in)
+    def forward_loss(self, image, text_metadata, label, class_weights=None, denom=None, zero_grad=True):
+        """forward + weighted CE + backward of the head in ONE library call.
+
+        Writes ``.grad`` of every live head parameter (views of one flat buffer, summed into
+        existing grads unless ``zero_grad``), back-propagates into the backbone when it has
+        trainable parameters, and returns (loss, logits) as device tensors without syncing.
+        ``denom``: device scalar with the global sum of class weights (data parallel runs)."""
+        L = _lib.lib()
+        img_feat, text_in = self._encode(image, text_metadata)
+        train = bool(self.training)
+        if train:
+            self._step += 1
+        need_dimg, need_dtxt = bool(img_feat.requires_grad), bool(text_in.requires_grad)
+        cfg = self._cfg(train)
+        flags = cfg["flags"] | (_lib.FLAG_NEED_DIMG if need_dimg else 0) | (_lib.FLAG_NEED_DTEXT if need_dtxt else 0)
+        B = img_feat.shape[0]
+        desc = make_desc(cfg["mechanism"], B, cfg["F"], cfg["V"], cfg["T"], cfg["D"], cfg["H"], cfg["C"], cfg["n"],
+                         cfg["text_mode"], cfg["dtype"], train, flags)
+        x = _check_input(img_feat.detach(), "img_feat", cfg["F"])
+        t = _check_input(text_in.detach(), "text_metadata", cfg["T"] if cfg["text_mode"] else cfg["V"])
+        params = self._params_in_slot_order()
+        table = ParamTable([p.detach() if p is not None else None for p in params])
+        dev = x.device
+        ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
+        total, offs = _lib.grad_layout(desc)
+        flat = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+        logits = torch.empty(B, cfg["C"], dtype=torch.float32, device=dev)
+        loss_out = torch.empty(3, dtype=torch.float32, device=dev)
+        d_img = torch.empty_like(x) if need_dimg else None
+        d_txt = torch.empty_like(t) if need_dtxt else None
+        y = label.to(device=dev, dtype=torch.int64).contiguous()
+        w = None if class_weights is None else class_weights.to(device=dev, dtype=torch.float32).contiguous()
+        marr, _keep = _mask_table(self._injected_masks)
+        with torch.cuda.device(dev):
+            _lib.check(L.fb200_head_train_step(C.byref(desc), table.arr, _ptr(x), _ptr(t), _ptr(y), _ptr(w), _ptr(denom), marr,
+                                               torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, self._step,
+                                               _ptr(logits), _ptr(loss_out), _ptr(flat), _ptr(d_img), _ptr(d_txt), _ptr(ws), _stream()),
+                       "fb200_head_train_step")
+        for s, p in enumerate(params):
+            if p is None or s not in offs or not p.requires_grad:
+                continue
+            g = flat[offs[s]: offs[s] + p.numel()].view(p.shape)
+            if p.grad is None or zero_grad:
+                p.grad = g
+            else:
+                p.grad = p.grad + g
+        self.flat_grad = flat                # one contiguous bucket for the DP all-reduce
+        if need_dimg:
+            img_feat.backward(d_img)
+        if need_dtxt:
+            text_in.backward(d_txt)
+        return loss_out[0], logits

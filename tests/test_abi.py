@@ -1,0 +1,117 @@
+"""CPU: the C-ABI library loads, exports every symbol include/fb200.h declares, and its
+host-side introspection (slots, shapes, gradient liveness, dropout sites, work model) agrees
+with the oracle and with the reference's None/zero gradient pattern stored in the goldens.
+No compute entry point is called here (no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from fusion_b200 import _lib, make_desc
+from oracle import head_oracle as ho
+from tests import parity
+from tests.golden import cases as C
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(fb200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 15
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"libfb200.so does not export {n}"
+    assert _lib.lib().fb200_version() == 100
+
+
+def test_strerror_and_mechanism_strings():
+    L = _lib.lib()
+    for i, m in enumerate(ho.MECHANISMS):
+        assert L.fb200_mechanism_from_string(m.encode()) == i
+        assert L.fb200_mechanism_string(i).decode() == m
+    assert L.fb200_mechanism_from_string(b"metablock-se") == -1        # referenced at :114 but never implemented
+    assert b"no CPU path" in L.fb200_strerror(-2)
+
+
+@pytest.mark.parametrize("mech", ho.MECHANISMS)
+def test_slots_match_oracle_shapes(mech):
+    cfg = ho.HeadConfig(mech, F=2048, C=6, V=85)
+    d = make_desc(mech, 32, 2048, 85, 512, 512, 8, 6)
+    shapes = cfg.param_shapes()
+    names = _lib.param_names()
+    assert names == list(shapes.keys())
+    for i, k in enumerate(names):
+        assert _lib.param_shape(d, i) == tuple(shapes[k]), k
+
+
+def test_text_mode1_has_no_text_fc():
+    d = make_desc("gfcam", 8, 768, 0, 85, 512, 8, 2, text_mode=1)
+    names = _lib.param_names()
+    for i, k in enumerate(names):
+        shp = _lib.param_shape(d, i)
+        assert (shp is None) == k.startswith("text_fc."), k
+    assert _lib.param_shape(d, names.index("text_projector.weight")) == (512, 85)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in C.all_cases() if n.startswith("small") or n.endswith("_eval")))
+def test_gradient_liveness_matches_reference(name):
+    """fb200_grad_offset >= 0 exactly for the parameters whose .grad is a tensor in the reference."""
+    case = C.all_cases()[name]
+    kw = case["cfg"]
+    g = parity.load_golden(name)
+    d = make_desc(kw["mechanism"], case["B"], kw["F"], kw.get("V") or 0, kw.get("T", 512), kw.get("D", 512), kw.get("H", 8), kw["C"],
+                  text_mode=0 if kw.get("text_model", "one-hot-encoder") == "one-hot-encoder" else 1)
+    total, offs = _lib.grad_layout(d)
+    names = _lib.param_names()
+    live = {names[s] for s in offs}
+    assert live == set(g["grad_names"].tolist())
+    assert not (live & set(g["none_grads"].tolist()))
+    # offsets are 16-byte aligned, disjoint and inside the flat buffer
+    spans = sorted((o, int(np.prod(_lib.param_shape(d, s)))) for s, o in offs.items())
+    for (o, n), (o2, _) in zip(spans, spans[1:] + [(total, 0)]):
+        assert o % 4 == 0 and o + n <= o2
+
+
+def test_work_model_matches_survey_table():
+    """live params and algorithmic FLOPs/bytes of the BASELINE configs."""
+    rows = {  # mechanism, F, V, C, T, text_mode -> live params (M), bytes (MB)
+        "cfg1": (("concatenation", 512, 85, 6, 512, 0), 1.601e6, 19.4e6),
+        "cfg2": (("crossattention", 2048, 85, 6, 512, 0), 4.488e6, 54.4e6),
+        "cfg3a": (("metablock", 1664, 13, 8, 512, 0), 3.099e6, 37.6e6),
+        "cfg3b": (("weighted", 1664, 13, 8, 512, 0), 2.698e6, 32.8e6),
+        "cfg5": ((ho.RG_ATT, 1024, 85, 6, 512, 0), 5.542e6, None),
+    }
+    for k, ((m, F, V, Cn, T, tm), plive, nbytes) in rows.items():
+        d = make_desc(m, 32, F, V, T, 512, 8, Cn, text_mode=tm, flags=_lib.FLAG_NEED_DIMG)
+        flops, b, p = _lib.algorithmic_work(d)
+        assert abs(p - plive) / plive < 2e-3, (k, p)
+        if nbytes:
+            assert abs(b - nbytes) / nbytes < 1e-2, (k, b)
+        assert abs(flops - 6 * 32 * p) / flops < 0.03, (k, flops)    # 6*B*MAC_live minus the text_fc.0 dX
+
+
+def test_bad_descriptors_are_rejected():
+    L = _lib.lib()
+    n = ctypes.c_size_t()
+    d = make_desc("crossattention", 32, 2048, 85, 512, 512, 7, 6)          # D % H != 0 -> like nn.MultiheadAttention's assert
+    assert L.fb200_workspace_bytes(ctypes.byref(d), ctypes.byref(n)) == -1
+    d = make_desc("crossattention", 0, 2048, 85, 512, 512, 8, 6)
+    assert L.fb200_workspace_bytes(ctypes.byref(d), ctypes.byref(n)) == -1
+    d = make_desc("crossattention", 32, 2048, 85, 512, 512, 8, 6, n=1)
+    assert L.fb200_workspace_bytes(ctypes.byref(d), ctypes.byref(n)) == -1
+    with pytest.raises(ValueError, match="not implemented"):
+        make_desc("metablock-se", 32, 2048, 85, 512, 512, 8, 6)
+
+
+def test_dropout_sites():
+    d = make_desc(ho.RG_ATT, 16, 1024, 85, 512, 512, 8, 6, train=True)
+    s = _lib.dropout_sites(d)
+    assert s == {0: (pytest.approx(0.1), 16, 512), 1: (pytest.approx(0.1), 16, 512),
+                 4: (pytest.approx(0.5), 16, 512), 5: (pytest.approx(0.5), 16, 256)}
+    d = make_desc("metablock", 16, 1664, 13, 512, 512, 8, 8, train=True)
+    s = _lib.dropout_sites(d)
+    assert set(s) == {4, 5} and abs(s[4][0] - 0.3) < 1e-7

@@ -1,0 +1,113 @@
+"""GPU: the CUDA path (through the drop-in model -> ctypes -> C ABI) against the golden
+fixtures generated from the unmodified reference, and against the numpy oracle on fresh
+seeded inputs.  fp32: 1e-5 relative; bf16: 2e-2 relative; identical argmax (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import fusion_b200 as fb
+from fusion_b200 import _lib
+from oracle import head_oracle as ho
+from tests import parity
+from tests.golden import cases as C
+from tests.gpu_util import build_model, case_inputs, run_autograd, run_fused
+
+pytestmark = pytest.mark.gpu
+CASES = C.all_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fp32_matches_reference_golden(name):
+    case = CASES[name]
+    cfg, model = build_model(case, "fp32")
+    logits, loss, grads, dx = run_autograd(model, cfg, case)
+    worst = parity.check_against_golden(name, case, logits, loss, grads, dx, tol=parity.FP32_TOL)
+    print(f"{name}: worst rel err {worst:.2e}")
+    # W_q / W_k rows: materialised exact zeros, like autograd
+    for k, g in grads.items():
+        if g is not None and k.endswith("in_proj_weight"):
+            assert (g[: 2 * cfg.D] == 0).all(), k
+        if g is not None and k.endswith("in_proj_bias"):
+            assert (g[: 2 * cfg.D] == 0).all(), k
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith("cfg")])
+def test_bf16_matches_reference_golden(name):
+    case = CASES[name]
+    cfg, model = build_model(case, "bf16")
+    logits, loss, grads, dx = run_autograd(model, cfg, case)
+    worst = parity.check_against_golden(name, case, logits, loss, grads, dx, tol=parity.BF16_TOL)
+    print(f"{name}: worst rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("name", ["cfg2_cross_train", "cfg3a_meta_train", "cfg5_rgatt_train", "small14_train", "small16_train"])
+def test_fused_train_step_equals_autograd_path(name):
+    case = CASES[name]
+    cfg, model = build_model(case, "fp32")
+    l1, loss1, g1, _ = run_autograd(model, cfg, case)
+    l2, loss2, g2 = run_fused(model, cfg, case)
+    assert parity.rel_err(l2, l1) < 1e-6 and abs(loss1 - loss2) < 1e-6 * abs(loss1)
+    for k in g1:
+        if g1[k] is None:
+            assert g2[k] is None, k
+        else:
+            assert parity.rel_err(g2[k], g1[k]) < 2e-6, k       # atomics reorder the split-K sums
+
+
+@pytest.mark.parametrize("mech,F,V,Cn,B", [("crossattention", 2048, 85, 6, 257), ("metablock", 1664, 13, 8, 130),
+                                            (ho.RG_ATT, 1024, 85, 6, 1024), ("gfcam", 768, 11, 2, 96)])
+def test_fp32_against_oracle_on_fresh_inputs(mech, F, V, Cn, B):
+    """Bigger / ragged batches than the fixtures: oracle (float64) on the same seeded inputs."""
+    kw = dict(mechanism=mech, F=F, V=V, C=Cn)
+    case = dict(cfg=kw, B=B, seed=4242 + B, train=True, full_grads=False)
+    cfg, model = build_model(case, "fp32")
+    logits, loss, grads, dx = run_autograd(model, cfg, case)
+    params = C.gen_params(cfg, case["seed"], np.float64)
+    x, tin, labels, cw, masks = C.gen_inputs(cfg, B, case["seed"], True, np.float64)
+    o = ho.head_forward_backward(cfg, params, x, tin, labels, cw, masks, need_input_grad=True)
+    assert parity.rel_err(logits, o["logits"]) < parity.FP32_TOL
+    assert abs(loss - o["loss"]) < parity.FP32_TOL * abs(o["loss"])
+    for k, g in o["grads"].items():
+        if g is None:
+            assert grads[k] is None, k
+        else:
+            assert parity.rel_err(grads[k], g) < parity.FP32_TOL, k
+    if o["d_img_feat"] is not None:
+        assert parity.rel_err(dx, o["d_img_feat"]) < parity.FP32_TOL
+
+
+def test_eval_mode_is_deterministic_and_philox_dropout_is_unbiased():
+    case = dict(cfg=dict(mechanism="crossattention", F=512, V=85, C=6), B=64, seed=5, train=False, full_grads=False)
+    cfg, model = build_model(case, "fp32")
+    x, tin, y, cw, _ = case_inputs(cfg, case)
+    model.eval()
+    with torch.no_grad():
+        a = model(x, tin); b = model(x, tin)
+    assert torch.equal(a, b)
+    model.train()
+    outs = []
+    with torch.no_grad():
+        for _ in range(2):
+            outs.append(model(x, tin))
+    assert not torch.equal(outs[0], outs[1])                 # Philox offset advances per step
+    # keep-rate of the in-kernel Philox mask ~ 1 - p
+    L = _lib.lib()
+    import ctypes as Ct
+    n = 512
+    xx = torch.ones(2048, n, device="cuda"); g = torch.ones(n, device="cuda"); bb = torch.ones(n, device="cuda")
+    yy = torch.empty_like(xx); st = torch.empty(2048, 2, device="cuda")
+    xx += torch.arange(n, device="cuda").float() * 1e-3        # non-constant rows so LN is defined
+    _lib.check(L.fb200_ln_relu_dropout_fwd(Ct.c_void_p(xx.data_ptr()), Ct.c_void_p(g.data_ptr()), Ct.c_void_p(bb.data_ptr()), None,
+                                           Ct.c_float(0.5), 1, 1234, 1, 4, 2048, n, Ct.c_void_p(yy.data_ptr()), Ct.c_void_p(st.data_ptr()), None))
+    torch.cuda.synchronize()
+    # LN(x)*1+1 > 0 for roughly the upper ~84% of columns; among positive pre-dropout values half survive
+    pre = torch.nn.functional.layer_norm(xx, (n,), g, bb).clamp_min(0)
+    kept = ((yy > 0).sum().item()) / max((pre > 0).sum().item(), 1)
+    assert abs(kept - 0.5) < 0.01, kept
+
+
+def test_cpu_tensors_are_refused_on_gpu_box_too():
+    case = dict(cfg=dict(mechanism="concatenation", F=512, V=85, C=6), B=4, seed=5, train=False, full_grads=False)
+    cfg, model = build_model(case, "fp32")
+    with pytest.raises(fb.Fb200Error):
+        fb.cross_entropy(torch.zeros(4, 6), torch.zeros(4, dtype=torch.long))
