@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py - fusion-head train samples/sec (forward + weighted CE + backward) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): ResNet-50 feature width F=2048, one-hot
+PAD-UFES-20 metadata V=85, fusion "crossattention" (8 heads, COMMON_DIM=512), 6 classes,
+fp32, random-init weights under torch.manual_seed(1234), synthetic N(0,1) inputs under
+torch.manual_seed(4321+rank).  One step = one pass of the hot path over one batch of
+--batch samples per GPU (weak scaling: per-GPU batch fixed; gradients all-reduced by NCCL).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "multimodal-model-skin-lesion-classifier_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: mechanism, F, V, C, T, text_mode, dtype
+    "cfg1": ("concatenation", 512, 85, 6, 512, 0, "fp32"),
+    "cfg2": ("crossattention", 2048, 85, 6, 512, 0, "fp32"),
+    "cfg3a": ("metablock", 1664, 13, 8, 512, 0, "fp32"),
+    "cfg3b": ("weighted", 1664, 13, 8, 512, 0, "fp32"),
+    "cfg4a": ("gfcam", 768, 0, 2, 85, 1, "bf16"),
+    "cfg4b": ("att-intramodal+residual+cross-attention-metadados", 768, 0, 2, 85, 1, "bf16"),
+    "cfg5": ("att-intramodal+residual+cross-attention-metadados", 1024, 85, 6, 512, 0, "bf16"),
+}
+WORKLOAD_DESC = {
+    "cfg2": "ResNet-50 (F=2048) + one-hot metadata (V=85) + crossattention (8 heads, COMMON_DIM=512), PAD-UFES-20 synthetic (6 classes)",
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
+    ap.add_argument("--dtype", default=None, choices=[None, "fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", default="", help="comma-separated extra per-GPU batch sizes reported under 'sweep'")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                smax = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def reference_arm(args, wl):
+    """The reference's own CPU implementation of the path (torch.nn on the host cores)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle.torch_port import time_cpu_train_step
+    mech, F, V, Cn, T, tm, dtype = wl
+    threads = os.cpu_count() or 1
+    B = args.batch
+    r = time_cpu_train_step(mech, F, V, Cn, B, T=T, one_hot=(tm == 0), steps=max(args.steps, 2), warmup=max(min(args.warmup, 3), 1),
+                            threads=threads, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": "fusion-head train samples/sec (fwd+bwd)", "value": r["samples_per_s"], "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "per_gpu_batch": B, "mechanism": mech,
+                   "note": "reference torch.nn CPU path (oracle/torch_port.py: same modules, same dead work as the reference forward) on the host cores"},
+        "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
+                         "sample": f"{r['steps']} train steps of batch {B} (median)"},
+        "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- b200 arm
+def main():
+    args = parse()
+    wl = list(WORKLOADS[args.workload])
+    if args.dtype:
+        wl[6] = args.dtype
+    if args.impl == "reference":
+        return reference_arm(args, wl)
+
+    import torch
+    import torch.distributed as dist
+    import fusion_b200 as fb
+    from fusion_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mech, F, V, Cn, T, tm, dtype = wl
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    def build(Bsz):
+        torch.manual_seed(1234)
+        model = fb.MultimodalModel(Cn, 8, dev, f"identity:{F}", "one-hot-encoder" if tm == 0 else "tab-transformer",
+                                   vocab_size=V if V else 91, text_encoder_dim_output=T, attention_mecanism=mech, compute_dtype=dtype).to(dev)
+        model.train()
+        return model
+
+    def make_pool(Bsz, nbatch, pinned=False):
+        g = torch.Generator().manual_seed(4321 + rank)
+        xs, ts, ys = [], [], []
+        for _ in range(nbatch):
+            x = torch.randn(Bsz, F, generator=g); t = torch.randn(Bsz, V if tm == 0 else T, generator=g)
+            y = torch.randint(0, Cn, (Bsz,), generator=g)
+            if pinned:
+                xs.append(x.pin_memory()); ts.append(t.pin_memory()); ys.append(y.pin_memory())
+            else:
+                xs.append(x.to(dev)); ts.append(t.to(dev)); ys.append(y.to(dev))
+        return xs, ts, ys
+
+    def class_weights(ys):
+        y = torch.cat([v.cpu() for v in ys])
+        counts = torch.bincount(y, minlength=Cn).clamp_min(1).float()
+        return (y.numel() / (Cn * counts)).to(dev)
+
+    def run_config(Bsz, steps, warm, sample_clocks=False):
+        model = build(Bsz)
+        in_bytes = Bsz * (F + (V if tm == 0 else T)) * 4
+        nb = max(2, min(16, int(160e6 // in_bytes) + 1))        # pool > 126 MB L2 where affordable
+        xs, ts, ys = make_pool(Bsz, nb)
+        cw = class_weights(ys)
+
+        def step(i):
+            j = i % nb
+            denom = None
+            if world > 1:                                        # global weighted-CE denominator
+                denom = cw[ys[j]].sum().reshape(1)
+                dist.all_reduce(denom)
+            loss, _ = model.forward_loss(xs[j], ts[j], ys[j], cw, denom=denom)
+            if world > 1:
+                dist.all_reduce(model.flat_grad)                 # summed: the global denominator already averages
+            return loss
+
+        for i in range(warm):
+            step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start(); time.sleep(0.25)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        e0.record()
+        for i in range(steps):
+            loss = step(warm + i)
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop(t0, t1) if sampler else None
+        return model, ms.item() / steps, clocks, float(loss), (nb, in_bytes)
+
+    # ---- headline: inputs resident in HBM
+    model, ms_step, clocks, last_loss, (nb, in_bytes) = run_config(B, K, W, sample_clocks=True)
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (H2D inside the timed region, loss read back)
+    def run_e2e(Bsz, steps, warm):
+        m2 = build(Bsz)
+        nbh = 4
+        hx, ht, hy = make_pool(Bsz, nbh, pinned=True)
+        cw = class_weights(hy)
+        copy_stream = torch.cuda.Stream(device=dev)
+        slots = [dict(x=torch.empty(Bsz, F, device=dev), t=torch.empty(Bsz, ht[0].shape[1], device=dev),
+                      y=torch.empty(Bsz, dtype=torch.int64, device=dev), ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        host_loss = torch.empty(steps + warm, dtype=torch.float32).pin_memory()
+
+        def prefetch(i):
+            s = slots[i % 2]; j = i % nbh
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(s["free"])
+                s["x"].copy_(hx[j], non_blocking=True); s["t"].copy_(ht[j], non_blocking=True); s["y"].copy_(hy[j], non_blocking=True)
+                s["ready"].record(copy_stream)
+
+        def run(n, base):
+            cur = torch.cuda.current_stream()
+            prefetch(base)
+            for i in range(base, base + n):
+                if i + 1 < base + n:
+                    prefetch(i + 1)
+                s = slots[i % 2]
+                cur.wait_event(s["ready"])
+                denom = None
+                if world > 1:
+                    denom = cw[s["y"]].sum().reshape(1); dist.all_reduce(denom)
+                loss, _ = m2.forward_loss(s["x"], s["t"], s["y"], cw, denom=denom)
+                if world > 1:
+                    dist.all_reduce(m2.flat_grad)
+                host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)       # D2H read of the step's result
+                s["free"].record(cur)
+        for s in slots:
+            s["free"].record(torch.cuda.current_stream())
+        run(warm, 0)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        run(steps, warm)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dtt = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(dtt, op=dist.ReduceOp.MAX)
+        h2d = Bsz * (F + ht[0].shape[1]) * 4 + Bsz * 8
+        return Bsz * world * steps / dtt.item(), h2d, 4
+
+    e2e_value, h2d, d2h = run_e2e(B, K, W)
+
+    # ---- roofline of the dominant kernel (the GEMM), replayed live through the C ABI with CUDA events
+    desc = fb.make_desc(mech, B, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype, train=True)
+    flops, nbytes, plive = _lib.algorithmic_work(desc)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roof = dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype)
+    t_roof_ms = max(flops / (roof["step_peak_tflops"] * 1e12), nbytes / (roof["hbm_gbs"] * 1e9)) * 1e3
+    roof["step"] = {"algorithmic_flops": flops, "algorithmic_bytes": nbytes, "t_roof_ms": t_roof_ms, "frac": t_roof_ms / ms_step}
+
+    fwd_l, bwd_l = _lib.launch_count(desc)
+    launches = K * (fwd_l + bwd_l + 2)
+
+    sweep = {}
+    for bs in [int(v) for v in args.sweep.split(",") if v]:
+        _, ms_b, _, _, _ = run_config(bs, max(10, K // 2), W)
+        sweep[str(bs)] = {"ms_per_step": ms_b, "samples_per_s": bs * world / (ms_b * 1e-3)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.torch_port import time_cpu_train_step
+        r = time_cpu_train_step(mech, F, V, Cn, B, T=T, one_hot=(tm == 0), steps=6, warmup=2, threads=os.cpu_count(), budget_s=25.0)
+        cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
+               "sample": f"{r['steps']} train steps of batch {B} on the reference torch.nn CPU path (median), {r['ms_per_step']:.1f} ms/step"}
+
+    if rank == 0:
+        line = {
+            "metric": "fusion-head train samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if dtype == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "mechanism": mech, "per_gpu_batch": B, "global_batch": B * world,
+                       "F": F, "V": V, "C": Cn, "D": 512, "heads": 8, "parallelism": f"dp{world}",
+                       "l2": f"inputs rotate over a pool of {nb} batches = {nb * in_bytes / 1e6:.0f} MB (> 126 MB L2 when >= 127); weights ({plive * 4 / 1e6:.1f} MB) stay L2-resident by design"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss": last_loss, "sweep": sweep or None,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype):
+    """Times every GEMM launch shape of one train step (forward NT, dX NN, dW TN of each Linear)
+    through fb200_gemm - the same kernels the step launches - with CUDA events on the launch
+    stream, and reports algorithmic FLOPs / measured time for the GEMM kernel family."""
+    L = _lib.lib()
+    n = C.c_int(0)
+    cap = 256
+    arr = (C.c_int32 * (cap * 5))()
+    L.fb200_list_gemms.restype = C.c_int
+    L.fb200_list_gemms.argtypes = [C.POINTER(_lib.Desc), C.POINTER(C.c_int32), C.c_int]
+    cnt = L.fb200_list_gemms(C.byref(desc), arr, cap)
+    shapes = {}
+    for i in range(cnt):
+        key = tuple(arr[i * 5 + j] for j in range(5))           # layout, engine, M, N, K
+        shapes[key] = shapes.get(key, 0) + 1
+    stream = torch.cuda.current_stream()
+    tot_flops, tot_ms, per = 0.0, 0.0, []
+    engine_names = {0: "simt_fp32_ffma", 1: "tcgen05_3xtf32", 2: "tcgen05_bf16"}
+    for (layout, engine, M, N, Kd), count in shapes.items():
+        a_shape = (Kd, M) if layout == 2 else (M, Kd)
+        b_shape = (N, Kd) if layout == 0 else (Kd, N)
+        A = torch.randn(*a_shape, device=dev); Bm = torch.randn(*b_shape, device=dev); Cm = torch.empty(M, N, device=dev)
+        wsz = C.c_size_t(0)
+        L.fb200_gemm_workspace_bytes(layout, engine, M, N, Kd, C.byref(wsz))
+        ws = torch.empty(max(wsz.value, 256), dtype=torch.uint8, device=dev)
+
+        def call():
+            _lib.check(L.fb200_gemm(layout, engine, M, N, Kd, A.data_ptr(), a_shape[1], Bm.data_ptr(), b_shape[1], Cm.data_ptr(), N,
+                                    None, 0, 0, ws.data_ptr(), ws.numel(), stream.cuda_stream), "fb200_gemm")
+        for _ in range(3):
+            call()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            call()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        fl = 2.0 * M * N * Kd
+        tot_flops += fl * count; tot_ms += ms * count
+        per.append({"layout": "NT NN TN".split()[layout], "engine": engine_names[engine], "M": M, "N": N, "K": Kd, "launches_per_step": count,
+                    "us": ms * 1e3, "tflops": fl / (ms * 1e-3) / 1e12})
+    per.sort(key=lambda r: -r["us"] * r["launches_per_step"])
+    achieved = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    if dtype == "fp32":
+        # fp32-strict GEMMs: FFMA pipe peak = 148 SMs x 128 lanes x 2 flop x 1.965 GHz
+        peak, peak_note = 74.4, "fp32 FFMA pipe peak 148 SM x 128 x 2 x 1.965 GHz (SURVEY 8d fp32-strict rule); bf16 tensor peak listed beside it"
+    else:
+        peak, peak_note = bf16_peak, f"dense bf16 sustained, {src}"
+    return {"bound": "tensor", "kernel": "GEMM family (forward NT, dX NN, dW TN) of one train step", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_note": peak_note, "bf16_peak_tflops": bf16_peak,
+            "hbm_gbs": hbm, "step_peak_tflops": peak, "gemm_ms_per_step": tot_ms, "top_shapes": per[:6]}
+
+
+if __name__ == "__main__":
+    main()

@@ -124,6 +124,10 @@ int          fb200_algorithmic_work(const fb200_desc* d, double* flops, double* 
 /* Number of kernel launches one forward / one backward issues (for bench.py's gpu_launches). */
 int          fb200_launch_count(const fb200_desc* d, int* forward, int* backward);
 
+/* GEMM launches of one train step: writes up to cap entries of 5 int32 {layout, engine, M, N, K}
+ * (layouts / engines as in fb200_gemm) and returns how many were written. */
+int          fb200_list_gemms(const fb200_desc* d, int32_t* out, int cap);
+
 /* ---- the hot path ----------------------------------------------------------------- */
 /* All pointers are DEVICE pointers on the current device; `stream` is a cudaStream_t.
  * params[slot]  : fp32 parameter tensors, contiguous, reference shapes (NULL for absent slots)

@@ -52,14 +52,14 @@ struct Ctx {
     if (a.ext == 1) return make_ref((float*)img + v.col0, a.cols, FMT_F32);
     if (a.ext == 2) return make_ref((float*)txt + v.col0, a.cols, FMT_F32);
     if (a.ext == 3) return make_ref((float*)logits + v.col0, a.cols, FMT_F32);
-    return make_ref(ws + a.off + (size_t)v.col0 * fmt_bytes(p.fmt), a.cols, p.fmt, (int64_t)p.d.B * a.cols);
+    return make_ref(ws + a.off + (size_t)v.col0 * fmt_bytes(a.vfmt), a.cols, a.vfmt, (int64_t)p.d.B * a.cols);
   }
   TRef grad(const View& v) const {
     const Act& a = p.acts[v.buf];
     if (a.ext == 1) return make_ref(d_img ? (float*)d_img + v.col0 : nullptr, a.cols, FMT_F32);
     if (a.ext == 2) return make_ref(d_txt ? (float*)d_txt + v.col0 : nullptr, a.cols, FMT_F32);
     if (a.ext == 3) return make_ref((float*)dlogits + v.col0, a.cols, FMT_F32);
-    return make_ref(ws + a.goff + (size_t)v.col0 * fmt_bytes(p.fmt), a.cols, p.fmt, (int64_t)p.d.B * a.cols);
+    return make_ref(ws + a.goff + (size_t)v.col0 * fmt_bytes(a.gfmt), a.cols, a.gfmt, (int64_t)p.d.B * a.cols);
   }
   const float* param(int slot, int64_t elem_off = 0) const { return (const float*)params[slot] + elem_off; }
   float* pgrad(int slot, int64_t elem_off = 0) const { return grads + p.goff[slot] + elem_off; }
@@ -360,6 +360,26 @@ int fb200_launch_count(const fb200_desc* d, int* forward, int* backward) {
   if (forward) *forward = f;
   if (backward) *backward = b;
   return FB200_OK;
+}
+
+int fb200_list_gemms(const fb200_desc* d, int32_t* out, int cap) {
+  if (!d || !out || cap < 1) return FB200_EBADARG;
+  Plan p; int rc = build_plan(*d, p); if (rc != FB200_OK) return rc;
+  const bool need_dimg = d->flags & FB200_FLAG_NEED_DIMG, need_dtxt = d->flags & FB200_FLAG_NEED_DTEXT;
+  int n = 0;
+  auto put = [&](int layout, int engine, int M, int N, int K) {
+    if (n < cap) { int32_t* e = out + 5 * n; e[0] = layout; e[1] = engine; e[2] = M; e[3] = N; e[4] = K; }
+    ++n;
+  };
+  for (auto& o : p.ops) {
+    if (o.kind != OP_LINEAR) continue;
+    const int eng = o.engine == 0 ? 0 : (d->dtype == FB200_BF16 ? 2 : 1);
+    put(0, eng, d->B, o.out.cols, o.in0.cols);
+    put(2, eng, o.out.cols, o.in0.cols, d->B);
+    const int ext = p.acts[o.in0.buf].ext;
+    if (ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) put(1, eng, d->B, o.in0.cols, o.out.cols);
+  }
+  return n < cap ? n : cap;
 }
 
 int fb200_head_forward(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,

@@ -305,18 +305,24 @@ int build_plan(const fb200_desc& d, Plan& p) {
   }
   p.grad_elems = off;
 
+  // ---- per-buffer storage format: only GEMM operands pay for the operand format (bf16 / tf32 pair);
+  //      everything the row kernels exchange among themselves stays fp32
+  for (auto& o : p.ops) if (o.kind == OP_LINEAR) {
+    if (!p.acts[o.in0.buf].ext) p.acts[o.in0.buf].vfmt = p.fmt;
+    if (!p.acts[o.out.buf].ext) p.acts[o.out.buf].gfmt = p.fmt;
+  }
   // ---- workspace layout: values, then gradients, then row statistics
-  const size_t esz = fmt_bytes(p.fmt);
   auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+  auto fbytes = [](int fmt) -> size_t { return fmt == FMT_BF16 ? 2 : (fmt == FMT_PAIR ? 8 : 4); };
   size_t cur = 0;
   for (auto& a : p.acts) {
     if (a.ext) continue;
     if (a.cols % 4 != 0) { p.error = "internal activation width must be a multiple of 4"; return FB200_EUNSUPPORTED; }
-    a.off = cur; cur = align(cur + (size_t)d.B * a.cols * esz);
+    a.off = cur; cur = align(cur + (size_t)d.B * a.cols * fbytes(a.vfmt));
   }
   for (auto& a : p.acts) {
     if (a.ext) continue;
-    a.goff = cur; cur = align(cur + (size_t)d.B * a.cols * esz);
+    a.goff = cur; cur = align(cur + (size_t)d.B * a.cols * fbytes(a.gfmt));
   }
   for (auto& o : p.ops) {
     if (o.kind == OP_LNRD || o.kind == OP_GRB) { o.stats_off = cur; cur = align(cur + (size_t)d.B * 2 * sizeof(float)); }

@@ -48,6 +48,8 @@ struct Act {             // one activation buffer (and its gradient twin)
   int cols = 0;
   int ext = 0;           // 0: workspace, 1: img_feat, 2: text_in, 3: logits (gradient = dlogits)
   bool relu_out = false; // produced by Linear+ReLU: the gradient written into it must be masked by [value > 0]
+  int vfmt = FMT_F32;    // storage format of the value: the GEMM operand format iff some Linear reads it, else fp32
+  int gfmt = FMT_F32;    // storage format of the gradient: the operand format iff some Linear wrote the value (dY operand)
   size_t off = 0;        // byte offset of the value in the workspace
   size_t goff = 0;       // byte offset of the gradient
 };
@@ -65,7 +67,7 @@ struct Op {
 
 struct Plan {
   fb200_desc d;
-  int fmt = FMT_F32;                 // storage format of workspace activations
+  int fmt = FMT_F32;                 // GEMM operand format of workspace activations (F32 / PAIR / BF16)
   std::vector<Act> acts;
   std::vector<Op> ops;
   View logits;
