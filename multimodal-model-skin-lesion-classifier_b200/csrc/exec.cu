@@ -70,12 +70,58 @@ struct Ctx {
   }
 };
 
+
+// One launch converts every weight the tcgen05 GEMMs read into the operand format (bf16, or
+// tf32 hi/lo planes): weights change every optimizer step, so this runs at the top of forward.
+struct PrepSeg { const float* src; void* dst; int64_t n4; int64_t plane; };
+struct PrepArgs { PrepSeg seg[32]; int nseg; int fmt; };
+__global__ void __launch_bounds__(256) wprep_kernel(const PrepArgs a) {
+  const PrepSeg sg = a.seg[blockIdx.y];
+  const TRef out = make_ref(sg.dst, 0, a.fmt, sg.plane);          // flat view: row 0, column = element index
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n4; i += (int64_t)gridDim.x * blockDim.x)
+    st4(out, 0, (int)(i * 4), __ldg((const float4*)sg.src + i));
+}
+
+static TcOperand tc_operand(const TRef& r, int inner, int outer) {
+  TcOperand o; o.base = r.p; o.plane_elems = r.plane; o.ld = r.ld; o.inner = inner; o.outer = outer; return o;
+}
+
 // ------------------------------------------------------------------------------- forward
+static TRef wprep_ref(const Ctx& c, const WPrep& w) {
+  return make_ref(c.ws + w.off, w.cols, c.p.fmt, (int64_t)w.rows * w.cols);
+}
+
 static int run_forward(Ctx& c) {
   const Plan& p = c.p; const int B = p.d.B;
+  for (size_t base = 0; base < p.wprep.size(); base += 32) {
+    PrepArgs a{}; a.fmt = p.fmt; a.nseg = 0;
+    for (size_t i = base; i < p.wprep.size() && a.nseg < 32; ++i) {
+      const WPrep& w = p.wprep[i];
+      PrepSeg& sg = a.seg[a.nseg++];
+      sg.src = c.param(w.slot, (int64_t)w.row0 * w.cols); sg.dst = c.ws + w.off; sg.n4 = (int64_t)w.rows * w.cols / 4; sg.plane = (int64_t)w.rows * w.cols;
+    }
+    wprep_kernel<<<dim3(64, a.nseg), 256, 0, c.st>>>(a);
+    CUDA_OK(cudaGetLastError());
+  }
   for (const Op& o : p.ops) {
     switch (o.kind) {
+      case OP_CAST: {
+        const TRef src = c.value(o.in0);
+        convert_kernel<<<c.dev.num_sms * 4, 256, 0, c.st>>>((const float*)src.p, src.ld, c.value(o.out), B, o.out.cols);
+      } break;
       case OP_LINEAR: {
+        if (o.engine == 1) {
+          TcGemmArgs t{};
+          t.kind = p.fmt == FMT_BF16 ? 0 : 1; t.a_mn = 0; t.b_mn = 0;
+          t.A = tc_operand(c.value(o.in0), o.in0.cols, B);
+          t.B = tc_operand(wprep_ref(c, p.wprep[o.wprep]), o.in0.cols, o.out.cols);
+          t.M = B; t.N = o.out.cols; t.K = o.in0.cols;
+          t.ep.C = c.value(o.out); t.ep.bias = c.param(o.b_slot, o.w_row0); t.ep.relu = o.relu; t.ep.mask_src.p = nullptr;
+          t.ep.accumulate = 0; t.ep.atomic = 0; t.ep.colsum = nullptr; t.allow_split = 0;
+          int rc = launch_tc_gemm(t, c.dev.num_sms, c.st);
+          if (rc != FB200_OK) return rc;
+          break;
+        }
         GemmArgs g{};
         g.A = c.value(o.in0); g.B = make_ref((void*)c.param(o.w_slot, (int64_t)o.w_row0 * o.in0.cols), o.in0.cols, FMT_F32);
         g.C = c.value(o.out); g.M = B; g.N = o.out.cols; g.K = o.in0.cols; g.a_kc = 1; g.b_kc = 1;
@@ -150,8 +196,45 @@ static int run_backward(Ctx& c) {
     // the gradient of a view that lives inside a fully written buffer counts as written
     if (!is_written(o.out)) return FB200_EBADARG;
     switch (o.kind) {
+      case OP_CAST: break;
       case OP_LINEAR: {
         const int N = o.out.cols, K = o.in0.cols;
+        if (o.engine == 1) {
+          const int kind = p.fmt == FMT_BF16 ? 0 : 1;
+          // dW[N,K] (+)= dY^T X : both operands MN-major views of the row-major activations
+          TcGemmArgs t{};
+          t.kind = kind; t.a_mn = 1; t.b_mn = 1;
+          t.A = tc_operand(c.grad(o.out), N, B); t.B = tc_operand(c.value(o.in0), K, B);
+          t.M = N; t.N = K; t.K = B;
+          t.ep.C = make_ref(c.pgrad(o.w_slot, (int64_t)o.w_row0 * K), K, FMT_F32); t.ep.bias = nullptr; t.ep.relu = 0; t.ep.mask_src.p = nullptr;
+          t.ep.accumulate = pwritten[o.w_slot]; t.ep.atomic = 0; t.ep.colsum = nullptr; t.allow_split = 1;
+          int rc = launch_tc_gemm(t, c.dev.num_sms, c.st);
+          if (rc != FB200_OK) return rc;
+          pwritten[o.w_slot] = 1;
+          {   // db[N] += column sums of dY
+            const TRef dy = c.grad(o.out);
+            float* db = c.pgrad(o.b_slot, o.w_row0);
+            const int grid = row_grid_for(B, N, c.dev.num_sms);
+#define CALL(NV, TPR) colsum_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(dy, B, N, db)
+            FB200_ROW_DISPATCH(N, CALL);
+#undef CALL
+            CUDA_OK(cudaGetLastError());
+          }
+          if (grad_wanted(o.dx_view)) {
+            // dX[B,K] (+)= dY W : W read MN-major from the same operand-format copy the forward used
+            TcGemmArgs h{};
+            h.kind = kind; h.a_mn = 0; h.b_mn = 1;
+            h.A = tc_operand(c.grad(o.out), N, B); h.B = tc_operand(wprep_ref(c, p.wprep[o.wprep]), K, N);
+            h.M = B; h.N = K; h.K = N;
+            h.ep.C = c.grad(o.dx_view); h.ep.bias = nullptr; h.ep.relu = 0; h.ep.mask_src.p = nullptr;
+            if (p.acts[o.in0.buf].relu_out) h.ep.mask_src = c.value(o.in0);
+            h.ep.accumulate = is_written(o.dx_view); h.ep.atomic = 0; h.ep.colsum = nullptr; h.allow_split = 0;
+            rc = launch_tc_gemm(h, c.dev.num_sms, c.st);
+            if (rc != FB200_OK) return rc;
+            set_written(o.dx_view);
+          }
+          break;
+        }
         // dW[N,K] (+)= dY^T X ; db[N] += colsum(dY)
         GemmArgs g{};
         g.A = c.grad(o.out); g.a_kc = 0; g.B = c.value(o.in0); g.b_kc = 0;
@@ -161,15 +244,15 @@ static int run_backward(Ctx& c) {
         CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
         pwritten[o.w_slot] = 1;
         // dX[B,K] (+)= dY W, masked by the producer's ReLU when the input came out of Linear+ReLU
-        if (grad_wanted(o.in0)) {
+        if (grad_wanted(o.dx_view)) {
           GemmArgs h{};
           h.A = c.grad(o.out); h.a_kc = 1; h.B = make_ref((void*)c.param(o.w_slot, (int64_t)o.w_row0 * K), K, FMT_F32); h.b_kc = 0;
-          h.C = c.grad(o.in0); h.M = B; h.N = K; h.K = N; h.bias = nullptr; h.relu = 0;
+          h.C = c.grad(o.dx_view); h.M = B; h.N = K; h.K = N; h.bias = nullptr; h.relu = 0;
           h.mask_src.p = nullptr;
           if (p.acts[o.in0.buf].relu_out) h.mask_src = c.value(o.in0);
-          h.accumulate = is_written(o.in0); h.split_k = 1; h.colsum_a = nullptr;
+          h.accumulate = is_written(o.dx_view); h.split_k = 1; h.colsum_a = nullptr;
           CUDA_OK(launch_simt_gemm(h, c.dev.num_sms, c.st));
-          set_written(o.in0);
+          set_written(o.dx_view);
         }
       } break;
       case OP_LNRD: {
@@ -350,12 +433,13 @@ int fb200_launch_count(const fb200_desc* d, int* forward, int* backward) {
   Plan p; int rc = build_plan(*d, p); if (rc != FB200_OK) return rc;
   int f = 0, b = 0;
   const bool need_dimg = d->flags & FB200_FLAG_NEED_DIMG, need_dtxt = d->flags & FB200_FLAG_NEED_DTEXT;
+  f += (int)((p.wprep.size() + 31) / 32);
   for (auto& o : p.ops) {
     f += 1;
     if (o.kind == OP_LINEAR) {
-      const int ext = p.acts[o.in0.buf].ext;
-      b += 1 + ((ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) ? 1 : 0);
-    } else b += 1;
+      const int ext = p.acts[o.dx_view.buf].ext;
+      b += 1 + (o.engine == 1 ? 1 : 0) + ((ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) ? 1 : 0);
+    } else if (o.kind != OP_CAST) b += 1;
   }
   if (forward) *forward = f;
   if (backward) *backward = b;
@@ -376,7 +460,7 @@ int fb200_list_gemms(const fb200_desc* d, int32_t* out, int cap) {
     const int eng = o.engine == 0 ? 0 : (d->dtype == FB200_BF16 ? 2 : 1);
     put(0, eng, d->B, o.out.cols, o.in0.cols);
     put(2, eng, o.out.cols, o.in0.cols, d->B);
-    const int ext = p.acts[o.in0.buf].ext;
+    const int ext = p.acts[o.dx_view.buf].ext;
     if (ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) put(1, eng, d->B, o.in0.cols, o.out.cols);
   }
   return n < cap ? n : cap;
@@ -457,6 +541,10 @@ int fb200_gemm(int layout, int engine, int M, int N, int K, const float* A, int 
     g.a_kc = (layout == 2) ? 0 : 1;            // TN: A is [K,M]
     g.b_kc = (layout == 0) ? 1 : 0;            // NT: B is [N,K]
     g.bias = bias; g.relu = relu; g.mask_src.p = nullptr; g.accumulate = accumulate; g.split_k = 1; g.colsum_a = nullptr;
+    if (layout == 2 && !bias && !relu && ldc == N) {     // weight-gradient shape: same auto split-K as the train step
+      g.split_k = 0;
+      if (!accumulate) CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream));
+    }
     CUDA_OK(launch_simt_gemm(g, dev.num_sms, (cudaStream_t)stream));
     return FB200_OK;
   }

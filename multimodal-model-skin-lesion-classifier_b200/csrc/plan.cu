@@ -96,8 +96,30 @@ struct Builder {
 
   // y = x W^T + b (optionally ReLU).  `dst` lets the producer write straight into a
   // concatenation half (torch.cat at :212-228 never materialises separately).
+  int cast_of[3] = {-1, -1, -1};       // operand-format copies of the external inputs (built once)
   View linear(View x, int w_slot, int out_cols, bool relu = false, const View* dst = nullptr, int w_row0 = 0) {
-    Op o; o.kind = OP_LINEAR; o.in0 = x; o.w_slot = w_slot; o.b_slot = w_slot + 1; o.w_row0 = w_row0; o.relu = relu ? 1 : 0;
+    Op o; o.kind = OP_LINEAR; o.w_slot = w_slot; o.b_slot = w_slot + 1; o.w_row0 = w_row0; o.relu = relu ? 1 : 0;
+    o.dx_view = x;
+    // tcgen05 takes 16-byte global strides: both widths multiples of 8 (metadata widths 85/13/11 and the
+    // class count stay on the FFMA kernel)
+    o.engine = (p.use_tc && x.cols % 8 == 0 && out_cols % 8 == 0 && x.cols >= 32 && out_cols >= 32) ? 1 : 0;
+    const int ext = p.acts[x.buf].ext;
+    if (o.engine == 1 && ext != 0) {   // TMA reads operand-format data: convert the fp32 input once
+      if (cast_of[ext] < 0) {
+        cast_of[ext] = new_act(p.acts[x.buf].cols);
+        Op c; c.kind = OP_CAST; c.in0 = whole(x.buf); c.out = whole(cast_of[ext]);
+        p.ops.push_back(c);
+      }
+      View xc = x; xc.buf = cast_of[ext];
+      x = xc;
+    }
+    o.in0 = x;
+    if (o.engine == 1) {
+      int found = -1;
+      for (size_t i = 0; i < p.wprep.size(); ++i) if (p.wprep[i].slot == w_slot && p.wprep[i].row0 == w_row0) found = (int)i;
+      if (found < 0) { p.wprep.push_back(WPrep{w_slot, w_row0, out_cols, x.cols, 0}); found = (int)p.wprep.size() - 1; }
+      o.wprep = found;
+    }
     o.out = dst ? *dst : whole(new_act(out_cols));
     if (relu) p.acts[o.out.buf].relu_out = true;
     touch(w_slot); touch(w_slot + 1);
@@ -169,7 +191,10 @@ int build_plan(const fb200_desc& d, Plan& p) {
       d.mechanism != FB200_RGATT2FUSEFEATURES && d.mechanism != FB200_RGATT_FULL_RGATT2FUSE && d.mechanism != FB200_RGATT_FULL_METABLOCK && d.n != 2) {
     p.error = "fusion strings that concatenate two modalities need n = 2"; return FB200_EBADARG;
   }
-  p.fmt = d.dtype == FB200_BF16 ? FMT_BF16 : FMT_F32;
+  // engine policy: bf16 always rides the tensor cores; fp32 switches to the 3xTF32 tensor path once the
+  // batch is large enough to be compute-bound (below that the exact FFMA kernel streams fp32 weights once)
+  p.use_tc = !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B >= 256);
+  p.fmt = d.dtype == FB200_BF16 ? FMT_BF16 : (p.use_tc ? FMT_PAIR : FMT_F32);
 
   Builder b(p);
   const int D = d.D;
@@ -324,6 +349,7 @@ int build_plan(const fb200_desc& d, Plan& p) {
     if (a.ext) continue;
     a.goff = cur; cur = align(cur + (size_t)d.B * a.cols * fbytes(a.gfmt));
   }
+  for (auto& w : p.wprep) { w.off = cur; cur = align(cur + (size_t)w.rows * w.cols * fbytes(p.fmt)); }
   for (auto& o : p.ops) {
     if (o.kind == OP_LNRD || o.kind == OP_GRB) { o.stats_off = cur; cur = align(cur + (size_t)d.B * 2 * sizeof(float)); }
     if (o.kind == OP_META) { o.stats_off = cur; cur = align(cur + (size_t)d.B * 4 * sizeof(float)); }
@@ -340,10 +366,10 @@ int build_plan(const fb200_desc& d, Plan& p) {
     if (o.kind == OP_LINEAR) {
       double mk = (double)o.in0.cols * o.out.cols;
       macs_fwd += mk;
-      const int ext = p.acts[o.in0.buf].ext;
+      const int ext = p.acts[o.dx_view.buf].ext;
       if (ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) macs_dx += mk;
       if (!counted[o.w_slot]) { counted[o.w_slot] = true; plive += (int64_t)o.in0.cols * o.out.cols + o.out.cols; }   // only the V third of in_proj is live
-    } else {
+    } else if (o.kind != OP_CAST) {
       for (int k = 0; k < 2; ++k) if (o.ln_w[k] >= 0 && !counted[o.ln_w[k]]) { counted[o.ln_w[k]] = true; plive += 2 * (int64_t)o.out.cols; }
     }
   }

@@ -40,7 +40,7 @@ extern const char* const kSlotNames[NUM_SLOTS];
 struct Shape { int64_t rows, cols; bool present; };   // cols = 0 -> 1-D
 Shape slot_shape(const fb200_desc& d, int slot);
 
-enum OpKind : int { OP_LINEAR = 0, OP_LNRD, OP_GATE, OP_GRB, OP_META };
+enum OpKind : int { OP_LINEAR = 0, OP_LNRD, OP_GATE, OP_GRB, OP_META, OP_CAST };
 
 struct View { int buf = -1; int col0 = 0; int cols = 0; };
 
@@ -63,10 +63,16 @@ struct Op {
   int site = -1; float p = 0.f;                     // dropout site
   size_t stats_off = 0;                             // fp32 row statistics in the workspace
   int engine = 0;                                   // LINEAR: 0 SIMT, 1 tcgen05
+  View dx_view;                                     // LINEAR: where dX goes (the fp32 external input when in0 is its operand-format copy)
+  int wprep = -1;                                   // LINEAR on tcgen05: index into Plan::wprep (operand-format copy of W)
 };
+
+struct WPrep { int slot, row0, rows, cols; size_t off; };   // operand-format weight copy living in the workspace
 
 struct Plan {
   fb200_desc d;
+  bool use_tc = false;               // tcgen05 GEMMs enabled for this call
+  std::vector<WPrep> wprep;
   int fmt = FMT_F32;                 // GEMM operand format of workspace activations (F32 / PAIR / BF16)
   std::vector<Act> acts;
   std::vector<Op> ops;

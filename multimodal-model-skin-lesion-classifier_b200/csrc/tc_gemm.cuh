@@ -1,8 +1,409 @@
-// tc_gemm.cuh - tcgen05 GEMM (placeholder until the kernel lands)
+// tc_gemm.cuh - tcgen05 / TMEM / TMA GEMM for sm_100a, hand-written PTX.
+//
+//   C[M,N] (+)= A x B      fp32 accumulation in tensor memory
+//   kind bf16   : tcgen05.mma.kind::f16, bf16 operands
+//   kind tf32x3 : tcgen05.mma.kind::tf32, every operand is a (hi, lo) pair of fp32 planes
+//                 (hi = tf32-rounded value, lo = exact remainder); three MMAs per k-slice
+//                 hi*hi + lo*hi + hi*lo reproduce fp32 products to ~2^-21 (fp32-strict mode).
+//   layouts     : each operand is either K-major (reduction dim contiguous) or MN-major, so
+//                 forward (X W^T), dX (dY W) and dW (dY^T X) all read the SAME row-major
+//                 tensors straight from HBM through TMA - nothing is ever transposed in memory.
+//
+// CTA = 192 threads: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2..5 = epilogue (TMEM -> registers -> global, fused bias /
+// ReLU / ReLU-mask / accumulate / split-K reduction).  One 128 x BLOCK_N output tile per CTA,
+// STAGES-deep smem ring of 128-byte-swizzled tiles guarded by full/empty mbarriers.
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
+
 namespace fb200 {
-inline int tc_gemm_workspace_bytes(int, int, int, int, int, size_t*) { return FB200_EUNSUPPORTED; }
-inline int tc_gemm_f32(int, int, int, int, int, const float*, int, const float*, int, float*, int, const float*, int, int,
-                       void*, size_t, int, cudaStream_t) { return FB200_EUNSUPPORTED; }
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 192;
+
+struct TcEpilogue {
+  TRef C;                 // output view (any Fmt)
+  const float* bias;      // [N] or nullptr
+  int relu;
+  TRef mask_src;          // multiply by [mask_src > 0] when .p != nullptr
+  int accumulate;         // C += result
+  int atomic;             // split-K: fp32 atomic add into C (FMT_F32 only)
+  float* colsum;          // optional: colsum[n] += sum_m result(m,n)  (unused by the head; reserved)
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 0) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (tcgen05 "SmemDescriptor"): start address, leading / stride
+// byte offsets (all >> 4), version 1 (bits 46-47), 128-byte swizzle (layout type 2 in bits 61-63).
+//   K-major  tile: rows of 128 B (the K slice), 8-row swizzle atoms 1024 B apart      -> SBO = 1024, LBO unused (1)
+//   MN-major tile: 128 B of MN per K row, 8 K rows per atom (1024 B), MN chunks LBO apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor: fp32 accumulate, operand format, majors, N >> 3, M >> 4.
+__host__ __device__ constexpr uint32_t make_idesc(int kind, int a_mn, int b_mn, int m, int n) {
+  return (1u << 4) | ((uint32_t)(kind == 0 ? 1 : 2) << 7) | ((uint32_t)(kind == 0 ? 1 : 2) << 10) |
+         ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int KIND, int BN>
+struct TcCfg {
+  static constexpr int ESIZE = KIND == 0 ? 2 : 4;
+  static constexpr int BK = 128 / ESIZE;                 // elements of K per stage (one 128-byte swizzle row)
+  static constexpr int UMMA_K = 32 / ESIZE;              // 16 (bf16) / 8 (tf32)
+  static constexpr int PLANES = KIND == 0 ? 1 : 2;
+  static constexpr int A_BYTES = TC_BM * 128;            // one plane of the A tile
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (KIND == 0) ? (BN <= 128 ? 6 : 4) : (BN <= 128 ? 3 : 2);
+  static constexpr int EPC = 128 / ESIZE;                // elements per 128-byte chunk along MN (MN-major operands)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int KIND, int A_MN, int B_MN, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcEpilogue ep, const int M, const int N, const int K, const int kb_per_split) {
+  using Cfg = TcCfg<KIND, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // 128B swizzle needs 1024-byte alignment
+  uint64_t* full_bar = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int total_kb = (K + Cfg::BK - 1) / Cfg::BK;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(total_kb, kb_begin + kb_per_split);
+  const int num_kb = kb_end - kb_begin;                                            // >= 1 by construction of the grid
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        const int k0 = (kb_begin + i) * Cfg::BK;
+#pragma unroll
+        for (int pl = 0; pl < Cfg::PLANES; ++pl) {
+          uint8_t* a_dst = st + pl * Cfg::A_BYTES;
+          uint8_t* b_dst = st + Cfg::PLANES * Cfg::A_BYTES + pl * Cfg::B_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < TC_BM / Cfg::EPC; ++c) tma_load_3d(&map_a, &full_bar[s], a_dst + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, k0, pl);
+          } else {
+            tma_load_3d(&map_a, &full_bar[s], a_dst, k0, m0, pl);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / Cfg::EPC; ++c) tma_load_3d(&map_b, &full_bar[s], b_dst + c * (Cfg::BK * 128), n0 + c * Cfg::EPC, k0, pl);
+          } else {
+            tma_load_3d(&map_b, &full_bar[s], b_dst, k0, n0, pl);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(KIND, A_MN, B_MN, TC_BM, BN);
+      constexpr uint32_t a_lbo = A_MN ? Cfg::BK * 128 : 16, a_sbo = 1024;
+      constexpr uint32_t b_lbo = B_MN ? Cfg::BK * 128 : 16, b_sbo = 1024;
+      constexpr uint32_t a_kstep = A_MN ? Cfg::UMMA_K * 128 : 32;                  // bytes per UMMA_K advance
+      constexpr uint32_t b_kstep = B_MN ? Cfg::UMMA_K * 128 : 32;
+      uint32_t acc = 0;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t b_hi = a_hi + Cfg::PLANES * Cfg::A_BYTES;
+#pragma unroll
+        for (int j = 0; j < Cfg::BK / Cfg::UMMA_K; ++j) {
+          const uint64_t da = make_smem_desc(a_hi + j * a_kstep, a_lbo, a_sbo);
+          const uint64_t db = make_smem_desc(b_hi + j * b_kstep, b_lbo, b_sbo);
+          umma<KIND>(tmem_base, da, db, idesc, acc);
+          acc = 1;
+          if (KIND == 1) {
+            const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + j * a_kstep, a_lbo, a_sbo);
+            const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + j * b_kstep, b_lbo, b_sbo);
+            umma<KIND>(tmem_base, da_lo, db, idesc, 1u);
+            umma<KIND>(tmem_base, da, db_lo, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);                                                 // frees the smem slot once these MMAs retire
+      }
+      umma_commit(tmem_full);                                                       // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int64_t row = (int64_t)m0 + q * 32 + lane;
+    const bool row_ok = row < M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;                                                      // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int n = n0 + c0 + g * 4;
+        if (n >= N) break;
+        float4 v = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
+        if (ep.atomic) {
+          float* c = (float*)ep.C.p + row * ep.C.ld + n;
+          atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
+          continue;
+        }
+        if (ep.bias) { const float4 b = __ldg((const float4*)(ep.bias + n)); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+        if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (ep.mask_src.p) {
+          const float4 mk = ld4(ep.mask_src, row, n);
+          v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+        }
+        if (ep.accumulate) { const float4 o = ld4(ep.C, row, n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+        st4(ep.C, row, n, v);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN < 32 ? 32 : BN); }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// One GEMM operand as it lies in HBM: a row-major [outer, inner] matrix (inner contiguous),
+// optionally a (hi, lo) pair of planes.  kmajor: inner is the reduction dimension.
+struct TcOperand {
+  const void* base; int64_t plane_elems; int ld; int inner, outer;
+};
+inline int make_operand_map(CUtensorMap* map, int kind, const TcOperand& o, int box_inner, int box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return FB200_ECUDA;
+  const int es = kind == 0 ? 2 : 4;
+  const int planes = kind == 0 ? 1 : 2;
+  if ((((uintptr_t)o.base) & 15) || ((int64_t)o.ld * es) % 16 || (planes == 2 && (o.plane_elems * es) % 16)) return FB200_EALIGN;
+  cuuint64_t dims[3] = {(cuuint64_t)o.inner, (cuuint64_t)o.outer, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)o.ld * es, (cuuint64_t)(planes == 2 ? o.plane_elems : (int64_t)o.ld * o.outer) * es};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)o.base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FB200_OK : FB200_ECUDA;
+}
+
+struct TcGemmArgs {
+  int kind;               // 0 bf16, 1 tf32x3
+  int a_mn, b_mn;         // operand majors: 0 K-major, 1 MN-major
+  TcOperand A, B;         // A covers (M, K), B covers (N, K) in the orientation given by the majors
+  int M, N, K;
+  TcEpilogue ep;
+  int allow_split;        // weight-gradient GEMMs: split K across CTAs, atomically reduce into pre-zeroed fp32 C
+};
+
+template <int KIND, int A_MN, int B_MN, int BN>
+inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg<KIND, BN>;
+  CUtensorMap ma, mb;
+  int rc = make_operand_map(&ma, KIND, g.A, A_MN ? Cfg::EPC : Cfg::BK, A_MN ? Cfg::BK : TC_BM);
+  if (rc != FB200_OK) return rc;
+  rc = make_operand_map(&mb, KIND, g.B, B_MN ? Cfg::EPC : Cfg::BK, B_MN ? Cfg::BK : BN);
+  if (rc != FB200_OK) return rc;
+  static bool attr_set = false;                   // idempotent; a benign race sets it twice
+  auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN>;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
+    attr_set = true;
+  }
+  const int tiles_m = (g.M + TC_BM - 1) / TC_BM, tiles_n = (g.N + BN - 1) / BN;
+  const int total_kb = (g.K + Cfg::BK - 1) / Cfg::BK;
+  int split = 1;
+  TcEpilogue ep = g.ep;
+  if (g.allow_split && ep.C.fmt == FMT_F32 && !ep.bias && !ep.relu && !ep.mask_src.p) {
+    const int tiles = tiles_m * tiles_n;
+    int want = (num_sms + tiles - 1) / tiles;
+    int maxs = total_kb / 8; if (maxs < 1) maxs = 1;            // keep >= 8 k-blocks per slice
+    split = want < maxs ? want : maxs;
+    if (split < 1) split = 1;
+  }
+  int kb_per = (total_kb + split - 1) / split;
+  split = (total_kb + kb_per - 1) / kb_per;                       // no empty slices
+  ep.atomic = split > 1 ? 1 : 0;
+  dim3 grid(tiles_n, tiles_m, split);
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, ep, g.M, g.N, g.K, kb_per);
+  return cudaGetLastError() == cudaSuccess ? FB200_OK : FB200_ECUDA;
+}
+
+template <int KIND, int BN>
+inline int tc_launch_major(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
+  if (!g.a_mn && !g.b_mn) return tc_launch_one<KIND, 0, 0, BN>(g, num_sms, st);
+  if (!g.a_mn && g.b_mn) return tc_launch_one<KIND, 0, 1, BN>(g, num_sms, st);
+  if (g.a_mn && g.b_mn) return tc_launch_one<KIND, 1, 1, BN>(g, num_sms, st);
+  return FB200_EUNSUPPORTED;
+}
+
+// Shapes the tcgen05 path takes: 16-byte global strides (K, N multiples of 8) - ragged M/N/K
+// tile edges are handled by TMA zero fill and epilogue predication.
+inline bool tc_shape_ok(int M, int N, int K) { return M >= 1 && N >= 8 && K >= 8 && N % 8 == 0 && K % 8 == 0; }
+
+inline int launch_tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
+  if (g.kind == 0) return tc_launch_major<0, 128>(g, num_sms, st);
+  return tc_launch_major<1, 128>(g, num_sms, st);
+}
+
+// ---- fp32-in / fp32-out wrapper used by the fb200_gemm primitive (unit tests, micro-benchmarks):
+// converts A and B into the operand format inside `ws`, then runs the tcgen05 kernel.
+__global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ in, int64_t rows, int cols, int ld_in, TRef out) {
+  const int64_t total4 = rows * (cols / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (cols / 4); const int c = (int)(i - r * (cols / 4)) * 4;
+    st4(out, r, c, *(const float4*)(in + r * ld_in + c));
+  }
+}
+inline size_t tc_operand_bytes(int kind, int64_t rows, int cols) { return (size_t)rows * cols * (kind == 0 ? 2 : 8); }
+inline int tc_gemm_workspace_bytes(int layout, int engine, int M, int N, int K, size_t* bytes) {
+  if (engine != 1 && engine != 2) return FB200_EBADARG;
+  if (!tc_shape_ok(M, N, K) || M % 4) return FB200_EUNSUPPORTED;
+  const int kind = engine == 2 ? 0 : 1;
+  *bytes = ((tc_operand_bytes(kind, layout == 2 ? K : M, layout == 2 ? M : K) + 255) & ~size_t(255)) +
+           ((tc_operand_bytes(kind, layout == 0 ? N : K, layout == 0 ? K : N) + 255) & ~size_t(255)) + 256;
+  return FB200_OK;
+}
+inline int tc_gemm_f32(int layout, int engine, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       const float* bias, int relu, int accumulate, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st) {
+  size_t need = 0;
+  int rc = tc_gemm_workspace_bytes(layout, engine, M, N, K, &need);
+  if (rc != FB200_OK) return rc;
+  if (!ws || ws_bytes < need || (((uintptr_t)ws) & 255)) return FB200_EBADARG;
+  if ((lda % 4) || (ldb % 4) || (ldc % 4) || (((uintptr_t)A) & 15) || (((uintptr_t)B) & 15) || (((uintptr_t)C) & 15)) return FB200_EALIGN;
+  const int kind = engine == 2 ? 0 : 1;
+  const int fmt = kind == 0 ? FMT_BF16 : FMT_PAIR;
+  const int64_t a_rows = layout == 2 ? K : M; const int a_cols = layout == 2 ? M : K;
+  const int64_t b_rows = layout == 0 ? N : K; const int b_cols = layout == 0 ? K : N;
+  char* w = (char*)ws;
+  TRef a_ref = make_ref(w, a_cols, fmt, a_rows * a_cols);
+  TRef b_ref = make_ref(w + ((tc_operand_bytes(kind, a_rows, a_cols) + 255) & ~size_t(255)), b_cols, fmt, b_rows * b_cols);
+  tc_split_kernel<<<296, 256, 0, st>>>(A, a_rows, a_cols, lda, a_ref);
+  tc_split_kernel<<<296, 256, 0, st>>>(B, b_rows, b_cols, ldb, b_ref);
+  TcGemmArgs g{};
+  g.kind = kind; g.a_mn = layout == 2; g.b_mn = layout != 0;
+  g.A = TcOperand{a_ref.p, a_ref.plane, a_cols, a_cols, (int)a_rows};
+  g.B = TcOperand{b_ref.p, b_ref.plane, b_cols, b_cols, (int)b_rows};
+  g.M = M; g.N = N; g.K = K;
+  g.ep.C = make_ref(C, ldc, FMT_F32); g.ep.bias = bias; g.ep.relu = relu; g.ep.mask_src.p = nullptr; g.ep.accumulate = accumulate;
+  g.ep.atomic = 0; g.ep.colsum = nullptr; g.allow_split = 0;
+  if (layout == 2 && !bias && !relu && ldc == N) {
+    g.allow_split = 1;
+    if (!accumulate && cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st) != cudaSuccess) return FB200_ECUDA;
+  }
+  return launch_tc_gemm(g, num_sms, st);
+}
+
+}  // namespace fb200
