@@ -106,13 +106,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // byte offsets (all >> 4), version 1 (bits 46-47), 128-byte swizzle (layout type 2 in bits 61-63).
 //   K-major  tile: rows of 128 B (the K slice), 8-row swizzle atoms 1024 B apart      -> SBO = 1024, LBO unused (1)
 //   MN-major tile: 128 B of MN per K row, 8 K rows per atom (1024 B), MN chunks LBO apart
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major fp32 (tf32) tiles exist only in the "128B swizzle, 32-byte atom" flavour (layout type 1):
+//   32-byte chunks swizzled by (k row % 4), 4 K rows per 512-byte atom -> SBO = 512
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // Instruction descriptor: fp32 accumulate, operand format, majors, N >> 3, M >> 4.
@@ -133,6 +135,14 @@ struct TcCfg {
   static constexpr int STAGES = (KIND == 0) ? (BN <= 128 ? 6 : 4) : (BN <= 128 ? 3 : 2);
   static constexpr int EPC = 128 / ESIZE;                // elements per 128-byte chunk along MN (MN-major operands)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // The tensor-core accumulator truncates on every accumulate, a bias that grows linearly with the number
+  // of MMAs chained into one TMEM accumulator (measured: 3e-5 relative at K = 4096 in 3xTF32).  The
+  // fp32-strict kind therefore accumulates at most CHUNK_KB k-blocks (K = 128) in TMEM, and the epilogue
+  // warps promote each chunk into fp32 registers (round-to-nearest FADD) while the MMA warp already
+  // fills the other of two TMEM accumulators.
+  static constexpr int CHUNK_KB = KIND == 1 ? 4 : (1 << 30);
+  static constexpr int ACC_BUFS = KIND == 1 ? 2 : 1;
+  static constexpr int TMEM_COLS = (ACC_BUFS * BN) < 32 ? 32 : (ACC_BUFS * BN);
 };
 
 template <int KIND, int A_MN, int B_MN, int BN>
@@ -144,8 +154,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // 128B swizzle needs 1024-byte alignment
   uint64_t* full_bar = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;            // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                     // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -157,10 +168,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full, 1);
+    mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);                     // one arrive per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -198,71 +210,87 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(KIND, A_MN, B_MN, TC_BM, BN);
-      constexpr uint32_t a_lbo = A_MN ? Cfg::BK * 128 : 16, a_sbo = 1024;
-      constexpr uint32_t b_lbo = B_MN ? Cfg::BK * 128 : 16, b_sbo = 1024;
+      constexpr uint32_t a_lt = (A_MN && KIND == 1) ? 1 : 2, b_lt = (B_MN && KIND == 1) ? 1 : 2;   // smem layout types
+      constexpr uint32_t a_lbo = A_MN ? Cfg::BK * 128 : 16, a_sbo = (A_MN && KIND == 1) ? 512 : 1024;
+      constexpr uint32_t b_lbo = B_MN ? Cfg::BK * 128 : 16, b_sbo = (B_MN && KIND == 1) ? 512 : 1024;
       constexpr uint32_t a_kstep = A_MN ? Cfg::UMMA_K * 128 : 32;                  // bytes per UMMA_K advance
       constexpr uint32_t b_kstep = B_MN ? Cfg::UMMA_K * 128 : 32;
-      uint32_t acc = 0;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
+        const int chunk = i / Cfg::CHUNK_KB, ab = chunk & (Cfg::ACC_BUFS - 1);
+        const bool chunk_first = (i % Cfg::CHUNK_KB) == 0;
+        if (chunk_first) { mbar_wait(&tmem_empty[ab], ((chunk / Cfg::ACC_BUFS) & 1) ^ 1); tc_fence_after(); }
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t b_hi = a_hi + Cfg::PLANES * Cfg::A_BYTES;
 #pragma unroll
         for (int j = 0; j < Cfg::BK / Cfg::UMMA_K; ++j) {
-          const uint64_t da = make_smem_desc(a_hi + j * a_kstep, a_lbo, a_sbo);
-          const uint64_t db = make_smem_desc(b_hi + j * b_kstep, b_lbo, b_sbo);
-          umma<KIND>(tmem_base, da, db, idesc, acc);
-          acc = 1;
+          const uint64_t da = make_smem_desc(a_hi + j * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t db = make_smem_desc(b_hi + j * b_kstep, b_lbo, b_sbo, b_lt);
+          umma<KIND>(d_tmem, da, db, idesc, (chunk_first && j == 0) ? 0u : 1u);
           if (KIND == 1) {
-            const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + j * a_kstep, a_lbo, a_sbo);
-            const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + j * b_kstep, b_lbo, b_sbo);
-            umma<KIND>(tmem_base, da_lo, db, idesc, 1u);
-            umma<KIND>(tmem_base, da, db_lo, idesc, 1u);
+            const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + j * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + j * b_kstep, b_lbo, b_sbo, b_lt);
+            umma<KIND>(d_tmem, da_lo, db, idesc, 1u);
+            umma<KIND>(d_tmem, da, db_lo, idesc, 1u);
           }
         }
         umma_commit(&empty_bar[s]);                                                 // frees the smem slot once these MMAs retire
+        if ((i % Cfg::CHUNK_KB) == Cfg::CHUNK_KB - 1 || i == num_kb - 1) umma_commit(&tmem_full[ab]);   // chunk accumulator complete
       }
-      umma_commit(tmem_full);                                                       // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
     const int q = warp & 3;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const int64_t row = (int64_t)m0 + q * 32 + lane;
     const bool row_ok = row < M;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= N) break;                                                      // warp-uniform
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (!row_ok) continue;
+    const int num_chunks = (num_kb + Cfg::CHUNK_KB - 1) / Cfg::CHUNK_KB;
+    float acc[BN];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int n = n0 + c0 + g * 4;
-        if (n >= N) break;
-        float4 v = make_float4(__uint_as_float(r[g * 4]), __uint_as_float(r[g * 4 + 1]), __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3]));
-        if (ep.atomic) {
-          float* c = (float*)ep.C.p + row * ep.C.ld + n;
-          atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
-          continue;
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int ch = 0; ch < num_chunks; ++ch) {
+      const int ab = ch & (Cfg::ACC_BUFS - 1);
+      mbar_wait(&tmem_full[ab], (ch / Cfg::ACC_BUFS) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[ab])) : "memory");
+    }
+    if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < BN / 4; ++g) {
+        const int n = n0 + g * 4;
+        if (n < N) {
+          float4 v = make_float4(acc[g * 4], acc[g * 4 + 1], acc[g * 4 + 2], acc[g * 4 + 3]);
+          if (ep.atomic) {
+            float* c = (float*)ep.C.p + row * ep.C.ld + n;
+            atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
+          } else {
+            if (ep.bias) { const float4 b = __ldg((const float4*)(ep.bias + n)); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+            if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (ep.mask_src.p) {
+              const float4 mk = ld4(ep.mask_src, row, n);
+              v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+            }
+            if (ep.accumulate) { const float4 o = ld4(ep.C, row, n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            st4(ep.C, row, n, v);
+          }
         }
-        if (ep.bias) { const float4 b = __ldg((const float4*)(ep.bias + n)); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
-        if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        if (ep.mask_src.p) {
-          const float4 mk = ld4(ep.mask_src, row, n);
-          v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
-        }
-        if (ep.accumulate) { const float4 o = ld4(ep.C, row, n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-        st4(ep.C, row, n, v);
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, BN < 32 ? 32 : BN); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -284,7 +312,7 @@ inline PFN_encodeTiled get_encode_fn() {
 struct TcOperand {
   const void* base; int64_t plane_elems; int ld; int inner, outer;
 };
-inline int make_operand_map(CUtensorMap* map, int kind, const TcOperand& o, int box_inner, int box_outer) {
+inline int make_operand_map(CUtensorMap* map, int kind, const TcOperand& o, int box_inner, int box_outer, bool mn_major) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return FB200_ECUDA;
   const int es = kind == 0 ? 2 : 4;
@@ -295,7 +323,7 @@ inline int make_operand_map(CUtensorMap* map, int kind, const TcOperand& o, int 
   cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)o.base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, (kind == 1 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? FB200_OK : FB200_ECUDA;
 }
 
@@ -312,9 +340,9 @@ template <int KIND, int A_MN, int B_MN, int BN>
 inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   using Cfg = TcCfg<KIND, BN>;
   CUtensorMap ma, mb;
-  int rc = make_operand_map(&ma, KIND, g.A, A_MN ? Cfg::EPC : Cfg::BK, A_MN ? Cfg::BK : TC_BM);
+  int rc = make_operand_map(&ma, KIND, g.A, A_MN ? Cfg::EPC : Cfg::BK, A_MN ? Cfg::BK : TC_BM, A_MN);
   if (rc != FB200_OK) return rc;
-  rc = make_operand_map(&mb, KIND, g.B, B_MN ? Cfg::EPC : Cfg::BK, B_MN ? Cfg::BK : BN);
+  rc = make_operand_map(&mb, KIND, g.B, B_MN ? Cfg::EPC : Cfg::BK, B_MN ? Cfg::BK : BN, B_MN);
   if (rc != FB200_OK) return rc;
   static bool attr_set = false;                   // idempotent; a benign race sets it twice
   auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN>;
@@ -370,7 +398,7 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__
 inline size_t tc_operand_bytes(int kind, int64_t rows, int cols) { return (size_t)rows * cols * (kind == 0 ? 2 : 8); }
 inline int tc_gemm_workspace_bytes(int layout, int engine, int M, int N, int K, size_t* bytes) {
   if (engine != 1 && engine != 2) return FB200_EBADARG;
-  if (!tc_shape_ok(M, N, K) || M % 4) return FB200_EUNSUPPORTED;
+  if (!tc_shape_ok(M, N, K) || (layout == 2 && M % 8)) return FB200_EUNSUPPORTED;
   const int kind = engine == 2 ? 0 : 1;
   *bytes = ((tc_operand_bytes(kind, layout == 2 ? K : M, layout == 2 ? M : K) + 255) & ~size_t(255)) +
            ((tc_operand_bytes(kind, layout == 0 ? N : K, layout == 0 ? K : N) + 255) & ~size_t(255)) + 256;

@@ -31,6 +31,19 @@ def test_fp32_matches_reference_golden(name):
             assert (g[: 2 * cfg.D] == 0).all(), k
 
 
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith("cfg") or n in ("small14_train", "small16_train", "small17_train", "edge_cross_B33")])
+def test_fp32_tensor_core_path_matches_reference_golden(name):
+    """Same fixtures through the tcgen05 3xTF32 GEMMs (FB200_FLAG_FORCE_TC; normally enabled from B >= 256)."""
+    case = CASES[name]
+    cfg, model = build_model(case, "fp32", flags=_lib.FLAG_FORCE_TC)
+    logits, loss, grads, dx = run_autograd(model, cfg, case)
+    worst = parity.check_against_golden(name, case, logits, loss, grads, dx, tol=parity.FP32_TOL)
+    print(f"{name}: worst rel err {worst:.2e} (3xTF32 tensor-core path)")
+    for k, g in grads.items():
+        if g is not None and k.endswith(("in_proj_weight", "in_proj_bias")):
+            assert (g[: 2 * cfg.D] == 0).all(), k
+
+
 @pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith("cfg")])
 def test_bf16_matches_reference_golden(name):
     """bf16 operands, fp32 accumulation: logits / loss within 2e-2 of the fp32 reference and

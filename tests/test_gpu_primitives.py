@@ -96,3 +96,47 @@ def test_metablock_fwd(B, N):
     _lib.check(L.fb200_metablock_fwd(*[vp(t) for t in ts], B, N, vp(y), vp(st), None))
     torch.cuda.synchronize()
     assert parity.rel_err(y.cpu().numpy(), ref) < 1e-5
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 512), (1024, 512, 2048), (512, 2048, 1024), (200, 136, 72), (40, 512, 512)])
+def test_tcgen05_gemm_all_layouts(engine, layout, M, N, K):
+    """tcgen05 GEMM (engine 1 = 3xTF32 fp32-strict, 2 = bf16) on K-major and MN-major operands,
+    ragged tiles included, with bias + ReLU + accumulate in the epilogue."""
+    rng = np.random.default_rng(M + N + K + layout)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    A = torch.from_numpy(a if layout != 2 else np.ascontiguousarray(a.T)).cuda()
+    Bm = torch.from_numpy(np.ascontiguousarray(b.T) if layout == 0 else b).cuda()
+    Cc = torch.full((M, N), 0.5, device="cuda")
+    L = _lib.lib()
+    wsz = Ct.c_size_t(0)
+    _lib.check(L.fb200_gemm_workspace_bytes(layout, engine, M, N, K, Ct.byref(wsz)))
+    ws = torch.empty(wsz.value, dtype=torch.uint8, device="cuda")
+    _lib.check(L.fb200_gemm(layout, engine, M, N, K, vp(A), A.shape[1], vp(Bm), Bm.shape[1], vp(Cc), N, vp(torch.from_numpy(bias).cuda()), 1, 1,
+                            vp(ws), ws.numel(), None))
+    torch.cuda.synchronize()
+    if engine == 2:
+        q = lambda x: torch.from_numpy(x).bfloat16().double().numpy()
+        ref = q(a) @ q(b)
+    else:
+        ref = a.astype(np.float64) @ b.astype(np.float64)
+    ref = np.maximum(ref + bias, 0) + 0.5
+    assert parity.rel_err(Cc.cpu().numpy(), ref) < (3e-6 if engine == 1 else 1e-5)
+
+
+def test_tcgen05_split_k_weight_gradient():
+    """dW-shaped TN GEMM with the reduction over a long batch: split-K + fp32 atomics."""
+    M, N, K = 512, 512, 8192
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((K, M)).astype(np.float32); b = rng.standard_normal((K, N)).astype(np.float32)
+    A, Bm = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    Cc = torch.empty(M, N, device="cuda")
+    L = _lib.lib(); wsz = Ct.c_size_t(0)
+    _lib.check(L.fb200_gemm_workspace_bytes(2, 1, M, N, K, Ct.byref(wsz)))
+    ws = torch.empty(wsz.value, dtype=torch.uint8, device="cuda")
+    _lib.check(L.fb200_gemm(2, 1, M, N, K, vp(A), M, vp(Bm), N, vp(Cc), N, None, 0, 0, vp(ws), ws.numel(), None))
+    torch.cuda.synchronize()
+    assert parity.rel_err(Cc.cpu().numpy(), a.astype(np.float64).T @ b.astype(np.float64)) < 3e-6

@@ -53,7 +53,7 @@ def main():
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"engine {engine} layout {layout} M {M} N {N} K {K} {extra}: rel err {err:.3e}  {ms * 1e3:.1f} us incl. operand conversion  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
-    tol = 2e-6 if engine == 1 else 1e-5
+    tol = 3e-6 if engine == 1 else 1e-5
     sys.exit(0 if err < tol else 1)
 
 
