@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
     ap.add_argument("--dtype", default=None, choices=[None, "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--sweep", default="", help="comma-separated extra per-GPU batch sizes reported under 'sweep'")
     return ap.parse_args()
 
@@ -182,15 +183,28 @@ def main():
         xs, ts, ys = make_pool(Bsz, nb)
         cw = class_weights(ys)
 
+        use_graph = not args.no_graph
+        denoms = [None] * nb
+        if world > 1:                                            # global weighted-CE denominator, static buffers
+            denoms = [torch.zeros(1, device=dev) for _ in range(nb)]
+        graphs = []
+        if use_graph:
+            for j in range(nb):
+                graphs.append(fb.GraphedTrainStep(model, xs[j], ts[j], ys[j], cw, denom=denoms[j]))
+
         def step(i):
             j = i % nb
-            denom = None
-            if world > 1:                                        # global weighted-CE denominator
-                denom = cw[ys[j]].sum().reshape(1)
-                dist.all_reduce(denom)
-            loss, _ = model.forward_loss(xs[j], ts[j], ys[j], cw, denom=denom)
             if world > 1:
-                dist.all_reduce(model.flat_grad)                 # summed: the global denominator already averages
+                denoms[j].copy_(cw[ys[j]].sum().reshape(1))
+                dist.all_reduce(denoms[j])
+            if use_graph:
+                loss = graphs[j].run()
+                flat = graphs[j].flat_grad
+            else:
+                loss, _ = model.forward_loss(xs[j], ts[j], ys[j], cw, denom=denoms[j])
+                flat = model.flat_grad
+            if world > 1:
+                dist.all_reduce(flat)                            # summed: the global denominator already averages
             return loss
 
         for i in range(warm):
@@ -240,6 +254,11 @@ def main():
                 s["x"].copy_(hx[j], non_blocking=True); s["t"].copy_(ht[j], non_blocking=True); s["y"].copy_(hy[j], non_blocking=True)
                 s["ready"].record(copy_stream)
 
+        use_graph = not args.no_graph
+        for s in slots:
+            s["denom"] = torch.zeros(1, device=dev) if world > 1 else None
+            s["graph"] = fb.GraphedTrainStep(m2, s["x"], s["t"], s["y"], cw, denom=s["denom"]) if use_graph else None
+
         def run(n, base):
             cur = torch.cuda.current_stream()
             prefetch(base)
@@ -248,12 +267,14 @@ def main():
                     prefetch(i + 1)
                 s = slots[i % 2]
                 cur.wait_event(s["ready"])
-                denom = None
                 if world > 1:
-                    denom = cw[s["y"]].sum().reshape(1); dist.all_reduce(denom)
-                loss, _ = m2.forward_loss(s["x"], s["t"], s["y"], cw, denom=denom)
+                    s["denom"].copy_(cw[s["y"]].sum().reshape(1)); dist.all_reduce(s["denom"])
+                if use_graph:
+                    loss = s["graph"].run(); flat = s["graph"].flat_grad
+                else:
+                    loss, _ = m2.forward_loss(s["x"], s["t"], s["y"], cw, denom=s["denom"]); flat = m2.flat_grad
                 if world > 1:
-                    dist.all_reduce(m2.flat_grad)
+                    dist.all_reduce(flat)
                 host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)       # D2H read of the step's result
                 s["free"].record(cur)
         for s in slots:
@@ -307,7 +328,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if dtype == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "mechanism": mech, "per_gpu_batch": B, "global_batch": B * world,
-                       "F": F, "V": V, "C": Cn, "D": 512, "heads": 8, "parallelism": f"dp{world}",
+                       "F": F, "V": V, "C": Cn, "D": 512, "heads": 8, "parallelism": f"dp{world}", "launch": "eager" if args.no_graph else "one CUDA graph per train step",
                        "l2": f"inputs rotate over a pool of {nb} batches = {nb * in_bytes / 1e6:.0f} MB (> 126 MB L2 when >= 127); weights ({plive * 4 / 1e6:.1f} MB) stay L2-resident by design"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss": last_loss, "sweep": sweep or None,

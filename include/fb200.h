@@ -136,13 +136,19 @@ int          fb200_list_gemms(const fb200_desc* d, int32_t* out, int cap);
  * masks[site]   : optional uint8 keep-masks ({0,1}, row-major, fb200_dropout_shape); when
  *                 train = 1 and masks == NULL (or masks[site] == NULL) the kernels draw the
  *                 mask from Philox4x32-10 keyed by (seed, offset, site, element)
+ * rng_state     : optional device uint64[2] = {seed, offset}; when non-NULL the kernels read the
+ *                 Philox key from it at run time instead of the immediate seed/offset, so a captured
+ *                 CUDA graph draws fresh masks on every replay (advance it with fb200_rng_advance)
  * logits        : [B,C] fp32 out
  * ws            : fb200_workspace_bytes() bytes, 256-byte aligned; must stay untouched
  *                 between forward and the matching backward (it holds the saved activations) */
 int fb200_head_forward(const fb200_desc* d, const void* const* params,
                        const void* img_feat, const void* text_in,
-                       const uint8_t* const* masks, uint64_t seed, uint64_t offset,
+                       const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
                        void* logits, void* ws, void* stream);
+
+/* rng_state[1] += increment, on `stream` (one tiny kernel; graph-capturable). */
+int fb200_rng_advance(void* rng_state, uint64_t increment, void* stream);
 
 /* dlogits : [B,C] fp32.  grads : flat fp32 buffer of fb200_grad_elems() elements; the call
  * overwrites it (rows of in_proj_weight/bias that belong to W_q/W_k are written as zeros,
@@ -150,7 +156,7 @@ int fb200_head_forward(const fb200_desc* d, const void* const* params,
  * fp32 out, required iff the matching FB200_FLAG_NEED_* bit is set, else may be NULL. */
 int fb200_head_backward(const fb200_desc* d, const void* const* params,
                         const void* img_feat, const void* text_in,
-                        const uint8_t* const* masks, uint64_t seed, uint64_t offset,
+                        const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
                         const void* dlogits, void* grads, void* d_img_feat, void* d_text_in,
                         void* ws, void* stream);
 
@@ -169,7 +175,7 @@ int fb200_cross_entropy(const void* logits, const int64_t* labels, const float* 
 int fb200_head_train_step(const fb200_desc* d, const void* const* params,
                           const void* img_feat, const void* text_in,
                           const int64_t* labels, const float* class_w, const float* denom,
-                          const uint8_t* const* masks, uint64_t seed, uint64_t offset,
+                          const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
                           void* logits, float* loss_out, void* grads,
                           void* d_img_feat, void* d_text_in, void* ws, void* stream);
 

@@ -103,6 +103,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 struct DropSpec {            // one dropout site
   const uint8_t* mask;       // explicit keep-mask [rows, N] or nullptr -> Philox
   uint64_t seed, offset;
+  const uint64_t* state;     // optional device pair {seed, offset} read at run time (CUDA-graph replays advance it)
   float p;                   // drop probability
   int site;
   int active;                // 0: identity
@@ -117,8 +118,10 @@ __device__ __forceinline__ float4 drop_mult4(const DropSpec& d, int64_t row, int
     return make_float4(m.x ? s : 0.f, m.y ? s : 0.f, m.z ? s : 0.f, m.w ? s : 0.f);
   }
   uint64_t g = (uint64_t)(row * N + c) >> 2;
-  uint4 ctr = make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)d.offset, (uint32_t)(d.offset >> 32) ^ ((uint32_t)d.site << 24));
-  uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
+  const uint64_t seed = d.state ? __ldg(d.state) : d.seed;
+  const uint64_t offset = d.state ? __ldg(d.state + 1) : d.offset;
+  uint4 ctr = make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32) ^ ((uint32_t)d.site << 24));
+  uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   uint32_t thr = (uint32_t)fminf(d.p * 4294967296.0f, 4294967040.0f);
   return make_float4(r.x >= thr ? s : 0.f, r.y >= thr ? s : 0.f, r.z >= thr ? s : 0.f, r.w >= thr ? s : 0.f);
 }

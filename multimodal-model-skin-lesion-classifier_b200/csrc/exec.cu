@@ -43,6 +43,7 @@ struct Ctx {
   void* d_img; void* d_txt;
   float* grads;
   const uint8_t* const* masks; uint64_t seed, offset;
+  const uint64_t* rng_state;
   char* ws;
   cudaStream_t st;
   DeviceInfo dev;
@@ -64,7 +65,7 @@ struct Ctx {
   const float* param(int slot, int64_t elem_off = 0) const { return (const float*)params[slot] + elem_off; }
   float* pgrad(int slot, int64_t elem_off = 0) const { return grads + p.goff[slot] + elem_off; }
   DropSpec drop(const Op& o) const {
-    DropSpec s; s.mask = nullptr; s.seed = seed; s.offset = offset; s.p = o.p; s.site = o.site; s.active = 0;
+    DropSpec s; s.mask = nullptr; s.seed = seed; s.offset = offset; s.state = rng_state; s.p = o.p; s.site = o.site; s.active = 0;
     if (p.d.train && o.site >= 0 && o.p > 0.f) { s.active = 1; if (masks && masks[o.site]) s.mask = masks[o.site]; }
     return s;
   }
@@ -194,6 +195,7 @@ static int run_backward(Ctx& c) {
   for (int oi = (int)p.ops.size() - 1; oi >= 0; --oi) {
     const Op& o = p.ops[oi];
     // the gradient of a view that lives inside a fully written buffer counts as written
+    if (o.kind == OP_CAST) continue;                  // format copy of an input: its gradient goes straight to the input (dx_view)
     if (!is_written(o.out)) return FB200_EBADARG;
     switch (o.kind) {
       case OP_CAST: break;
@@ -466,18 +468,28 @@ int fb200_list_gemms(const fb200_desc* d, int32_t* out, int cap) {
   return n < cap ? n : cap;
 }
 
+__global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { state[1] += inc; }
+
+int fb200_rng_advance(void* rng_state, uint64_t increment, void* stream) {
+  if (!rng_state) return FB200_EBADARG;
+  if (!is_device_ptr(rng_state)) return FB200_EUNSUPPORTED;
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint64_t*)rng_state, increment);
+  CUDA_OK(cudaGetLastError());
+  return FB200_OK;
+}
+
 int fb200_head_forward(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
-                       const uint8_t* const* masks, uint64_t seed, uint64_t offset, void* logits, void* ws, void* stream) {
+                       const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state, void* logits, void* ws, void* stream) {
   Plan plan; DeviceInfo dev;
   int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
   if (rc != FB200_OK) return rc;
   if (!logits) return FB200_EBADARG;
-  Ctx c{plan, params, img_feat, text_in, logits, nullptr, nullptr, nullptr, nullptr, masks, seed, offset, (char*)ws, (cudaStream_t)stream, dev};
+  Ctx c{plan, params, img_feat, text_in, logits, nullptr, nullptr, nullptr, nullptr, masks, seed, offset, (const uint64_t*)rng_state, (char*)ws, (cudaStream_t)stream, dev};
   return run_forward(c);
 }
 
 int fb200_head_backward(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
-                        const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* dlogits, void* grads,
+                        const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state, const void* dlogits, void* grads,
                         void* d_img_feat, void* d_text_in, void* ws, void* stream) {
   Plan plan; DeviceInfo dev;
   int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
@@ -487,7 +499,7 @@ int fb200_head_backward(const fb200_desc* d, const void* const* params, const vo
   if ((d->flags & FB200_FLAG_NEED_DTEXT) && !d_text_in) return FB200_EBADARG;
   Ctx c{plan, params, img_feat, text_in, nullptr, dlogits,
         (d->flags & FB200_FLAG_NEED_DIMG) ? d_img_feat : nullptr, (d->flags & FB200_FLAG_NEED_DTEXT) ? d_text_in : nullptr,
-        (float*)grads, masks, seed, offset, (char*)ws, (cudaStream_t)stream, dev};
+        (float*)grads, masks, seed, offset, (const uint64_t*)rng_state, (char*)ws, (cudaStream_t)stream, dev};
   return run_backward(c);
 }
 
@@ -499,7 +511,7 @@ int fb200_cross_entropy(const void* logits, const int64_t* labels, const float* 
 
 int fb200_head_train_step(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
                           const int64_t* labels, const float* class_w, const float* denom,
-                          const uint8_t* const* masks, uint64_t seed, uint64_t offset,
+                          const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
                           void* logits, float* loss_out, void* grads, void* d_img_feat, void* d_text_in, void* ws, void* stream) {
   Plan plan; DeviceInfo dev;
   int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
@@ -512,7 +524,7 @@ int fb200_head_train_step(const fb200_desc* d, const void* const* params, const 
   float* dlog = (float*)(w + plan.ws_bytes - (((size_t)d->B * d->C * sizeof(float) + 255) & ~size_t(255)) - 256);
   Ctx c{plan, params, img_feat, text_in, logits, dlog,
         (d->flags & FB200_FLAG_NEED_DIMG) ? d_img_feat : nullptr, (d->flags & FB200_FLAG_NEED_DTEXT) ? d_text_in : nullptr,
-        (float*)grads, masks, seed, offset, w, (cudaStream_t)stream, dev};
+        (float*)grads, masks, seed, offset, (const uint64_t*)rng_state, w, (cudaStream_t)stream, dev};
   rc = run_forward(c);
   if (rc != FB200_OK) return rc;
   rc = ce_launch(logits, labels, class_w, denom, d->B, d->C, loss_out, dlog, c.st);
@@ -557,7 +569,7 @@ int fb200_ln_relu_dropout_fwd(const float* x, const float* gamma, const float* b
   if (!is_device_ptr(x)) return FB200_EUNSUPPORTED;
   DeviceInfo dev; int rc = get_device_info(dev); if (rc != FB200_OK) return rc;
   LnrdArgs a{}; a.x = make_ref((void*)x, N); a.y = make_ref(y, N); a.gamma = gamma; a.beta = beta; a.stats = stats;
-  a.drop.mask = mask; a.drop.seed = seed; a.drop.offset = offset; a.drop.p = p; a.drop.site = site; a.drop.active = (train && p > 0.f) ? 1 : 0;
+  a.drop.mask = mask; a.drop.seed = seed; a.drop.offset = offset; a.drop.state = nullptr; a.drop.p = p; a.drop.site = site; a.drop.active = (train && p > 0.f) ? 1 : 0;
   a.B = B; a.N = N;
   const int grid = row_grid_for(B, N, dev.num_sms);
   cudaStream_t st = (cudaStream_t)stream;
@@ -578,7 +590,7 @@ int fb200_ln_relu_dropout_bwd(const float* x, const float* y, const float* gamma
   CUDA_OK(cudaMemsetAsync(dbeta, 0, N * sizeof(float), st));
   LnrdArgs a{}; a.x = make_ref((void*)x, N); a.y = make_ref((void*)y, N); a.dy = make_ref((void*)dy, N); a.dx = make_ref(dx, N);
   a.gamma = gamma; a.stats = (float*)stats; a.dgamma = dgamma; a.dbeta = dbeta;
-  a.drop.mask = nullptr; a.drop.p = p; a.drop.active = (train && p > 0.f) ? 1 : 0; a.B = B; a.N = N;
+  a.drop.mask = nullptr; a.drop.state = nullptr; a.drop.p = p; a.drop.active = (train && p > 0.f) ? 1 : 0; a.B = B; a.N = N;
   const int grid = row_grid_for(B, N, dev.num_sms);
 #define CALL(NV, TPR) lnrd_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, st>>>(a)
   FB200_ROW_DISPATCH(N, CALL);

@@ -379,7 +379,12 @@ inline int tc_launch_major(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
 
 // Shapes the tcgen05 path takes: 16-byte global strides (K, N multiples of 8) - ragged M/N/K
 // tile edges are handled by TMA zero fill and epilogue predication.
-inline bool tc_shape_ok(int M, int N, int K) { return M >= 1 && N >= 8 && K >= 8 && N % 8 == 0 && K % 8 == 0; }
+inline bool tc_shape_ok(int layout, int M, int N, int K) {
+  if (M < 1 || N < 8 || K < 1 || N % 8) return false;
+  if (layout == 0) return K % 8 == 0;                 // A [M,K], B [N,K]
+  if (layout == 1) return K % 8 == 0;                 // A [M,K], B [K,N]
+  return M % 8 == 0;                                  // A [K,M], B [K,N]: the reduction length is free
+}
 
 inline int launch_tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   if (g.kind == 0) return tc_launch_major<0, 128>(g, num_sms, st);
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__
 inline size_t tc_operand_bytes(int kind, int64_t rows, int cols) { return (size_t)rows * cols * (kind == 0 ? 2 : 8); }
 inline int tc_gemm_workspace_bytes(int layout, int engine, int M, int N, int K, size_t* bytes) {
   if (engine != 1 && engine != 2) return FB200_EBADARG;
-  if (!tc_shape_ok(M, N, K) || (layout == 2 && M % 8)) return FB200_EUNSUPPORTED;
+  if (!tc_shape_ok(layout, M, N, K)) return FB200_EUNSUPPORTED;
   const int kind = engine == 2 ? 0 : 1;
   *bytes = ((tc_operand_bytes(kind, layout == 2 ? K : M, layout == 2 ? M : K) + 255) & ~size_t(255)) +
            ((tc_operand_bytes(kind, layout == 0 ? N : K, layout == 0 ? K : N) + 255) & ~size_t(255)) + 256;

@@ -10,6 +10,6 @@ or, keeping the reference's own import line (train_pad_20.py:6):
 from . import _lib
 from ._lib import Fb200Error
 from .head import FusedCrossEntropyLoss, FusedHeadFunction, cross_entropy, make_desc
-from .model import MultimodalModel
+from .model import GraphedTrainStep, MultimodalModel
 
-__all__ = ["MultimodalModel", "FusedCrossEntropyLoss", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]
+__all__ = ["MultimodalModel", "GraphedTrainStep", "FusedCrossEntropyLoss", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]

@@ -69,10 +69,11 @@ def lib():
     sig("fb200_dropout_shape", i32, dp, i32, C.POINTER(i64), C.POINTER(i64))
     sig("fb200_algorithmic_work", i32, dp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64))
     sig("fb200_launch_count", i32, dp, C.POINTER(i32), C.POINTER(i32))
-    sig("fb200_head_forward", i32, dp, pp, vp, vp, pp, u64, u64, vp, vp, vp)
-    sig("fb200_head_backward", i32, dp, pp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp)
+    sig("fb200_head_forward", i32, dp, pp, vp, vp, pp, u64, u64, vp, vp, vp, vp)
+    sig("fb200_rng_advance", i32, vp, u64, vp)
+    sig("fb200_head_backward", i32, dp, pp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp)
     sig("fb200_cross_entropy", i32, vp, vp, vp, vp, i32, i32, vp, vp, vp)
-    sig("fb200_head_train_step", i32, dp, pp, vp, vp, vp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp)
+    sig("fb200_head_train_step", i32, dp, pp, vp, vp, vp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp)
     f32 = C.c_float
     sig("fb200_gemm", i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, vp, sz, vp)
     sig("fb200_gemm_workspace_bytes", i32, i32, i32, i32, i32, i32, C.POINTER(sz))
@@ -107,14 +108,37 @@ def param_shape(desc: Desc, slot: int):
     return (r.value, c.value) if c.value else (r.value,)
 
 
+_FIELDS = [f for f, _ in Desc._fields_]
+_ws_cache, _layout_cache = {}, {}
+
+
+def desc_key(desc: Desc):
+    return tuple(getattr(desc, f) for f in _FIELDS)
+
+
 def workspace_bytes(desc: Desc) -> int:
+    key = desc_key(desc)
+    hit = _ws_cache.get(key)
+    if hit is not None:
+        return hit
     n = C.c_size_t()
     check(lib().fb200_workspace_bytes(C.byref(desc), C.byref(n)), "fb200_workspace_bytes")
+    _ws_cache[key] = n.value
     return n.value
 
 
 def grad_layout(desc: Desc):
-    """(total elements, {slot: offset}) of the flat gradient buffer for live slots."""
+    """(total elements, {slot: offset}) of the flat gradient buffer for live slots (cached per descriptor)."""
+    key = desc_key(desc)[:10] + (0, 0, 0, 0)          # the layout depends on the model shape only
+    hit = _layout_cache.get(key)
+    if hit is not None:
+        return hit
+    r = _grad_layout_uncached(desc)
+    _layout_cache[key] = r
+    return r
+
+
+def _grad_layout_uncached(desc: Desc):
     L = lib()
     total = L.fb200_grad_elems(C.byref(desc))
     if total < 0:

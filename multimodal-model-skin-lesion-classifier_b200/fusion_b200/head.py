@@ -91,7 +91,7 @@ class FusedHeadFunction(torch.autograd.Function):
         logits = torch.empty(B, cfg["C"], dtype=torch.float32, device=x.device)
         marr, mkeep = _mask_table(masks)
         with torch.cuda.device(x.device):
-            _lib.check(L.fb200_head_forward(C.byref(desc), table.arr, _ptr(x), _ptr(t), marr, seed, offset,
+            _lib.check(L.fb200_head_forward(C.byref(desc), table.arr, _ptr(x), _ptr(t), marr, seed, offset, None,
                                             _ptr(logits), _ptr(ws), _stream()), "fb200_head_forward")
         ctx.desc, ctx.table, ctx.ws, ctx.x, ctx.t = desc, table, ws, x, t
         ctx.marr, ctx.mkeep, ctx.seed, ctx.offset = marr, mkeep, seed, offset
@@ -110,7 +110,7 @@ class FusedHeadFunction(torch.autograd.Function):
         d_img = torch.empty_like(ctx.x) if ctx.need[0] else None
         d_txt = torch.empty_like(ctx.t) if ctx.need[1] else None
         with torch.cuda.device(dl.device):
-            _lib.check(L.fb200_head_backward(C.byref(desc), ctx.table.arr, _ptr(ctx.x), _ptr(ctx.t), ctx.marr, ctx.seed, ctx.offset,
+            _lib.check(L.fb200_head_backward(C.byref(desc), ctx.table.arr, _ptr(ctx.x), _ptr(ctx.t), ctx.marr, ctx.seed, ctx.offset, None,
                                              _ptr(dl), _ptr(flat), _ptr(d_img), _ptr(d_txt), _ptr(ctx.ws), _stream()),
                        "fb200_head_backward")
         grads = []

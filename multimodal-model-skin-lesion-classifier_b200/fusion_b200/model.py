@@ -98,6 +98,7 @@ class MultimodalModel(nn.Module):
         self._slot_names = _lib.param_names()
         self._step = 0                       # Philox offset: advances once per training forward
         self._injected_masks = None          # tests: {site: uint8 keep-mask}
+        self._rng_state = None               # device {seed, offset} for the fused / graph-captured train step
 
     # ------------------------------------------------------------------ plumbing
     def _cfg(self, train):
@@ -178,11 +179,16 @@ class MultimodalModel(nn.Module):
         y = label.to(device=dev, dtype=torch.int64).contiguous()
         w = None if class_weights is None else class_weights.to(device=dev, dtype=torch.float32).contiguous()
         marr, _keep = _mask_table(self._injected_masks)
+        if self._rng_state is None or self._rng_state.device != dev:
+            # Philox key lives on the device so that a captured CUDA graph draws new masks on every replay
+            self._rng_state = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 1], dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.fb200_head_train_step(C.byref(desc), table.arr, _ptr(x), _ptr(t), _ptr(y), _ptr(w), _ptr(denom), marr,
-                                               torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, self._step,
+                                               0, 0, _ptr(self._rng_state),
                                                _ptr(logits), _ptr(loss_out), _ptr(flat), _ptr(d_img), _ptr(d_txt), _ptr(ws), _stream()),
                        "fb200_head_train_step")
+            if train:
+                _lib.check(L.fb200_rng_advance(_ptr(self._rng_state), 1, _stream()), "fb200_rng_advance")
         for s, p in enumerate(params):
             if p is None or s not in offs or not p.requires_grad:
                 continue
@@ -197,3 +203,34 @@ class MultimodalModel(nn.Module):
         if need_dtxt:
             text_in.backward(d_txt)
         return loss_out[0], logits
+
+
+class GraphedTrainStep:
+    """One CUDA graph = one whole train step of the head (weight prep, forward, weighted CE,
+    backward, Philox advance) on fixed device buffers: ~70 kernel launches become one
+    cudaGraphLaunch, which is what makes small batches (B = 32: microseconds of GPU work)
+    anything but launch-bound.  Gradients land in ``model.flat_grad`` / the parameters' ``.grad``
+    views, the loss in ``self.loss`` (device scalar), logits in ``self.logits``.
+
+        step = GraphedTrainStep(model, x, meta, y, class_weights)   # x, meta, y: static CUDA tensors
+        x.copy_(next_x); ...; step.run(); optimizer.step()
+    """
+
+    def __init__(self, model, image, text_metadata, label, class_weights=None, denom=None, warmup=2):
+        if any(p.requires_grad for p in model.image_encoder.parameters()):
+            raise ValueError("GraphedTrainStep captures the head only: use a frozen backbone (or feed features)")
+        self.model, self.args = model, (image, text_metadata, label, class_weights, denom)
+        side = torch.cuda.Stream(device=image.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                model.forward_loss(*self.args)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.logits = model.forward_loss(*self.args)
+        self.flat_grad = model.flat_grad
+
+    def run(self):
+        self.graph.replay()
+        return self.loss

@@ -70,6 +70,7 @@ class Var:
 class Tape:
     def __init__(self):
         self.steps = []
+        self.relu_margin = np.inf      # smallest |pre-activation| any ReLU saw (ties make gradients discontinuous)
 
     def push(self, fn):
         self.steps.append(fn)
@@ -101,6 +102,8 @@ def linear(t, x, W, b):
 
 def relu(t, x):
     y = Var(np.maximum(x.v, 0))
+    if x.v.size:
+        t.relu_margin = min(t.relu_margin, float(np.abs(x.v).min()))
 
     def bwd():
         if y.grad is not None:
@@ -543,7 +546,7 @@ def head_forward_backward(cfg, params, img_feat, text_in, labels=None, class_w=N
     else:
         raise ValueError(f"Attention mechanism '{m}' not implemented.")
 
-    out = {"logits": logits.v, "loss": None, "grads": None, "d_img_feat": None, "d_text_in": None}
+    out = {"logits": logits.v, "loss": None, "grads": None, "d_img_feat": None, "d_text_in": None, "relu_margin": t.relu_margin}
     if labels is None and dlogits is None:
         return out
     if dlogits is None:

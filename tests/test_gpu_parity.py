@@ -92,12 +92,19 @@ def test_fused_train_step_equals_autograd_path(name):
 def test_fp32_against_oracle_on_fresh_inputs(mech, F, V, Cn, B):
     """Bigger / ragged batches than the fixtures: oracle (float64) on the same seeded inputs."""
     kw = dict(mechanism=mech, F=F, V=V, C=Cn)
-    case = dict(cfg=kw, B=B, seed=4242 + B, train=True, full_grads=False)
+    # A ReLU pre-activation within rounding distance of zero makes the gradient of that sample
+    # discontinuous (observed: B=257, one row flips at |z| ~ 1e-7).  Such numerical ties say nothing
+    # about parity, so draw the inputs again until the oracle reports a safe margin.
+    for attempt in range(8):
+        case = dict(cfg=kw, B=B, seed=4242 + B + 1000 * attempt, train=True, full_grads=False)
+        cfg = C.make_cfg(kw)
+        params = C.gen_params(cfg, case["seed"], np.float64)
+        x, tin, labels, cw, masks = C.gen_inputs(cfg, B, case["seed"], True, np.float64)
+        o = ho.head_forward_backward(cfg, params, x, tin, labels, cw, masks, need_input_grad=True)
+        if o["relu_margin"] > 2e-5:
+            break
     cfg, model = build_model(case, "fp32")
     logits, loss, grads, dx = run_autograd(model, cfg, case)
-    params = C.gen_params(cfg, case["seed"], np.float64)
-    x, tin, labels, cw, masks = C.gen_inputs(cfg, B, case["seed"], True, np.float64)
-    o = ho.head_forward_backward(cfg, params, x, tin, labels, cw, masks, need_input_grad=True)
     assert parity.rel_err(logits, o["logits"]) < parity.FP32_TOL
     assert abs(loss - o["loss"]) < parity.FP32_TOL * abs(o["loss"])
     for k, g in o["grads"].items():
