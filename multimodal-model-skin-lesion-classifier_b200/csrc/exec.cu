@@ -88,8 +88,10 @@ static TcOperand tc_operand(const TRef& r, int inner, int outer) {
 }
 
 // ------------------------------------------------------------------------------- forward
-static TRef wprep_ref(const Ctx& c, const WPrep& w) {
-  return make_ref(c.ws + w.off, w.cols, c.p.fmt, (int64_t)w.rows * w.cols);
+// The [N,K] weight operand of a tcgen05 Linear: the bf16 copy in the workspace, or the fp32 master itself.
+static TRef weight_operand(const Ctx& c, const Op& o) {
+  if (o.wprep >= 0) { const WPrep& w = c.p.wprep[o.wprep]; return make_ref(c.ws + w.off, w.cols, c.p.fmt, (int64_t)w.rows * w.cols); }
+  return make_ref((void*)c.param(o.w_slot, (int64_t)o.w_row0 * o.in0.cols), o.in0.cols, FMT_F32);
 }
 
 static int run_forward(Ctx& c) {
@@ -115,7 +117,7 @@ static int run_forward(Ctx& c) {
           TcGemmArgs t{};
           t.kind = p.fmt == FMT_BF16 ? 0 : 1; t.a_mn = 0; t.b_mn = 0;
           t.A = tc_operand(c.value(o.in0), o.in0.cols, B);
-          t.B = tc_operand(wprep_ref(c, p.wprep[o.wprep]), o.in0.cols, o.out.cols);
+          t.B = tc_operand(weight_operand(c, o), o.in0.cols, o.out.cols);
           t.M = B; t.N = o.out.cols; t.K = o.in0.cols;
           t.ep.C = c.value(o.out); t.ep.bias = c.param(o.b_slot, o.w_row0); t.ep.relu = o.relu; t.ep.mask_src.p = nullptr;
           t.ep.accumulate = 0; t.ep.atomic = 0; t.ep.colsum = nullptr; t.allow_split = 0;
@@ -192,6 +194,7 @@ static int run_backward(Ctx& c) {
     return true;
   };
 
+  std::vector<ColsumSeg> colsums;
   for (int oi = (int)p.ops.size() - 1; oi >= 0; --oi) {
     const Op& o = p.ops[oi];
     // the gradient of a view that lives inside a fully written buffer counts as written
@@ -213,20 +216,12 @@ static int run_backward(Ctx& c) {
           int rc = launch_tc_gemm(t, c.dev.num_sms, c.st);
           if (rc != FB200_OK) return rc;
           pwritten[o.w_slot] = 1;
-          {   // db[N] += column sums of dY
-            const TRef dy = c.grad(o.out);
-            float* db = c.pgrad(o.b_slot, o.w_row0);
-            const int grid = row_grid_for(B, N, c.dev.num_sms);
-#define CALL(NV, TPR) colsum_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(dy, B, N, db)
-            FB200_ROW_DISPATCH(N, CALL);
-#undef CALL
-            CUDA_OK(cudaGetLastError());
-          }
+          colsums.push_back(ColsumSeg{c.grad(o.out), N, c.pgrad(o.b_slot, o.w_row0)});   // db: batched after the loop
           if (grad_wanted(o.dx_view)) {
             // dX[B,K] (+)= dY W : W read MN-major from the same operand-format copy the forward used
             TcGemmArgs h{};
             h.kind = kind; h.a_mn = 0; h.b_mn = 1;
-            h.A = tc_operand(c.grad(o.out), N, B); h.B = tc_operand(wprep_ref(c, p.wprep[o.wprep]), K, N);
+            h.A = tc_operand(c.grad(o.out), N, B); h.B = tc_operand(weight_operand(c, o), K, N);
             h.M = B; h.N = K; h.K = N;
             h.ep.C = c.grad(o.dx_view); h.ep.bias = nullptr; h.ep.relu = 0; h.ep.mask_src.p = nullptr;
             if (p.acts[o.in0.buf].relu_out) h.ep.mask_src = c.value(o.in0);
@@ -309,6 +304,14 @@ static int run_backward(Ctx& c) {
       } break;
       default: return FB200_EBADARG;
     }
+    CUDA_OK(cudaGetLastError());
+  }
+  // bias gradients of all tcgen05 Linears: the dY buffers are still intact in the workspace
+  for (size_t base = 0; base < colsums.size(); base += 24) {
+    ColsumBatch cb{}; cb.B = B; cb.nseg = 0;
+    for (size_t i = base; i < colsums.size() && cb.nseg < 24; ++i) cb.seg[cb.nseg++] = colsums[i];
+    int gx = (B + 31) / 32; if (gx > 2 * c.dev.num_sms / cb.nseg + 1) gx = 2 * c.dev.num_sms / cb.nseg + 1; if (gx < 1) gx = 1;
+    colsum_batch_kernel<<<dim3(gx, cb.nseg), 256, 0, c.st>>>(cb);
     CUDA_OK(cudaGetLastError());
   }
   // inputs nobody differentiated through still owe the caller a defined gradient
@@ -436,13 +439,16 @@ int fb200_launch_count(const fb200_desc* d, int* forward, int* backward) {
   int f = 0, b = 0;
   const bool need_dimg = d->flags & FB200_FLAG_NEED_DIMG, need_dtxt = d->flags & FB200_FLAG_NEED_DTEXT;
   f += (int)((p.wprep.size() + 31) / 32);
+  int ntc = 0;
   for (auto& o : p.ops) {
     f += 1;
     if (o.kind == OP_LINEAR) {
       const int ext = p.acts[o.dx_view.buf].ext;
-      b += 1 + (o.engine == 1 ? 1 : 0) + ((ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) ? 1 : 0);
+      if (o.engine == 1) ++ntc;
+      b += 1 + ((ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) ? 1 : 0);
     } else if (o.kind != OP_CAST) b += 1;
   }
+  b += (ntc + 23) / 24;
   if (forward) *forward = f;
   if (backward) *backward = b;
   return FB200_OK;

@@ -104,7 +104,7 @@ struct Builder {
     // class count stay on the FFMA kernel)
     o.engine = (p.use_tc && x.cols % 8 == 0 && out_cols % 8 == 0 && x.cols >= 32 && out_cols >= 32) ? 1 : 0;
     const int ext = p.acts[x.buf].ext;
-    if (o.engine == 1 && ext != 0) {   // TMA reads operand-format data: convert the fp32 input once
+    if (o.engine == 1 && ext != 0 && p.fmt == FMT_BF16) {   // bf16 operands: convert the fp32 input once (fp32-strict reads it as is)
       if (cast_of[ext] < 0) {
         cast_of[ext] = new_act(p.acts[x.buf].cols);
         Op c; c.kind = OP_CAST; c.in0 = whole(x.buf); c.out = whole(cast_of[ext]);
@@ -114,7 +114,7 @@ struct Builder {
       x = xc;
     }
     o.in0 = x;
-    if (o.engine == 1) {
+    if (o.engine == 1 && p.fmt == FMT_BF16) {       // bf16 copy of W, refreshed at the top of every forward
       int found = -1;
       for (size_t i = 0; i < p.wprep.size(); ++i) if (p.wprep[i].slot == w_slot && p.wprep[i].row0 == w_row0) found = (int)i;
       if (found < 0) { p.wprep.push_back(WPrep{w_slot, w_row0, out_cols, x.cols, 0}); found = (int)p.wprep.size() - 1; }
@@ -194,7 +194,7 @@ int build_plan(const fb200_desc& d, Plan& p) {
   // engine policy: bf16 always rides the tensor cores; fp32 switches to the 3xTF32 tensor path once the
   // batch is large enough to be compute-bound (below that the exact FFMA kernel streams fp32 weights once)
   p.use_tc = !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B >= 256);
-  p.fmt = d.dtype == FB200_BF16 ? FMT_BF16 : (p.use_tc ? FMT_PAIR : FMT_F32);
+  p.fmt = d.dtype == FB200_BF16 ? FMT_BF16 : FMT_F32;    // fp32-strict keeps everything fp32 in memory (hi/lo split happens in smem)
 
   Builder b(p);
   const int D = d.D;

@@ -517,6 +517,31 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) colsum_kernel(TRef x, int B, i
   cta_colsum_atomic<NV, TPR>(G, acc, N, dst, red);
 }
 
+
+// Bias gradients of every tcgen05 Linear of the step in ONE launch: segment = (dY view, N, db).
+// Thread t owns 4 columns of its segment and walks the rows with a CTA-wide stride, so each
+// access is a coalesced 128-bit load; partial sums go out as fp32 atomics (db is pre-zeroed).
+struct ColsumSeg { TRef x; int N; float* dst; };
+struct ColsumBatch { ColsumSeg seg[24]; int nseg; int B; };
+__global__ void __launch_bounds__(256) colsum_batch_kernel(const ColsumBatch a) {
+  const ColsumSeg sg = a.seg[blockIdx.y];
+  const int nv = sg.N / 4;                                   // float4 columns
+  const int lanes = nv < 256 ? nv : 256;                     // threads across one row
+  const int rows_per_iter = 256 / lanes;
+  const int t = threadIdx.x;
+  if (t >= lanes * rows_per_iter) return;
+  const int r_off = t / lanes, c_lane = t % lanes;
+  for (int cg = c_lane; cg < nv; cg += lanes) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + r_off; r < a.B; r += (int64_t)gridDim.x * rows_per_iter) {
+      const float4 v = ld4(sg.x, r, cg * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float* d = sg.dst + cg * 4;
+    atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+  }
+}
+
 // ---- launch helpers ------------------------------------------------------------------
 inline int row_grid(int B, int num_sms) {
   int ctas = (B + ROW_WARPS * 4 - 1) / (ROW_WARPS * 4);      // aim at >= 4 rows per warp

@@ -2,9 +2,11 @@
 //
 //   C[M,N] (+)= A x B      fp32 accumulation in tensor memory
 //   kind bf16   : tcgen05.mma.kind::f16, bf16 operands
-//   kind tf32x3 : tcgen05.mma.kind::tf32, every operand is a (hi, lo) pair of fp32 planes
-//                 (hi = tf32-rounded value, lo = exact remainder); three MMAs per k-slice
-//                 hi*hi + lo*hi + hi*lo reproduce fp32 products to ~2^-21 (fp32-strict mode).
+//   kind tf32x3 : fp32-strict.  TMA lands raw fp32 tiles in shared memory; the four epilogue warps
+//                 split every tile IN PLACE into hi = tf32(x) and lo = x - hi (second buffer, same
+//                 swizzled offsets), and the MMA thread issues three tcgen05.mma.kind::tf32 per
+//                 k-slice (hi*hi + lo*hi + hi*lo): fp32 products to ~2^-21 while HBM / L2 only ever
+//                 carry 4 bytes per element and no operand is pre-processed in memory.
 //   layouts     : each operand is either K-major (reduction dim contiguous) or MN-major, so
 //                 forward (X W^T), dX (dY W) and dW (dY^T X) all read the SAME row-major
 //                 tensors straight from HBM through TMA - nothing is ever transposed in memory.
@@ -128,13 +130,14 @@ struct TcCfg {
   static constexpr int ESIZE = KIND == 0 ? 2 : 4;
   static constexpr int BK = 128 / ESIZE;                 // elements of K per stage (one 128-byte swizzle row)
   static constexpr int UMMA_K = 32 / ESIZE;              // 16 (bf16) / 8 (tf32)
-  static constexpr int PLANES = KIND == 0 ? 1 : 2;
+  static constexpr int PLANES = KIND == 0 ? 1 : 2;       // smem planes per operand tile (tf32x3: raw/hi + lo)
   static constexpr int A_BYTES = TC_BM * 128;            // one plane of the A tile
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int TMA_BYTES = A_BYTES + B_BYTES;    // bytes TMA delivers per stage (one plane of each)
   static constexpr int STAGES = (KIND == 0) ? (BN <= 128 ? 6 : 4) : (BN <= 128 ? 3 : 2);
   static constexpr int EPC = 128 / ESIZE;                // elements per 128-byte chunk along MN (MN-major operands)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   // The tensor-core accumulator truncates on every accumulate, a bias that grows linearly with the number
   // of MMAs chained into one TMEM accumulator (measured: 3e-5 relative at K = 4096 in 3xTF32).  The
   // fp32-strict kind therefore accumulates at most CHUNK_KB k-blocks (K = 128) in TMEM, and the epilogue
@@ -154,7 +157,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // 128B swizzle needs 1024-byte alignment
   uint64_t* full_bar = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full = empty_bar + Cfg::STAGES;            // [2]
+  uint64_t* split_bar = empty_bar + Cfg::STAGES;            // [STAGES] tf32x3: tile split into hi/lo, ready for the MMA thread
+  uint64_t* tmem_full = split_bar + Cfg::STAGES;            // [2]
   uint64_t* tmem_empty = tmem_full + 2;                     // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
@@ -167,7 +171,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);                     // one arrive per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -184,25 +188,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        mbar_expect_tx(&full_bar[s], Cfg::TMA_BYTES);
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         const int k0 = (kb_begin + i) * Cfg::BK;
+        uint8_t* a_dst = st;
+        uint8_t* b_dst = st + Cfg::PLANES * Cfg::A_BYTES;
+        if (A_MN) {
 #pragma unroll
-        for (int pl = 0; pl < Cfg::PLANES; ++pl) {
-          uint8_t* a_dst = st + pl * Cfg::A_BYTES;
-          uint8_t* b_dst = st + Cfg::PLANES * Cfg::A_BYTES + pl * Cfg::B_BYTES;
-          if (A_MN) {
+          for (int c = 0; c < TC_BM / Cfg::EPC; ++c) tma_load_3d(&map_a, &full_bar[s], a_dst + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, k0, 0);
+        } else {
+          tma_load_3d(&map_a, &full_bar[s], a_dst, k0, m0, 0);
+        }
+        if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < TC_BM / Cfg::EPC; ++c) tma_load_3d(&map_a, &full_bar[s], a_dst + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, k0, pl);
-          } else {
-            tma_load_3d(&map_a, &full_bar[s], a_dst, k0, m0, pl);
-          }
-          if (B_MN) {
-#pragma unroll
-            for (int c = 0; c < BN / Cfg::EPC; ++c) tma_load_3d(&map_b, &full_bar[s], b_dst + c * (Cfg::BK * 128), n0 + c * Cfg::EPC, k0, pl);
-          } else {
-            tma_load_3d(&map_b, &full_bar[s], b_dst, k0, n0, pl);
-          }
+          for (int c = 0; c < BN / Cfg::EPC; ++c) tma_load_3d(&map_b, &full_bar[s], b_dst + c * (Cfg::BK * 128), n0 + c * Cfg::EPC, k0, 0);
+        } else {
+          tma_load_3d(&map_b, &full_bar[s], b_dst, k0, n0, 0);
         }
       }
     }
@@ -220,7 +221,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int chunk = i / Cfg::CHUNK_KB, ab = chunk & (Cfg::ACC_BUFS - 1);
         const bool chunk_first = (i % Cfg::CHUNK_KB) == 0;
         if (chunk_first) { mbar_wait(&tmem_empty[ab], ((chunk / Cfg::ACC_BUFS) & 1) ^ 1); tc_fence_after(); }
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(KIND == 1 ? &split_bar[s] : &full_bar[s], ph);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
@@ -250,7 +251,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float acc[BN];
 #pragma unroll
     for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-    for (int ch = 0; ch < num_chunks; ++ch) {
+    // chunk accumulator (TMEM) -> fp32 registers, then hand the TMEM buffer back to the MMA thread
+    auto promote = [&](int ch) {
       const int ab = ch & (Cfg::ACC_BUFS - 1);
       mbar_wait(&tmem_full[ab], (ch / Cfg::ACC_BUFS) & 1);
       tc_fence_after();
@@ -264,7 +266,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[ab])) : "memory");
+    };
+    int next_promote = 0;
+    if (KIND == 1) {
+      const int t128 = threadIdx.x - 64;                                            // 0..127 over the four warps
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        // elementwise and position preserving, hence oblivious to the swizzle / major of the tile
+#pragma unroll 4
+        for (int v = t128; v < Cfg::TMA_BYTES / 16; v += 128) {
+          const int off = v * 16;
+          float4* hi_p = (float4*)(off < Cfg::A_BYTES ? st + off : st + Cfg::A_BYTES + off);           // B tile starts after both A planes
+          float4* lo_p = (float4*)((uint8_t*)hi_p + (off < Cfg::A_BYTES ? Cfg::A_BYTES : Cfg::B_BYTES));
+          const float4 x = *hi_p;
+          const float4 h = make_float4(tf32_round(x.x), tf32_round(x.y), tf32_round(x.z), tf32_round(x.w));
+          *hi_p = h;
+          *lo_p = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // generic-proxy writes -> visible to tcgen05 (async proxy)
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_bar[s])) : "memory");
+        // promote one chunk behind the split front so the MMA thread never starves
+        if ((i % Cfg::CHUNK_KB) == Cfg::CHUNK_KB - 1 && i / Cfg::CHUNK_KB >= 1) { promote(next_promote); ++next_promote; }
+      }
     }
+    for (; next_promote < num_chunks; ++next_promote) promote(next_promote);
     if (row_ok) {
 #pragma unroll
       for (int g = 0; g < BN / 4; ++g) {
@@ -316,7 +344,7 @@ inline int make_operand_map(CUtensorMap* map, int kind, const TcOperand& o, int 
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return FB200_ECUDA;
   const int es = kind == 0 ? 2 : 4;
-  const int planes = kind == 0 ? 1 : 2;
+  const int planes = 1;                        // tf32x3 reads raw fp32: the hi/lo split happens in shared memory
   if ((((uintptr_t)o.base) & 15) || ((int64_t)o.ld * es) % 16 || (planes == 2 && (o.plane_elems * es) % 16)) return FB200_EALIGN;
   cuuint64_t dims[3] = {(cuuint64_t)o.inner, (cuuint64_t)o.outer, (cuuint64_t)planes};
   cuuint64_t strides[2] = {(cuuint64_t)o.ld * es, (cuuint64_t)(planes == 2 ? o.plane_elems : (int64_t)o.ld * o.outer) * es};
@@ -400,13 +428,14 @@ __global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__
     st4(out, r, c, *(const float4*)(in + r * ld_in + c));
   }
 }
-inline size_t tc_operand_bytes(int kind, int64_t rows, int cols) { return (size_t)rows * cols * (kind == 0 ? 2 : 8); }
+inline size_t tc_operand_bytes(int64_t rows, int cols) { return (size_t)rows * cols * 2; }
 inline int tc_gemm_workspace_bytes(int layout, int engine, int M, int N, int K, size_t* bytes) {
   if (engine != 1 && engine != 2) return FB200_EBADARG;
   if (!tc_shape_ok(layout, M, N, K)) return FB200_EUNSUPPORTED;
-  const int kind = engine == 2 ? 0 : 1;
-  *bytes = ((tc_operand_bytes(kind, layout == 2 ? K : M, layout == 2 ? M : K) + 255) & ~size_t(255)) +
-           ((tc_operand_bytes(kind, layout == 0 ? N : K, layout == 0 ? K : N) + 255) & ~size_t(255)) + 256;
+  *bytes = 256;
+  if (engine == 2)      // bf16 copies of both operands
+    *bytes = ((tc_operand_bytes(layout == 2 ? K : M, layout == 2 ? M : K) + 255) & ~size_t(255)) +
+             ((tc_operand_bytes(layout == 0 ? N : K, layout == 0 ? K : N) + 255) & ~size_t(255)) + 256;
   return FB200_OK;
 }
 inline int tc_gemm_f32(int layout, int engine, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
@@ -414,21 +443,25 @@ inline int tc_gemm_f32(int layout, int engine, int M, int N, int K, const float*
   size_t need = 0;
   int rc = tc_gemm_workspace_bytes(layout, engine, M, N, K, &need);
   if (rc != FB200_OK) return rc;
-  if (!ws || ws_bytes < need || (((uintptr_t)ws) & 255)) return FB200_EBADARG;
   if ((lda % 4) || (ldb % 4) || (ldc % 4) || (((uintptr_t)A) & 15) || (((uintptr_t)B) & 15) || (((uintptr_t)C) & 15)) return FB200_EALIGN;
   const int kind = engine == 2 ? 0 : 1;
-  const int fmt = kind == 0 ? FMT_BF16 : FMT_PAIR;
   const int64_t a_rows = layout == 2 ? K : M; const int a_cols = layout == 2 ? M : K;
   const int64_t b_rows = layout == 0 ? N : K; const int b_cols = layout == 0 ? K : N;
-  char* w = (char*)ws;
-  TRef a_ref = make_ref(w, a_cols, fmt, a_rows * a_cols);
-  TRef b_ref = make_ref(w + ((tc_operand_bytes(kind, a_rows, a_cols) + 255) & ~size_t(255)), b_cols, fmt, b_rows * b_cols);
-  tc_split_kernel<<<296, 256, 0, st>>>(A, a_rows, a_cols, lda, a_ref);
-  tc_split_kernel<<<296, 256, 0, st>>>(B, b_rows, b_cols, ldb, b_ref);
   TcGemmArgs g{};
   g.kind = kind; g.a_mn = layout == 2; g.b_mn = layout != 0;
-  g.A = TcOperand{a_ref.p, a_ref.plane, a_cols, a_cols, (int)a_rows};
-  g.B = TcOperand{b_ref.p, b_ref.plane, b_cols, b_cols, (int)b_rows};
+  if (kind == 0) {
+    if (!ws || ws_bytes < need || (((uintptr_t)ws) & 255)) return FB200_EBADARG;
+    char* w = (char*)ws;
+    TRef a_ref = make_ref(w, a_cols, FMT_BF16);
+    TRef b_ref = make_ref(w + ((tc_operand_bytes(a_rows, a_cols) + 255) & ~size_t(255)), b_cols, FMT_BF16);
+    tc_split_kernel<<<296, 256, 0, st>>>(A, a_rows, a_cols, lda, a_ref);
+    tc_split_kernel<<<296, 256, 0, st>>>(B, b_rows, b_cols, ldb, b_ref);
+    g.A = TcOperand{a_ref.p, 0, a_cols, a_cols, (int)a_rows};
+    g.B = TcOperand{b_ref.p, 0, b_cols, b_cols, (int)b_rows};
+  } else {
+    g.A = TcOperand{A, 0, lda, a_cols, (int)a_rows};
+    g.B = TcOperand{B, 0, ldb, b_cols, (int)b_rows};
+  }
   g.M = M; g.N = N; g.K = K;
   g.ep.C = make_ref(C, ldc, FMT_F32); g.ep.bias = bias; g.ep.relu = relu; g.ep.mask_src.p = nullptr; g.ep.accumulate = accumulate;
   g.ep.atomic = 0; g.ep.colsum = nullptr; g.allow_split = 0;
