@@ -386,14 +386,39 @@ def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype):
     bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm = peaks.get("hbm_gbs", 6650.0)
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    traffic = None
+    try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     if dtype == "fp32":
-        # fp32-strict GEMMs: FFMA pipe peak = 148 SMs x 128 lanes x 2 flop x 1.965 GHz
-        peak, peak_note = 74.4, "fp32 FFMA pipe peak 148 SM x 128 x 2 x 1.965 GHz (SURVEY 8d fp32-strict rule); bf16 tensor peak listed beside it"
+        # fp32-strict GEMMs run as 3 TF32 MMAs per product: peak = cuBLAS TF32 8192^3, measured here, / 3
+        tf32 = measure_tf32_peak(torch, dev)
+        peak = tf32 / 3.0
+        peak_note = (f"cuBLAS TF32 8192^3 measured live = {tf32:.0f} TFLOP/s, / 3 MMAs per fp32-strict product (SURVEY 8d rule); "
+                     f"for scale: fp32 FFMA pipe peak 74.4, dense bf16 sustained {bf16_peak:.0f} ({src})")
     else:
         peak, peak_note = bf16_peak, f"dense bf16 sustained, {src}"
-    return {"bound": "tensor", "kernel": "GEMM family (forward NT, dX NN, dW TN) of one train step", "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_note": peak_note, "bf16_peak_tflops": bf16_peak,
+    return {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 GEMM family: forward NT, dX NN, dW TN of one train step)", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_note": peak_note, "bf16_peak_tflops": bf16_peak,
             "hbm_gbs": hbm, "step_peak_tflops": peak, "gemm_ms_per_step": tot_ms, "top_shapes": per[:6]}
+
+
+def measure_tf32_peak(torch, dev, n=8192):
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=dev); b = torch.randn(n, n, device=dev)
+        for _ in range(2):
+            a @ b
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 if __name__ == "__main__":

@@ -147,6 +147,10 @@ int fb200_head_forward(const fb200_desc* d, const void* const* params,
                        const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
                        void* logits, void* ws, void* stream);
 
+/* Debug aid (not part of the drop-in surface): record clock64 stamps of the TMA / MMA pipeline of
+ * CTA (0,0,0) of each later tcgen05 GEMM into device_buf (int64[8 * k_blocks]); NULL switches it off. */
+int fb200_debug_tc_trace(void* device_buf);
+
 /* rng_state[1] += increment, on `stream` (one tiny kernel; graph-capturable). */
 int fb200_rng_advance(void* rng_state, uint64_t increment, void* stream);
 

@@ -476,6 +476,9 @@ int fb200_list_gemms(const fb200_desc* d, int32_t* out, int cap) {
 
 __global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { state[1] += inc; }
 
+/* debug: device buffer of >= 8*k_blocks int64 receiving pipeline time stamps of CTA (0,0,0) of every tcgen05 GEMM launched afterwards; NULL disables */
+int fb200_debug_tc_trace(void* device_buf) { tc_trace_buffer() = (long long*)device_buf; return FB200_OK; }
+
 int fb200_rng_advance(void* rng_state, uint64_t increment, void* stream) {
   if (!rng_state) return FB200_EBADARG;
   if (!is_device_ptr(rng_state)) return FB200_EUNSUPPORTED;

@@ -32,6 +32,7 @@ struct TcEpilogue {
   int accumulate;         // C += result
   int atomic;             // split-K: fp32 atomic add into C (FMT_F32 only)
   float* colsum;          // optional: colsum[n] += sum_m result(m,n)  (unused by the head; reserved)
+  long long* trace;       // debug: per-k-block clock64 stamps of CTA (0,0,0): [i*8 + {issue, full, mma_issued, empty_seen, split_done}]
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -168,6 +169,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(total_kb, kb_begin + kb_per_split);
   const int num_kb = kb_end - kb_begin;                                            // >= 1 by construction of the grid
+  long long* tr = (ep.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? ep.trace : nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
@@ -188,6 +190,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if (tr) tr[i * 8 + 3] = clock64();
         mbar_expect_tx(&full_bar[s], Cfg::TMA_BYTES);
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         const int k0 = (kb_begin + i) * Cfg::BK;
@@ -205,6 +208,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         } else {
           tma_load_3d(&map_b, &full_bar[s], b_dst, k0, n0, 0);
         }
+        if (tr) tr[i * 8 + 0] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -216,6 +220,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr uint32_t b_lbo = B_MN ? Cfg::BK * 128 : 16, b_sbo = (B_MN && KIND == 1) ? 512 : 1024;
       constexpr uint32_t a_kstep = A_MN ? Cfg::UMMA_K * 128 : 32;                  // bytes per UMMA_K advance
       constexpr uint32_t b_kstep = B_MN ? Cfg::UMMA_K * 128 : 32;
+      const uint64_t a_desc_base = make_smem_desc(0, a_lbo, a_sbo, a_lt), b_desc_base = make_smem_desc(0, b_lbo, b_sbo, b_lt);
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
         const int chunk = i / Cfg::CHUNK_KB, ab = chunk & (Cfg::ACC_BUFS - 1);
@@ -223,22 +228,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (chunk_first) { mbar_wait(&tmem_empty[ab], ((chunk / Cfg::ACC_BUFS) & 1) ^ 1); tc_fence_after(); }
         mbar_wait(KIND == 1 ? &split_bar[s] : &full_bar[s], ph);
         tc_fence_after();
+        if (tr) tr[i * 8 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t b_hi = a_hi + Cfg::PLANES * Cfg::A_BYTES;
+        // descriptors differ only in the 14-bit start-address field (>> 4): add to the low word
+        const uint64_t da0 = a_desc_base + (uint64_t)(a_hi >> 4), db0 = b_desc_base + (uint64_t)(b_hi >> 4);
 #pragma unroll
         for (int j = 0; j < Cfg::BK / Cfg::UMMA_K; ++j) {
-          const uint64_t da = make_smem_desc(a_hi + j * a_kstep, a_lbo, a_sbo, a_lt);
-          const uint64_t db = make_smem_desc(b_hi + j * b_kstep, b_lbo, b_sbo, b_lt);
+          const uint64_t da = da0 + (uint64_t)((j * a_kstep) >> 4);
+          const uint64_t db = db0 + (uint64_t)((j * b_kstep) >> 4);
           umma<KIND>(d_tmem, da, db, idesc, (chunk_first && j == 0) ? 0u : 1u);
           if (KIND == 1) {
-            const uint64_t da_lo = make_smem_desc(a_hi + Cfg::A_BYTES + j * a_kstep, a_lbo, a_sbo, a_lt);
-            const uint64_t db_lo = make_smem_desc(b_hi + Cfg::B_BYTES + j * b_kstep, b_lbo, b_sbo, b_lt);
-            umma<KIND>(d_tmem, da_lo, db, idesc, 1u);
-            umma<KIND>(d_tmem, da, db_lo, idesc, 1u);
+            umma<KIND>(d_tmem, da + (uint64_t)(Cfg::A_BYTES >> 4), db, idesc, 1u);
+            umma<KIND>(d_tmem, da, db + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);
           }
         }
         umma_commit(&empty_bar[s]);                                                 // frees the smem slot once these MMAs retire
+        if (tr) tr[i * 8 + 2] = clock64();
         if ((i % Cfg::CHUNK_KB) == Cfg::CHUNK_KB - 1 || i == num_kb - 1) umma_commit(&tmem_full[ab]);   // chunk accumulator complete
       }
     }
@@ -273,21 +280,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
-        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-        // elementwise and position preserving, hence oblivious to the swizzle / major of the tile
-#pragma unroll 4
+        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        // elementwise and position preserving, hence oblivious to the swizzle / major of the tile;
+        // explicit ld/st.shared (a generic pointer would go through the slow generic-address path)
+#pragma unroll 8
         for (int v = t128; v < Cfg::TMA_BYTES / 16; v += 128) {
           const int off = v * 16;
-          float4* hi_p = (float4*)(off < Cfg::A_BYTES ? st + off : st + Cfg::A_BYTES + off);           // B tile starts after both A planes
-          float4* lo_p = (float4*)((uint8_t*)hi_p + (off < Cfg::A_BYTES ? Cfg::A_BYTES : Cfg::B_BYTES));
-          const float4 x = *hi_p;
-          const float4 h = make_float4(tf32_round(x.x), tf32_round(x.y), tf32_round(x.z), tf32_round(x.w));
-          *hi_p = h;
-          *lo_p = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          const uint32_t hi_a = off < Cfg::A_BYTES ? st + off : st + Cfg::A_BYTES + off;                // B tile starts after both A planes
+          const uint32_t lo_a = hi_a + (off < Cfg::A_BYTES ? Cfg::A_BYTES : Cfg::B_BYTES);
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
+          // tf32 round-to-nearest (ties away) on the bit pattern: add half an ulp, clear the 13 low mantissa bits
+          const float4 h = make_float4(__uint_as_float((__float_as_uint(x.x) + 0x1000u) & 0xFFFFE000u), __uint_as_float((__float_as_uint(x.y) + 0x1000u) & 0xFFFFE000u),
+                                       __uint_as_float((__float_as_uint(x.z) + 0x1000u) & 0xFFFFE000u), __uint_as_float((__float_as_uint(x.w) + 0x1000u) & 0xFFFFE000u));
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(x.x - h.x), "f"(x.y - h.y), "f"(x.z - h.z), "f"(x.w - h.w) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // generic-proxy writes -> visible to tcgen05 (async proxy)
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_bar[s])) : "memory");
+        if (tr && t128 == 0) tr[i * 8 + 4] = clock64();
         // promote one chunk behind the split front so the MMA thread never starves
         if ((i % Cfg::CHUNK_KB) == Cfg::CHUNK_KB - 1 && i / Cfg::CHUNK_KB >= 1) { promote(next_promote); ++next_promote; }
       }
@@ -322,6 +334,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ----------------------------------------------------------------------------- host side
+inline long long*& tc_trace_buffer() { static long long* p = nullptr; return p; }     // debug only (fb200_debug_tc_trace)
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -392,6 +406,7 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   int kb_per = (total_kb + split - 1) / split;
   split = (total_kb + kb_per - 1) / kb_per;                       // no empty slices
   ep.atomic = split > 1 ? 1 : 0;
+  ep.trace = tc_trace_buffer();
   dim3 grid(tiles_n, tiles_m, split);
   kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, ep, g.M, g.N, g.K, kb_per);
   return cudaGetLastError() == cudaSuccess ? FB200_OK : FB200_ECUDA;

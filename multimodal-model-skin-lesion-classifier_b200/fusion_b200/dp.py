@@ -1,0 +1,58 @@
+"""Data-parallel plumbing for the fused head: one process per GPU, torch.distributed (NCCL over
+NVLink / NVSwitch on the box, gloo in the CPU tests).  The head shards over the batch with no
+data-path collective; two reductions keep N ranks equal to one process at the global batch
+(SURVEY.md 8e):
+
+  1. the weighted-CE denominator sum_i w[y_i] must be the GLOBAL one (nn.CrossEntropyLoss(weight)
+     normalises by the batch's weight sum, train_pad_20.py:52) - one scalar all-reduce before the
+     step, handed to the kernels as ``denom``;
+  2. the flat gradient buffer (one contiguous fp32 bucket laid out by fb200_grad_offset, W_q/W_k rows
+     included as the zeros autograd materialises) is all-reduced with SUM - the global denominator
+     already makes the per-rank gradients partial sums of the global mean.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def global_denominator(labels, class_weights, group=None, out=None):
+    """sum over ALL ranks of class_weights[labels]; returns a 1-element tensor on labels' device."""
+    w = class_weights[labels].sum().reshape(1) if class_weights is not None else labels.new_tensor([labels.numel()], dtype=torch.float32)
+    if out is not None:
+        out.copy_(w)
+        w = out
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(w, op=dist.ReduceOp.SUM, group=group)
+    return w
+
+
+def allreduce_gradients(flat_grad, group=None, async_op=False):
+    """SUM all-reduce of the head's flat gradient bucket (in place)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return None
+
+
+def shard_rows(n_rows, rank, world):
+    """Contiguous row range [lo, hi) of this rank (rank r gets rows r*B/N .. (r+1)*B/N)."""
+    base, rem = divmod(n_rows, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class DataParallelHead:
+    """Wraps a MultimodalModel for data-parallel training of the head with the fused step:
+
+        dp = DataParallelHead(model)
+        loss = dp.train_step(img_feat_shard, meta_shard, label_shard, class_weights)   # grads are global afterwards
+    """
+
+    def __init__(self, model, group=None):
+        self.model, self.group = model, group
+
+    def train_step(self, image, text_metadata, label, class_weights=None):
+        denom = global_denominator(label.to(self.model.device), None if class_weights is None else class_weights.to(self.model.device), self.group)
+        loss, logits = self.model.forward_loss(image, text_metadata, label, class_weights, denom=denom)
+        allreduce_gradients(self.model.flat_grad, self.group)
+        return loss, logits

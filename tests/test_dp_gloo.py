@@ -1,0 +1,80 @@
+"""CPU, world_size = 2 over gloo: the data-parallel host logic (row sharding, global weighted-CE
+denominator, SUM all-reduce of the flat gradient bucket) makes two ranks on half batches equal to
+one process on the global batch.  The per-rank arithmetic here is the numpy oracle standing in for
+the CUDA kernels (same ``denom`` contract as fb200_cross_entropy / fb200_head_train_step)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, mech, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "multimodal-model-skin-lesion-classifier_b200"))
+    from fusion_b200 import _lib, dp, make_desc
+    from oracle import head_oracle as ho
+    from tests.golden import cases as C
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kw = dict(C.SMALL_DIMS, mechanism=mech)
+    cfg = C.make_cfg(kw)
+    B = 11                                             # odd: uneven shards
+    params = C.gen_params(cfg, 77, np.float64)
+    x, tin, labels, cw, masks = C.gen_inputs(cfg, B, 77, True, np.float64)
+    lo, hi = dp.shard_rows(B, rank, world)
+    den = dp.global_denominator(torch.from_numpy(labels[lo:hi]), torch.from_numpy(cw))
+    sm = {k: v[lo:hi] for k, v in masks.items()}
+    o = ho.head_forward_backward(cfg, params, x[lo:hi], tin[lo:hi], labels[lo:hi], cw, sm, denom=float(den))
+    # flat bucket in the library's layout
+    d = make_desc(mech, hi - lo, cfg.F, cfg.V, cfg.T, cfg.D, cfg.H, cfg.C)
+    total, offs = _lib.grad_layout(d)
+    names = _lib.param_names()
+    flat = torch.zeros(total, dtype=torch.float64)
+    for s, off in offs.items():
+        g = o["grads"][names[s]]
+        flat[off: off + g.size] = torch.from_numpy(g.ravel())
+    dp.allreduce_gradients(flat)
+    num = torch.tensor([o["num"]]); dist.all_reduce(num)
+    if rank == 0:
+        full = ho.head_forward_backward(cfg, params, x, tin, labels, cw, masks)
+        worst = 0.0
+        for s, off in offs.items():
+            g = full["grads"][names[s]]
+            got = flat[off: off + g.size].numpy().reshape(g.shape)
+            worst = max(worst, float(np.abs(got - g).max() / max(np.abs(g).max(), 1e-30)))
+        q.put((worst, abs(float(num) / float(den) - full["loss"]), abs(float(den) - full["den"])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mech", ["crossattention", "att-intramodal+residual+cross-attention-metadados", "metablock"])
+def test_two_ranks_equal_one_process(mech):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, mech, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    worst, loss_err, den_err = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert worst < 1e-12 and loss_err < 1e-12 and den_err < 1e-12
+
+
+def test_shard_rows_cover_the_batch():
+    from fusion_b200 import dp
+    for B in (1, 7, 32, 1024):
+        for world in (1, 2, 3, 8):
+            spans = [dp.shard_rows(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
