@@ -93,6 +93,21 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t 
                  ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
   }
 }
+// A operand from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -126,7 +141,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int kind, int a_mn, int b_mn, 
          ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <int KIND, int BN>
+template <int KIND, int BN, int ATM = 0>
 struct TcCfg {
   static constexpr int ESIZE = KIND == 0 ? 2 : 4;
   static constexpr int BK = 128 / ESIZE;                 // elements of K per stage (one 128-byte swizzle row)
@@ -134,9 +149,15 @@ struct TcCfg {
   static constexpr int PLANES = KIND == 0 ? 1 : 2;       // smem planes per operand tile (tf32x3: raw/hi + lo)
   static constexpr int A_BYTES = TC_BM * 128;            // one plane of the A tile
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  // ATM (fp32-strict, K-major A): the split A tile goes to TENSOR MEMORY (tcgen05.st) instead of back to
+  // shared memory, and the MMAs read A from TMEM - shared memory then only carries the raw A tile once and
+  // the B planes, which is what keeps the 128-byte/clk smem port from starving the tensor pipe.
+  static constexpr int A_PLANES = ATM ? 1 : PLANES;      // smem planes of A
+  static constexpr int B_OFF = A_PLANES * A_BYTES;       // B tile offset inside a stage
+  static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + PLANES * B_BYTES;
   static constexpr int TMA_BYTES = A_BYTES + B_BYTES;    // bytes TMA delivers per stage (one plane of each)
-  static constexpr int STAGES = (KIND == 0) ? (BN <= 128 ? 6 : 4) : (BN <= 128 ? 3 : 2);
+  static constexpr int STAGES = (KIND == 0) ? (BN <= 128 ? 6 : 4) : (ATM ? 4 : (BN <= 128 ? 3 : 2));
+  static constexpr int A_TMEM_COLS = 2 * (128 / ESIZE);  // hi + lo columns of one A stage in TMEM (ATM)
   static constexpr int EPC = 128 / ESIZE;                // elements per 128-byte chunk along MN (MN-major operands)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   // The tensor-core accumulator truncates on every accumulate, a bias that grows linearly with the number
@@ -146,14 +167,18 @@ struct TcCfg {
   // fills the other of two TMEM accumulators.
   static constexpr int CHUNK_KB = KIND == 1 ? 4 : (1 << 30);
   static constexpr int ACC_BUFS = KIND == 1 ? 2 : 1;
-  static constexpr int TMEM_COLS = (ACC_BUFS * BN) < 32 ? 32 : (ACC_BUFS * BN);
+  static constexpr int ACC_COLS = ACC_BUFS * BN;
+  static constexpr int TMEM_NEED = ACC_COLS + (ATM ? STAGES * A_TMEM_COLS : 0);
+  static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  static_assert(TMEM_NEED <= 512, "tensor memory has 512 columns");
 };
 
 template <int KIND, int A_MN, int B_MN, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcEpilogue ep, const int M, const int N, const int K, const int kb_per_split) {
-  using Cfg = TcCfg<KIND, BN>;
+  constexpr int ATM = (KIND == 1 && !A_MN) ? 1 : 0;
+  using Cfg = TcCfg<KIND, BN, ATM>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // 128B swizzle needs 1024-byte alignment
   uint64_t* full_bar = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -195,7 +220,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
         const int k0 = (kb_begin + i) * Cfg::BK;
         uint8_t* a_dst = st;
-        uint8_t* b_dst = st + Cfg::PLANES * Cfg::A_BYTES;
+        uint8_t* b_dst = st + Cfg::B_OFF;
         if (A_MN) {
 #pragma unroll
           for (int c = 0; c < TC_BM / Cfg::EPC; ++c) tma_load_3d(&map_a, &full_bar[s], a_dst + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, k0, 0);
@@ -231,17 +256,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (tr) tr[i * 8 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
         const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t b_hi = a_hi + Cfg::PLANES * Cfg::A_BYTES;
+        const uint32_t b_hi = a_hi + Cfg::B_OFF;
         // descriptors differ only in the 14-bit start-address field (>> 4): add to the low word
         const uint64_t da0 = a_desc_base + (uint64_t)(a_hi >> 4), db0 = b_desc_base + (uint64_t)(b_hi >> 4);
+        const uint32_t a_tm = tmem_base + (uint32_t)(Cfg::ACC_COLS + s * Cfg::A_TMEM_COLS);      // ATM: hi columns, lo = +BK
 #pragma unroll
         for (int j = 0; j < Cfg::BK / Cfg::UMMA_K; ++j) {
           const uint64_t da = da0 + (uint64_t)((j * a_kstep) >> 4);
           const uint64_t db = db0 + (uint64_t)((j * b_kstep) >> 4);
-          umma<KIND>(d_tmem, da, db, idesc, (chunk_first && j == 0) ? 0u : 1u);
-          if (KIND == 1) {
-            umma<KIND>(d_tmem, da + (uint64_t)(Cfg::A_BYTES >> 4), db, idesc, 1u);
-            umma<KIND>(d_tmem, da, db + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);
+          const uint32_t first = (chunk_first && j == 0) ? 0u : 1u;
+          if (ATM) {
+            umma_ts_tf32(d_tmem, a_tm + j * Cfg::UMMA_K, db, idesc, first);
+            umma_ts_tf32(d_tmem, a_tm + Cfg::BK + j * Cfg::UMMA_K, db, idesc, 1u);
+            umma_ts_tf32(d_tmem, a_tm + j * Cfg::UMMA_K, db + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);
+          } else {
+            umma<KIND>(d_tmem, da, db, idesc, first);
+            if (KIND == 1) {
+              umma<KIND>(d_tmem, da + (uint64_t)(Cfg::A_BYTES >> 4), db, idesc, 1u);
+              umma<KIND>(d_tmem, da, db + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);
+            }
           }
         }
         umma_commit(&empty_bar[s]);                                                 // frees the smem slot once these MMAs retire
@@ -281,20 +314,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        // elementwise and position preserving, hence oblivious to the swizzle / major of the tile;
-        // explicit ld/st.shared (a generic pointer would go through the slow generic-address path)
+        auto rnd = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };   // tf32 RN (ties away) on the bit pattern
+        if (ATM) {
+          // B: split in place (elementwise, swizzle-oblivious); explicit ld/st.shared
 #pragma unroll 8
-        for (int v = t128; v < Cfg::TMA_BYTES / 16; v += 128) {
-          const int off = v * 16;
-          const uint32_t hi_a = off < Cfg::A_BYTES ? st + off : st + Cfg::A_BYTES + off;                // B tile starts after both A planes
-          const uint32_t lo_a = hi_a + (off < Cfg::A_BYTES ? Cfg::A_BYTES : Cfg::B_BYTES);
-          float4 x;
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
-          // tf32 round-to-nearest (ties away) on the bit pattern: add half an ulp, clear the 13 low mantissa bits
-          const float4 h = make_float4(__uint_as_float((__float_as_uint(x.x) + 0x1000u) & 0xFFFFE000u), __uint_as_float((__float_as_uint(x.y) + 0x1000u) & 0xFFFFE000u),
-                                       __uint_as_float((__float_as_uint(x.z) + 0x1000u) & 0xFFFFE000u), __uint_as_float((__float_as_uint(x.w) + 0x1000u) & 0xFFFFE000u));
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(x.x - h.x), "f"(x.y - h.y), "f"(x.z - h.z), "f"(x.w - h.w) : "memory");
+          for (int v = t128; v < Cfg::B_BYTES / 16; v += 128) {
+            const uint32_t hi_a = st + Cfg::B_OFF + v * 16, lo_a = hi_a + Cfg::B_BYTES;
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
+            const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(x.x - h.x), "f"(x.y - h.y), "f"(x.z - h.z), "f"(x.w - h.w) : "memory");
+          }
+          // A: thread = row (TMEM lane 32q + lane).  The K-major tile keeps row r at r*128 B with its eight
+          // 16-byte chunks XOR-swizzled by (r & 7): un-swizzle while reading, split, store hi | lo to TMEM.
+          const int r = q * 32 + lane;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + r * 128 + ((j ^ (r & 7)) << 4)));
+            const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
+            hi[4 * j] = __float_as_uint(h.x); hi[4 * j + 1] = __float_as_uint(h.y); hi[4 * j + 2] = __float_as_uint(h.z); hi[4 * j + 3] = __float_as_uint(h.w);
+            lo[4 * j] = __float_as_uint(x.x - h.x); lo[4 * j + 1] = __float_as_uint(x.y - h.y); lo[4 * j + 2] = __float_as_uint(x.z - h.z); lo[4 * j + 3] = __float_as_uint(x.w - h.w);
+          }
+          const uint32_t a_tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ACC_COLS + s * Cfg::A_TMEM_COLS);
+          tmem_st32(a_tm, hi);
+          tmem_st32(a_tm + Cfg::BK, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+        } else {
+          // elementwise and position preserving, hence oblivious to the swizzle / major of the tile;
+          // explicit ld/st.shared (a generic pointer would go through the slow generic-address path)
+#pragma unroll 8
+          for (int v = t128; v < Cfg::TMA_BYTES / 16; v += 128) {
+            const int off = v * 16;
+            const uint32_t hi_a = off < Cfg::A_BYTES ? st + off : st + Cfg::A_BYTES + off;                // B tile starts after both A planes
+            const uint32_t lo_a = hi_a + (off < Cfg::A_BYTES ? Cfg::A_BYTES : Cfg::B_BYTES);
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
+            const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(x.x - h.x), "f"(x.y - h.y), "f"(x.z - h.z), "f"(x.w - h.w) : "memory");
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // generic-proxy writes -> visible to tcgen05 (async proxy)
         __syncwarp();
@@ -380,7 +442,7 @@ struct TcGemmArgs {
 
 template <int KIND, int A_MN, int B_MN, int BN>
 inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
-  using Cfg = TcCfg<KIND, BN>;
+  using Cfg = TcCfg<KIND, BN, (KIND == 1 && !A_MN) ? 1 : 0>;
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, KIND, g.A, A_MN ? Cfg::EPC : Cfg::BK, A_MN ? Cfg::BK : TC_BM, A_MN);
   if (rc != FB200_OK) return rc;
