@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
 
 namespace fb200 {
 
@@ -195,6 +196,8 @@ static int run_backward(Ctx& c) {
   };
 
   std::vector<ColsumSeg> colsums;
+  std::vector<std::vector<TcGroupProblem>> dw_round;   // [k]: k-th application of a weight (k > 0 accumulates, in launch order)
+  std::vector<int> tc_uses(NUM_SLOTS, 0);
   for (int oi = (int)p.ops.size() - 1; oi >= 0; --oi) {
     const Op& o = p.ops[oi];
     // the gradient of a view that lives inside a fully written buffer counts as written
@@ -206,16 +209,19 @@ static int run_backward(Ctx& c) {
         const int N = o.out.cols, K = o.in0.cols;
         if (o.engine == 1) {
           const int kind = p.fmt == FMT_BF16 ? 0 : 1;
-          // dW[N,K] (+)= dY^T X : both operands MN-major views of the row-major activations
-          TcGemmArgs t{};
-          t.kind = kind; t.a_mn = 1; t.b_mn = 1;
-          t.A = tc_operand(c.grad(o.out), N, B); t.B = tc_operand(c.value(o.in0), K, B);
-          t.M = N; t.N = K; t.K = B;
-          t.ep.C = make_ref(c.pgrad(o.w_slot, (int64_t)o.w_row0 * K), K, FMT_F32); t.ep.bias = nullptr; t.ep.relu = 0; t.ep.mask_src.p = nullptr;
-          t.ep.accumulate = pwritten[o.w_slot]; t.ep.atomic = 0; t.ep.colsum = nullptr; t.allow_split = 1;
-          int rc = launch_tc_gemm(t, c.dev.num_sms, c.st);
-          if (rc != FB200_OK) return rc;
-          pwritten[o.w_slot] = 1;
+          // dW[N,K] (+)= dY^T X : both operands MN-major views of the row-major activations.  Deferred: every
+          // weight gradient of the step goes into one grouped launch after the dX chain (dY / X stay in the workspace).
+          {
+            TcGroupProblem gp{};
+            gp.A = tc_operand(c.grad(o.out), N, B); gp.B = tc_operand(c.value(o.in0), K, B);
+            gp.M = N; gp.N = K; gp.C = c.pgrad(o.w_slot, (int64_t)o.w_row0 * K); gp.ldc = K;
+            const int use = tc_uses[o.w_slot]++;             // the same weight applied again: later rounds accumulate
+            gp.accumulate = (use > 0 || pwritten[o.w_slot]) ? 1 : 0;
+            if ((int)dw_round.size() <= use) dw_round.resize(use + 1);
+            dw_round[use].push_back(gp);
+            pwritten[o.w_slot] = 1;
+          }
+          int rc = FB200_OK;
           colsums.push_back(ColsumSeg{c.grad(o.out), N, c.pgrad(o.b_slot, o.w_row0)});   // db: batched after the loop
           if (grad_wanted(o.dx_view)) {
             // dX[B,K] (+)= dY W : W read MN-major from the same operand-format copy the forward used
@@ -305,6 +311,14 @@ static int run_backward(Ctx& c) {
       default: return FB200_EBADARG;
     }
     CUDA_OK(cudaGetLastError());
+  }
+  // weight gradients of all tcgen05 Linears, grouped (round 1 only exists for weights applied twice)
+  for (size_t round = 0; round < dw_round.size(); ++round) {
+    for (size_t base = 0; base < dw_round[round].size(); base += TC_MAX_GROUP) {
+      const int n = (int)std::min<size_t>(TC_MAX_GROUP, dw_round[round].size() - base);
+      int rc = launch_tc_grouped_tn(p.fmt == FMT_BF16 ? 0 : 1, dw_round[round].data() + base, n, B, c.st);
+      if (rc != FB200_OK) return rc;
+    }
   }
   // bias gradients of all tcgen05 Linears: the dY buffers are still intact in the workspace
   for (size_t base = 0; base < colsums.size(); base += 24) {
@@ -439,16 +453,16 @@ int fb200_launch_count(const fb200_desc* d, int* forward, int* backward) {
   int f = 0, b = 0;
   const bool need_dimg = d->flags & FB200_FLAG_NEED_DIMG, need_dtxt = d->flags & FB200_FLAG_NEED_DTEXT;
   f += (int)((p.wprep.size() + 31) / 32);
-  int ntc = 0;
+  int ntc = 0, rounds = 0; int uses[NUM_SLOTS] = {};
   for (auto& o : p.ops) {
     f += 1;
     if (o.kind == OP_LINEAR) {
       const int ext = p.acts[o.dx_view.buf].ext;
-      if (o.engine == 1) ++ntc;
-      b += 1 + ((ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) ? 1 : 0);
+      if (o.engine == 1) { ++ntc; int u = ++uses[o.w_slot]; if (u > rounds) rounds = u; }
+      b += (o.engine == 1 ? 0 : 1) + ((ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) ? 1 : 0);
     } else if (o.kind != OP_CAST) b += 1;
   }
-  b += (ntc + 23) / 24;
+  b += (ntc + 23) / 24 + rounds;      // batched bias-gradient kernel(s) + grouped weight-gradient launch(es)
   if (forward) *forward = f;
   if (backward) *backward = b;
   return FB200_OK;

@@ -173,11 +173,12 @@ struct TcCfg {
   static_assert(TMEM_NEED <= 512, "tensor memory has 512 columns");
 };
 
+// One 128 x BN output tile: the whole pipeline described at the top of this file.
 template <int KIND, int A_MN, int B_MN, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const TcEpilogue ep, const int M, const int N, const int K, const int kb_per_split) {
-  constexpr int ATM = (KIND == 1 && !A_MN) ? 1 : 0;
+__device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pmap_a, const CUtensorMap* __restrict__ pmap_b, const TcEpilogue& ep,
+                                             const int M, const int N, const int m0, const int n0, const int kb_begin, const int num_kb,
+                                             long long* tr) {
+  constexpr int ATM = (KIND == 1) ? 1 : 0;
   using Cfg = TcCfg<KIND, BN, ATM>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // 128B swizzle needs 1024-byte alignment
@@ -187,14 +188,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = split_bar + Cfg::STAGES;            // [2]
   uint64_t* tmem_empty = tmem_full + 2;                     // [2]
   uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  const CUtensorMap& map_a = *pmap_a;
+  const CUtensorMap& map_b = *pmap_b;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int total_kb = (K + Cfg::BK - 1) / Cfg::BK;
-  const int kb_begin = blockIdx.z * kb_per_split;
-  const int kb_end = min(total_kb, kb_begin + kb_per_split);
-  const int num_kb = kb_end - kb_begin;                                            // >= 1 by construction of the grid
-  long long* tr = (ep.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? ep.trace : nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
@@ -239,7 +236,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(KIND, A_MN, B_MN, TC_BM, BN);
+      constexpr uint32_t idesc = make_idesc(KIND, ATM ? 0 : A_MN, B_MN, TC_BM, BN);
       constexpr uint32_t a_lt = (A_MN && KIND == 1) ? 1 : 2, b_lt = (B_MN && KIND == 1) ? 1 : 2;   // smem layout types
       constexpr uint32_t a_lbo = A_MN ? Cfg::BK * 128 : 16, a_sbo = (A_MN && KIND == 1) ? 512 : 1024;
       constexpr uint32_t b_lbo = B_MN ? Cfg::BK * 128 : 16, b_sbo = (B_MN && KIND == 1) ? 512 : 1024;
@@ -326,17 +323,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(x.x - h.x), "f"(x.y - h.y), "f"(x.z - h.z), "f"(x.w - h.w) : "memory");
           }
-          // A: thread = row (TMEM lane 32q + lane).  The K-major tile keeps row r at r*128 B with its eight
-          // 16-byte chunks XOR-swizzled by (r & 7): un-swizzle while reading, split, store hi | lo to TMEM.
-          const int r = q * 32 + lane;
+          // A: thread = output row m (TMEM lane 32q + lane); gather its BK values of K, split, store hi | lo to TMEM.
           uint32_t hi[32], lo[32];
+          if (A_MN) {
+            // MN-major tile (dW: A = dY^T): chunk q holds m in [32q, 32q+32); K row r is 128 B with its four
+            // 32-byte groups XOR-swizzled by (r & 3).  One 4-byte load per K value, conflict-free across the warp.
+            const uint32_t base = st + q * (Cfg::BK * 128) + (lane & 7) * 4;
+            const int gsel = lane >> 3;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 x;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + r * 128 + ((j ^ (r & 7)) << 4)));
-            const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
-            hi[4 * j] = __float_as_uint(h.x); hi[4 * j + 1] = __float_as_uint(h.y); hi[4 * j + 2] = __float_as_uint(h.z); hi[4 * j + 3] = __float_as_uint(h.w);
-            lo[4 * j] = __float_as_uint(x.x - h.x); lo[4 * j + 1] = __float_as_uint(x.y - h.y); lo[4 * j + 2] = __float_as_uint(x.z - h.z); lo[4 * j + 3] = __float_as_uint(x.w - h.w);
+            for (int r = 0; r < 32; ++r) {
+              float x;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(base + r * 128 + ((gsel ^ (r & 3)) << 5)));
+              const float h = rnd(x);
+              hi[r] = __float_as_uint(h); lo[r] = __float_as_uint(x - h);
+            }
+          } else {
+            // K-major tile: row m at m*128 B with its eight 16-byte chunks XOR-swizzled by (m & 7)
+            const int r = q * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 x;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + r * 128 + ((j ^ (r & 7)) << 4)));
+              const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
+              hi[4 * j] = __float_as_uint(h.x); hi[4 * j + 1] = __float_as_uint(h.y); hi[4 * j + 2] = __float_as_uint(h.z); hi[4 * j + 3] = __float_as_uint(h.w);
+              lo[4 * j] = __float_as_uint(x.x - h.x); lo[4 * j + 1] = __float_as_uint(x.y - h.y); lo[4 * j + 2] = __float_as_uint(x.z - h.z); lo[4 * j + 3] = __float_as_uint(x.w - h.w);
+            }
           }
           const uint32_t a_tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ACC_COLS + s * Cfg::A_TMEM_COLS);
           tmem_st32(a_tm, hi);
@@ -395,6 +406,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
+template <int KIND, int A_MN, int B_MN, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcEpilogue ep, const int M, const int N, const int K, const int kb_per_split) {
+  using Cfg = TcCfg<KIND, BN, KIND == 1 ? 1 : 0>;
+  const int total_kb = (K + Cfg::BK - 1) / Cfg::BK;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int num_kb = min(total_kb, kb_begin + kb_per_split) - kb_begin;             // >= 1 by construction of the grid
+  long long* tr = (ep.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? ep.trace : nullptr;
+  tc_gemm_tile<KIND, A_MN, B_MN, BN>(&map_a, &map_b, ep, M, N, blockIdx.y * TC_BM, blockIdx.x * BN, kb_begin, num_kb, tr);
+}
+
+// All weight gradients of one backward pass in ONE launch: problem p is dW_p[M_p, N_p] = dY_p^T X_p with the
+// batch as the (shared) reduction length.  Tile -> problem by a prefix table; full-K tiles, plain stores:
+// no split-K, no atomics, no memset, and ~2 waves of 128-k-block tiles instead of a dozen latency-bound launches.
+constexpr int TC_MAX_GROUP = 24;
+struct TcGroupArgs {
+  CUtensorMap maps[2 * TC_MAX_GROUP];       // A (dY) and B (X) of every problem
+  float* C[TC_MAX_GROUP]; int ldc[TC_MAX_GROUP]; int M[TC_MAX_GROUP]; int N[TC_MAX_GROUP];
+  int tile_begin[TC_MAX_GROUP + 1]; int accumulate[TC_MAX_GROUP];
+  int nprob; int K;
+};
+template <int KIND, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_grouped_tn_kernel(const __grid_constant__ TcGroupArgs g) {
+  using Cfg = TcCfg<KIND, BN, KIND == 1 ? 1 : 0>;
+  int p = 0;
+  while (p + 1 < g.nprob && (int)blockIdx.x >= g.tile_begin[p + 1]) ++p;
+  const int t = blockIdx.x - g.tile_begin[p];
+  const int tiles_n = (g.N[p] + BN - 1) / BN;
+  TcEpilogue ep;
+  ep.C = make_ref(g.C[p], g.ldc[p], FMT_F32); ep.bias = nullptr; ep.relu = 0; ep.mask_src.p = nullptr; ep.accumulate = g.accumulate[p];
+  ep.atomic = 0; ep.colsum = nullptr; ep.trace = nullptr;
+  tc_gemm_tile<KIND, 1, 1, BN>(&g.maps[2 * p], &g.maps[2 * p + 1], ep, g.M[p], g.N[p], (t / tiles_n) * TC_BM, (t % tiles_n) * BN, 0,
+                               (g.K + Cfg::BK - 1) / Cfg::BK, nullptr);
+}
+
 // ----------------------------------------------------------------------------- host side
 inline long long*& tc_trace_buffer() { static long long* p = nullptr; return p; }     // debug only (fb200_debug_tc_trace)
 
@@ -442,7 +489,7 @@ struct TcGemmArgs {
 
 template <int KIND, int A_MN, int B_MN, int BN>
 inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
-  using Cfg = TcCfg<KIND, BN, (KIND == 1 && !A_MN) ? 1 : 0>;
+  using Cfg = TcCfg<KIND, BN, KIND == 1 ? 1 : 0>;
   CUtensorMap ma, mb;
   int rc = make_operand_map(&ma, KIND, g.A, A_MN ? Cfg::EPC : Cfg::BK, A_MN ? Cfg::BK : TC_BM, A_MN);
   if (rc != FB200_OK) return rc;
@@ -494,6 +541,43 @@ inline bool tc_shape_ok(int layout, int M, int N, int K) {
 inline int launch_tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   if (g.kind == 0) return tc_launch_major<0, 128>(g, num_sms, st);
   return tc_launch_major<1, 128>(g, num_sms, st);
+}
+
+
+// ---- grouped weight-gradient launch ---------------------------------------------------------------
+struct TcGroupProblem {
+  TcOperand A, B;          // A = dY [K rows, M cols] (MN-major), B = X [K rows, N cols] (MN-major)
+  int M, N;
+  float* C; int ldc; int accumulate;
+};
+template <int KIND>
+inline int tc_launch_grouped_tn(const TcGroupProblem* probs, int nprob, int K, cudaStream_t st) {
+  constexpr int BN = 128;
+  using Cfg = TcCfg<KIND, BN, KIND == 1 ? 1 : 0>;
+  if (nprob < 1 || nprob > TC_MAX_GROUP) return FB200_EBADARG;
+  TcGroupArgs g{};
+  int tiles = 0;
+  for (int p = 0; p < nprob; ++p) {
+    int rc = make_operand_map(&g.maps[2 * p], KIND, probs[p].A, Cfg::EPC, Cfg::BK, true);
+    if (rc != FB200_OK) return rc;
+    rc = make_operand_map(&g.maps[2 * p + 1], KIND, probs[p].B, Cfg::EPC, Cfg::BK, true);
+    if (rc != FB200_OK) return rc;
+    g.C[p] = probs[p].C; g.ldc[p] = probs[p].ldc; g.M[p] = probs[p].M; g.N[p] = probs[p].N; g.accumulate[p] = probs[p].accumulate;
+    g.tile_begin[p] = tiles;
+    tiles += ((probs[p].M + TC_BM - 1) / TC_BM) * ((probs[p].N + BN - 1) / BN);
+  }
+  g.tile_begin[nprob] = tiles; g.nprob = nprob; g.K = K;
+  static bool attr_set = false;
+  auto kern = tc_gemm_grouped_tn_kernel<KIND, BN>;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
+    attr_set = true;
+  }
+  kern<<<tiles, TC_THREADS, Cfg::SMEM_BYTES, st>>>(g);
+  return cudaGetLastError() == cudaSuccess ? FB200_OK : FB200_ECUDA;
+}
+inline int launch_tc_grouped_tn(int kind, const TcGroupProblem* probs, int nprob, int K, cudaStream_t st) {
+  return kind == 0 ? tc_launch_grouped_tn<0>(probs, nprob, K, st) : tc_launch_grouped_tn<1>(probs, nprob, K, st);
 }
 
 // ---- fp32-in / fp32-out wrapper used by the fb200_gemm primitive (unit tests, micro-benchmarks):
