@@ -303,7 +303,7 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    roof = dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype)
+    roof = dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype, model)
     t_roof_ms = max(flops / (roof["step_peak_tflops"] * 1e12), nbytes / (roof["hbm_gbs"] * 1e9)) * 1e3
     roof["step"] = {"algorithmic_flops": flops, "algorithmic_bytes": nbytes, "t_roof_ms": t_roof_ms, "frac": t_roof_ms / ms_step}
 
@@ -338,7 +338,7 @@ def main():
         dist.destroy_process_group()
 
 
-def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype):
+def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype, model):
     """Times every GEMM launch shape of one train step (forward NT, dX NN, dW TN of each Linear)
     through fb200_gemm - the same kernels the step launches - with CUDA events on the launch
     stream, and reports algorithmic FLOPs / measured time for the GEMM kernel family."""
@@ -382,7 +382,29 @@ def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype):
         per.append({"layout": "NT NN TN".split()[layout], "engine": engine_names[engine], "M": M, "N": N, "K": Kd, "launches_per_step": count,
                     "us": ms * 1e3, "tflops": fl / (ms * 1e-3) / 1e12})
     per.sort(key=lambda r: -r["us"] * r["launches_per_step"])
-    achieved = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    # The step's own GEMM launches (forward, dX chain, ONE grouped weight-gradient launch), replayed alone on the
+    # launch stream between CUDA events: algorithmic FLOPs of those launches / their measured time.
+    from fusion_b200.head import ParamTable
+    table = ParamTable([p.detach() if p is not None else None for p in model._params_in_slot_order()])
+    Bsz = desc.B
+    x = torch.randn(Bsz, desc.F, device=dev); t = torch.randn(Bsz, desc.V if desc.text_mode == 0 else desc.T, device=dev)
+    ws = torch.zeros(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
+    total, _ = _lib.grad_layout(desc)
+    flat = torch.zeros(total, device=dev); logits = torch.zeros(Bsz, desc.C, device=dev)
+
+    def replay():
+        _lib.check(L.fb200_debug_gemm_replay(C.byref(desc), table.arr, x.data_ptr(), t.data_ptr(), logits.data_ptr(), flat.data_ptr(),
+                                             ws.data_ptr(), stream.cuda_stream), "fb200_debug_gemm_replay")
+    for _ in range(3):
+        replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record(stream)
+    for _ in range(reps):
+        replay()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    tot_ms = e0.elapsed_time(e1) / reps
     bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm = peaks.get("hbm_gbs", 6650.0)
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
@@ -401,7 +423,9 @@ def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype):
         peak, peak_note = bf16_peak, f"dense bf16 sustained, {src}"
     return {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 GEMM family: forward NT, dX NN, dW TN of one train step)", "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_note": peak_note, "bf16_peak_tflops": bf16_peak,
-            "hbm_gbs": hbm, "step_peak_tflops": peak, "gemm_ms_per_step": tot_ms, "top_shapes": per[:6]}
+            "hbm_gbs": hbm, "step_peak_tflops": peak, "gemm_ms_per_step": tot_ms, "gemm_launches_per_step": sum(shapes.values()),
+            "how": "all GEMM launches of one train step replayed alone (fb200_debug_gemm_replay), CUDA events on the launch stream, eager launches",
+            "top_shapes_single_launch": per[:6]}
 
 
 def measure_tf32_peak(torch, dev, n=8192):

@@ -147,6 +147,11 @@ int fb200_head_forward(const fb200_desc* d, const void* const* params,
                        const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
                        void* logits, void* ws, void* stream);
 
+/* Debug / measurement aid: launches only the GEMM kernels of one train step (same kernels, grids and operands as
+ * fb200_head_train_step) so that bench.py can time the dominant kernel family with CUDA events on the launch stream. */
+int fb200_debug_gemm_replay(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
+                            void* logits, void* grads, void* ws, void* stream);
+
 /* Debug aid (not part of the drop-in surface): record clock64 stamps of the TMA / MMA pipeline of
  * CTA (0,0,0) of each later tcgen05 GEMM into device_buf (int64[8 * k_blocks]); NULL switches it off. */
 int fb200_debug_tc_trace(void* device_buf);

@@ -48,6 +48,7 @@ struct Ctx {
   char* ws;
   cudaStream_t st;
   DeviceInfo dev;
+  bool gemm_only = false;     // debug replay: launch only the GEMM kernels of the step (bench.py times them with CUDA events)
 
   TRef value(const View& v) const {
     const Act& a = p.acts[v.buf];
@@ -104,14 +105,14 @@ static int run_forward(Ctx& c) {
       PrepSeg& sg = a.seg[a.nseg++];
       sg.src = c.param(w.slot, (int64_t)w.row0 * w.cols); sg.dst = c.ws + w.off; sg.n4 = (int64_t)w.rows * w.cols / 4; sg.plane = (int64_t)w.rows * w.cols;
     }
-    wprep_kernel<<<dim3(64, a.nseg), 256, 0, c.st>>>(a);
+    if (!c.gemm_only) wprep_kernel<<<dim3(64, a.nseg), 256, 0, c.st>>>(a);
     CUDA_OK(cudaGetLastError());
   }
   for (const Op& o : p.ops) {
     switch (o.kind) {
       case OP_CAST: {
         const TRef src = c.value(o.in0);
-        convert_kernel<<<c.dev.num_sms * 4, 256, 0, c.st>>>((const float*)src.p, src.ld, c.value(o.out), B, o.out.cols);
+        if (!c.gemm_only) convert_kernel<<<c.dev.num_sms * 4, 256, 0, c.st>>>((const float*)src.p, src.ld, c.value(o.out), B, o.out.cols);
       } break;
       case OP_LINEAR: {
         if (o.engine == 1) {
@@ -126,6 +127,13 @@ static int run_forward(Ctx& c) {
           if (rc != FB200_OK) return rc;
           break;
         }
+        if (smalln_ok(o.out.cols, o.in0.cols) && c.value(o.out).fmt == FMT_F32 && !o.relu && o.in0.cols % 4 == 0 && c.value(o.in0).ld % 4 == 0) {
+          // classifier head: warp-per-row kernel instead of a >90% padded GEMM tile
+          SmallNArgs a{}; a.x = c.value(o.in0); a.y = c.value(o.out); a.W = c.param(o.w_slot, (int64_t)o.w_row0 * o.in0.cols);
+          a.bias = c.param(o.b_slot, o.w_row0); a.B = B; a.K = o.in0.cols; a.C = o.out.cols;
+          CUDA_OK(launch_smalln_fwd(a, c.dev.num_sms, c.st));
+          break;
+        }
         GemmArgs g{};
         g.A = c.value(o.in0); g.B = make_ref((void*)c.param(o.w_slot, (int64_t)o.w_row0 * o.in0.cols), o.in0.cols, FMT_F32);
         g.C = c.value(o.out); g.M = B; g.N = o.out.cols; g.K = o.in0.cols; g.a_kc = 1; g.b_kc = 1;
@@ -137,14 +145,14 @@ static int run_forward(Ctx& c) {
         a.stats = (float*)(c.ws + o.stats_off); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) lnrd_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
-        FB200_ROW_DISPATCH(a.N, CALL);
+        if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
       } break;
       case OP_GATE: {
         GateArgs a{}; a.x = c.value(o.in0); a.z = c.value(o.in1); a.y = c.value(o.out); a.B = B; a.N = o.out.cols;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) gate_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
-        FB200_ROW_DISPATCH(a.N, CALL);
+        if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
       } break;
       case OP_GRB: {
@@ -153,7 +161,7 @@ static int run_forward(Ctx& c) {
         a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) grb_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
-        FB200_ROW_DISPATCH(a.N, CALL);
+        if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
       } break;
       case OP_META: {
@@ -162,7 +170,7 @@ static int run_forward(Ctx& c) {
         a.stats = (float*)(c.ws + o.stats_off); a.B = B; a.N = o.out.cols;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) meta_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
-        FB200_ROW_DISPATCH(a.N, CALL);
+        if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
       } break;
       default: return FB200_EBADARG;
@@ -175,7 +183,7 @@ static int run_forward(Ctx& c) {
 // ------------------------------------------------------------------------------- backward
 static int run_backward(Ctx& c) {
   const Plan& p = c.p; const int B = p.d.B;
-  CUDA_OK(cudaMemsetAsync(c.grads, 0, (size_t)p.grad_elems * sizeof(float), c.st));
+  if (!c.gemm_only) CUDA_OK(cudaMemsetAsync(c.grads, 0, (size_t)p.grad_elems * sizeof(float), c.st));
   std::vector<char> gwritten(p.acts.size(), 0);       // has the gradient buffer been written yet?
   std::vector<char> pwritten(NUM_SLOTS, 0);           // has this weight gradient been written yet?
   gwritten[p.logits.buf] = 1;
@@ -238,6 +246,19 @@ static int run_backward(Ctx& c) {
           }
           break;
         }
+        if (smalln_ok(N, K) && c.grad(o.out).fmt == FMT_F32 && !o.relu && c.value(o.in0).ld % 4 == 0) {
+          SmallNArgs a{}; a.x = c.value(o.in0); a.dy = c.grad(o.out); a.W = c.param(o.w_slot, (int64_t)o.w_row0 * K);
+          a.dW = c.pgrad(o.w_slot, (int64_t)o.w_row0 * K); a.db = c.pgrad(o.b_slot, o.w_row0); a.B = B; a.K = K; a.C = N;
+          a.dx.p = nullptr; a.mask_src.p = nullptr;
+          if (grad_wanted(o.dx_view)) {
+            a.dx = c.grad(o.dx_view); a.dx_accumulate = is_written(o.dx_view);
+            if (p.acts[o.in0.buf].relu_out) a.mask_src = c.value(o.in0);
+          }
+          CUDA_OK(launch_smalln_bwd(a, c.dev.num_sms, c.st));
+          pwritten[o.w_slot] = 1;
+          if (a.dx.p) set_written(o.dx_view);
+          break;
+        }
         // dW[N,K] (+)= dY^T X ; db[N] += colsum(dY)
         GemmArgs g{};
         g.A = c.grad(o.out); g.a_kc = 0; g.B = c.value(o.in0); g.b_kc = 0;
@@ -265,7 +286,7 @@ static int run_backward(Ctx& c) {
         if (is_written(o.in0)) return FB200_EUNSUPPORTED;     // LN input has exactly one consumer in every program
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) lnrd_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
-        FB200_ROW_DISPATCH(a.N, CALL);
+        if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
         set_written(o.in0);
       } break;
@@ -275,7 +296,7 @@ static int run_backward(Ctx& c) {
         if (is_written(o.in1)) return FB200_EUNSUPPORTED;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) gate_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
-        FB200_ROW_DISPATCH(a.N, CALL);
+        if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
         set_written(o.in0); set_written(o.in1);
       } break;
@@ -287,7 +308,7 @@ static int run_backward(Ctx& c) {
         if (is_written(o.in1) || is_written(o.in2)) return FB200_EUNSUPPORTED;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) grb_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
-        FB200_ROW_DISPATCH(a.N, CALL);
+        if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
         set_written(o.in0); set_written(o.in1); set_written(o.in2);
       } break;
@@ -303,7 +324,7 @@ static int run_backward(Ctx& c) {
         if (is_written(o.in1) || is_written(o.in2)) return FB200_EUNSUPPORTED;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) meta_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
-        FB200_ROW_DISPATCH(a.N, CALL);
+        if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
         if (a.dv.p) set_written(o.in0);
         set_written(o.in1); set_written(o.in2);
@@ -324,8 +345,8 @@ static int run_backward(Ctx& c) {
   for (size_t base = 0; base < colsums.size(); base += 24) {
     ColsumBatch cb{}; cb.B = B; cb.nseg = 0;
     for (size_t i = base; i < colsums.size() && cb.nseg < 24; ++i) cb.seg[cb.nseg++] = colsums[i];
-    int gx = (B + 31) / 32; if (gx > 2 * c.dev.num_sms / cb.nseg + 1) gx = 2 * c.dev.num_sms / cb.nseg + 1; if (gx < 1) gx = 1;
-    colsum_batch_kernel<<<dim3(gx, cb.nseg), 256, 0, c.st>>>(cb);
+    int gx = (B + 63) / 64; if (gx > 8 * c.dev.num_sms / cb.nseg + 1) gx = 8 * c.dev.num_sms / cb.nseg + 1; if (gx < 1) gx = 1;   // ~64 rows per CTA
+    if (!c.gemm_only) colsum_batch_kernel<<<dim3(gx, cb.nseg), 256, 0, c.st>>>(cb);
     CUDA_OK(cudaGetLastError());
   }
   // inputs nobody differentiated through still owe the caller a defined gradient
@@ -459,6 +480,7 @@ int fb200_launch_count(const fb200_desc* d, int* forward, int* backward) {
     if (o.kind == OP_LINEAR) {
       const int ext = p.acts[o.dx_view.buf].ext;
       if (o.engine == 1) { ++ntc; int u = ++uses[o.w_slot]; if (u > rounds) rounds = u; }
+      if (o.engine == 0 && smalln_ok(o.out.cols, o.in0.cols) && !o.relu && p.acts[o.out.buf].ext == 3) { b += 1; continue; }
       b += (o.engine == 1 ? 0 : 1) + ((ext == 0 || (ext == 1 && need_dimg) || (ext == 2 && need_dtxt)) ? 1 : 0);
     } else if (o.kind != OP_CAST) b += 1;
   }
@@ -479,6 +501,7 @@ int fb200_list_gemms(const fb200_desc* d, int32_t* out, int cap) {
   };
   for (auto& o : p.ops) {
     if (o.kind != OP_LINEAR) continue;
+    if (o.engine == 0 && smalln_ok(o.out.cols, o.in0.cols) && !o.relu && p.acts[o.out.buf].ext == 3) continue;   // classifier head: warp-per-row kernels, not a GEMM
     const int eng = o.engine == 0 ? 0 : (d->dtype == FB200_BF16 ? 2 : 1);
     put(0, eng, d->B, o.out.cols, o.in0.cols);
     put(2, eng, o.out.cols, o.in0.cols, d->B);
@@ -499,6 +522,24 @@ int fb200_rng_advance(void* rng_state, uint64_t increment, void* stream) {
   rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint64_t*)rng_state, increment);
   CUDA_OK(cudaGetLastError());
   return FB200_OK;
+}
+
+
+/* debug / measurement aid: launch ONLY the GEMM kernels of one train step under desc (forward, dX chain, grouped
+ * weight gradients) on the given buffers - same kernels, grids and operands as fb200_head_train_step issues. */
+int fb200_debug_gemm_replay(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
+                            void* logits, void* grads, void* ws, void* stream) {
+  Plan plan; DeviceInfo dev;
+  int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
+  if (rc != FB200_OK) return rc;
+  if (!logits || !grads) return FB200_EBADARG;
+  char* w = (char*)ws;
+  float* dlog = (float*)(w + plan.ws_bytes - (((size_t)d->B * d->C * sizeof(float) + 255) & ~size_t(255)) - 256);
+  Ctx c{plan, params, img_feat, text_in, logits, dlog, nullptr, nullptr, (float*)grads, nullptr, 0, 0, nullptr, w, (cudaStream_t)stream, dev};
+  c.gemm_only = true;
+  rc = run_forward(c);
+  if (rc != FB200_OK) return rc;
+  return run_backward(c);
 }
 
 int fb200_head_forward(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,

@@ -491,6 +491,108 @@ __global__ void __launch_bounds__(256) ce_pass2_kernel(const float* __restrict__
   if (dlogits) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dlogits[i] *= inv;
 }
 
+
+// ------------------------------------------------------------------ small-N Linear (the classifier heads)
+// y[B,C] = x[B,K] W[C,K]^T + b with C <= 8 (num_classes): a GEMM tile would be >90% padding, so one warp
+// owns one row, lanes split K in 128-bit chunks, W (C*K*4 bytes <= 16 KB) is served by L1, and the C dot
+// products finish with warp shuffles.  Backward produces dX (coalesced 128-bit stores), dW and db in one pass.
+struct SmallNArgs {
+  TRef x, y, dy, dx;           // y / dy: [B,C] fp32 (ld = C)
+  TRef mask_src;               // dX *= [mask_src > 0] when .p != nullptr
+  const float *W, *bias;
+  float *dW, *db;
+  int dx_accumulate;
+  int B, K, C;
+};
+template <int MAXC>
+__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_fwd_kernel(const SmallNArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nch = a.K / 4;
+  for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < a.B; row += (int64_t)gridDim.x * ROW_WARPS) {
+    float acc[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) acc[c] = 0.f;
+    for (int j = lane; j < nch; j += 32) {
+      const float4 xv = ld4(a.x, row, j * 4);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < a.C) {
+          const float4 w = __ldg((const float4*)(a.W + (int64_t)c * a.K + j * 4));
+          acc[c] += (xv.x * w.x + xv.y * w.y) + (xv.z * w.z + xv.w * w.w);
+        }
+      }
+    }
+    float out = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) { const float v = warp_sum(acc[c]); if (lane == c) out = v; }
+    if (lane < a.C) ((float*)a.y.p)[row * a.y.ld + lane] = out + (a.bias ? __ldg(a.bias + lane) : 0.f);
+  }
+}
+template <int MAXC, int CH>      // CH = 128-bit chunks of K per lane (K <= 128 * CH)
+__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallNArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nch = a.K / 4;
+  float4 dw[MAXC][CH];
+  float dbacc[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) { dbacc[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) dw[c][i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < a.B; row += (int64_t)gridDim.x * ROW_WARPS) {
+    float dl[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) { dl[c] = c < a.C ? __ldg((const float*)a.dy.p + row * a.dy.ld + c) : 0.f; dbacc[c] += dl[c]; }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int j = lane + 32 * i;
+      if (j < nch) {
+        const float4 xv = ld4(a.x, row, j * 4);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          if (c < a.C) {
+            const float4 w = __ldg((const float4*)(a.W + (int64_t)c * a.K + j * 4));
+            g.x += dl[c] * w.x; g.y += dl[c] * w.y; g.z += dl[c] * w.z; g.w += dl[c] * w.w;
+            dw[c][i].x += dl[c] * xv.x; dw[c][i].y += dl[c] * xv.y; dw[c][i].z += dl[c] * xv.z; dw[c][i].w += dl[c] * xv.w;
+          }
+        }
+        if (a.dx.p) {
+          if (a.mask_src.p) { const float4 m = ld4(a.mask_src, row, j * 4); g.x = m.x > 0.f ? g.x : 0.f; g.y = m.y > 0.f ? g.y : 0.f; g.z = m.z > 0.f ? g.z : 0.f; g.w = m.w > 0.f ? g.w : 0.f; }
+          if (a.dx_accumulate) { const float4 o = ld4(a.dx, row, j * 4); g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+          st4(a.dx, row, j * 4, g);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (c < a.C) {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nch) {
+          float* d = a.dW + (int64_t)c * a.K + j * 4;
+          atomicAdd(d, dw[c][i].x); atomicAdd(d + 1, dw[c][i].y); atomicAdd(d + 2, dw[c][i].z); atomicAdd(d + 3, dw[c][i].w);
+        }
+      }
+      if (lane == 0) atomicAdd(a.db + c, dbacc[c]);      // every lane saw every row of its warp: lane 0 speaks for the warp
+    }
+  }
+}
+inline bool smalln_ok(int C, int K) { return C <= 8 && K % 4 == 0 && K <= 512; }
+inline cudaError_t launch_smalln_fwd(const SmallNArgs& a, int num_sms, cudaStream_t st) {
+  int grid = (a.B + ROW_WARPS * 2 - 1) / (ROW_WARPS * 2); if (grid > num_sms * 4) grid = num_sms * 4; if (grid < 1) grid = 1;
+  smalln_fwd_kernel<8><<<grid, ROW_WARPS * 32, 0, st>>>(a);
+  return cudaGetLastError();
+}
+inline cudaError_t launch_smalln_bwd(const SmallNArgs& a, int num_sms, cudaStream_t st) {
+  int grid = (a.B + ROW_WARPS * 16 - 1) / (ROW_WARPS * 16); if (grid > num_sms) grid = num_sms; if (grid < 1) grid = 1;   // >= 16 rows per warp amortise the dW atomics
+  if (a.K <= 128) smalln_bwd_kernel<8, 1><<<grid, ROW_WARPS * 32, 0, st>>>(a);
+  else if (a.K <= 256) smalln_bwd_kernel<8, 2><<<grid, ROW_WARPS * 32, 0, st>>>(a);
+  else smalln_bwd_kernel<8, 4><<<grid, ROW_WARPS * 32, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ format conversion
 // fp32 [rows, cols] (ld_in) -> FMT_PAIR / FMT_BF16 / FMT_F32 copy (ld_out); any alignment.
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ in, int ld_in, TRef out, int64_t rows, int cols) {
@@ -524,21 +626,38 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) colsum_kernel(TRef x, int B, i
 struct ColsumSeg { TRef x; int N; float* dst; };
 struct ColsumBatch { ColsumSeg seg[24]; int nseg; int B; };
 __global__ void __launch_bounds__(256) colsum_batch_kernel(const ColsumBatch a) {
+  __shared__ __align__(16) float4 red[256];
   const ColsumSeg sg = a.seg[blockIdx.y];
   const int nv = sg.N / 4;                                   // float4 columns
-  const int lanes = nv < 256 ? nv : 256;                     // threads across one row
-  const int rows_per_iter = 256 / lanes;
+  const int lanes = nv < 256 ? nv : 256;                     // threads across one row (power of two for the widths in use, else rounded down)
+  const int groups = 256 / lanes;                            // row groups working side by side
   const int t = threadIdx.x;
-  if (t >= lanes * rows_per_iter) return;
   const int r_off = t / lanes, c_lane = t % lanes;
-  for (int cg = c_lane; cg < nv; cg += lanes) {
+  const bool active = t < lanes * groups;
+  // this CTA's slab of rows
+  const int64_t rows_per_cta = (a.B + gridDim.x - 1) / gridDim.x;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta, r_end = r_begin + rows_per_cta < a.B ? r_begin + rows_per_cta : a.B;
+  for (int cg0 = 0; cg0 < nv; cg0 += lanes) {
+    const int cg = cg0 + c_lane;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = (int64_t)blockIdx.x * rows_per_iter + r_off; r < a.B; r += (int64_t)gridDim.x * rows_per_iter) {
-      const float4 v = ld4(sg.x, r, cg * 4);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (active && cg < nv) {
+      int64_t r = r_begin + r_off;
+      // 4 independent loads in flight per thread
+      for (; r + 3 * groups < r_end; r += 4 * groups) {
+        const float4 v0 = ld4(sg.x, r, cg * 4), v1 = ld4(sg.x, r + groups, cg * 4), v2 = ld4(sg.x, r + 2 * groups, cg * 4), v3 = ld4(sg.x, r + 3 * groups, cg * 4);
+        acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+        acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+      }
+      for (; r < r_end; r += groups) { const float4 v = ld4(sg.x, r, cg * 4); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
     }
-    float* d = sg.dst + cg * 4;
-    atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+    __syncthreads();
+    red[t] = acc;
+    __syncthreads();
+    if (active && r_off == 0 && cg < nv) {
+      for (int g2 = 1; g2 < groups; ++g2) { const float4 v = red[g2 * lanes + c_lane]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      float* d = sg.dst + cg * 4;
+      atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+    }
   }
 }
 
