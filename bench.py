@@ -405,6 +405,7 @@ def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype, model):
     e1.record(stream)
     torch.cuda.synchronize()
     tot_ms = e0.elapsed_time(e1) / reps
+    achieved = tot_flops / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
     bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm = peaks.get("hbm_gbs", 6650.0)
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"

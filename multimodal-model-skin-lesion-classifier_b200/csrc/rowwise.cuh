@@ -564,6 +564,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallN
       }
     }
   }
+  // warp partials -> CTA totals in shared memory (fast shared atomics) -> one global atomic per element per CTA
+  extern __shared__ float sm_dw[];                       // [C*K + C], zeroed below
+  const int tot = a.C * a.K + a.C;
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) sm_dw[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     if (c < a.C) {
@@ -571,12 +576,17 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallN
       for (int i = 0; i < CH; ++i) {
         const int j = lane + 32 * i;
         if (j < nch) {
-          float* d = a.dW + (int64_t)c * a.K + j * 4;
+          float* d = sm_dw + c * a.K + j * 4;
           atomicAdd(d, dw[c][i].x); atomicAdd(d + 1, dw[c][i].y); atomicAdd(d + 2, dw[c][i].z); atomicAdd(d + 3, dw[c][i].w);
         }
       }
-      if (lane == 0) atomicAdd(a.db + c, dbacc[c]);      // every lane saw every row of its warp: lane 0 speaks for the warp
+      if (lane == 0) atomicAdd(sm_dw + a.C * a.K + c, dbacc[c]);      // every lane saw every row of its warp: lane 0 speaks for the warp
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    const float v = sm_dw[i];
+    if (i < a.C * a.K) atomicAdd(a.dW + i, v); else atomicAdd(a.db + (i - a.C * a.K), v);
   }
 }
 inline bool smalln_ok(int C, int K) { return C <= 8 && K % 4 == 0 && K <= 512; }
@@ -586,10 +596,11 @@ inline cudaError_t launch_smalln_fwd(const SmallNArgs& a, int num_sms, cudaStrea
   return cudaGetLastError();
 }
 inline cudaError_t launch_smalln_bwd(const SmallNArgs& a, int num_sms, cudaStream_t st) {
-  int grid = (a.B + ROW_WARPS * 16 - 1) / (ROW_WARPS * 16); if (grid > num_sms) grid = num_sms; if (grid < 1) grid = 1;   // >= 16 rows per warp amortise the dW atomics
-  if (a.K <= 128) smalln_bwd_kernel<8, 1><<<grid, ROW_WARPS * 32, 0, st>>>(a);
-  else if (a.K <= 256) smalln_bwd_kernel<8, 2><<<grid, ROW_WARPS * 32, 0, st>>>(a);
-  else smalln_bwd_kernel<8, 4><<<grid, ROW_WARPS * 32, 0, st>>>(a);
+  int grid = (a.B + ROW_WARPS * 2 - 1) / (ROW_WARPS * 2); if (grid > num_sms * 2) grid = num_sms * 2; if (grid < 1) grid = 1;
+  const size_t smem = (size_t)(a.C * a.K + a.C) * sizeof(float);          // <= 8 * 512 * 4 + 32 = 16.4 KB
+  if (a.K <= 128) smalln_bwd_kernel<8, 1><<<grid, ROW_WARPS * 32, smem, st>>>(a);
+  else if (a.K <= 256) smalln_bwd_kernel<8, 2><<<grid, ROW_WARPS * 32, smem, st>>>(a);
+  else smalln_bwd_kernel<8, 4><<<grid, ROW_WARPS * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,58 @@
+"""Turn the ncu outputs under gpurun_out/ into the committed summaries under profiles/."""
+import csv, json, re, subprocess, sys, collections, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+
+def launch_list():
+    with open(os.path.join(G, f"launches_{tag}.csv")) as f:
+        lines = [l for l in f if l.startswith('"')]
+    r = csv.reader(lines); hdr = next(r)
+    ki, vi, ui, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Grid Size")
+    rows = list(r)
+    marks = [i for i, row in enumerate(rows) if "rng_advance" in row[ki]]
+    s, e = marks[0] + 1, marks[1] + 1
+    out, agg, tot = [], collections.OrderedDict(), 0.0
+    for row in rows[s:e]:
+        v = float(row[vi].replace(",", "")); v = v / 1000 if row[ui] == "ns" else v
+        name = re.sub(r"\(.*", "", row[ki]).replace("fb200::", "").replace("void ", "")
+        out.append(f"{v:9.1f} us  grid {row[gi]:>14s}  {name}")
+        a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v; tot += v
+    with open(os.path.join(P, f"{tag}_launch_list_cfg2_B4096.txt"), "w") as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none; one train step (forward + CE + backward), cfg2 crossattention, B=4096, fp32-strict\n")
+        f.write(f"# cold-cache, serialised durations: compare SHARES, not absolutes.  step total {tot:.1f} us over {e - s} launches\n")
+        f.write("# --- per kernel ---\n")
+        for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{t:9.1f} us  {100 * t / tot:5.1f}%  x{c:3d}  {n}\n")
+        f.write("# --- launch order ---\n" + "\n".join(out) + "\n")
+    return tot, agg
+
+def full():
+    rep = os.path.join(G, f"prof_{tag}_tc.ncu-rep")
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines())); hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    want = ["Kernel Name", "Grid Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_sectors_srcunit_tex_op_read.sum"]
+    recs = []
+    for r in rows[2:]:
+        recs.append({w: (r[idx[w]] + " " + units[idx[w]]).strip() for w in want if w in idx})
+    json.dump(recs, open(os.path.join(P, f"{tag}_tc_gemm_ncu_full_summary.json"), "w"), indent=1)
+    def num(x): return float(x.split()[0].replace(",", ""))
+    def to_bytes(x):
+        v, u = x.split()[0], x.split()[1] if len(x.split()) > 1 else "byte"
+        return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    first = [r for r in recs if "tc_gemm_kernel" in r["Kernel Name"]][0]
+    tr = to_bytes(first["dram__bytes_read.sum"]) + to_bytes(first["dram__bytes_write.sum"])
+    json.dump({"kernel": first["Kernel Name"][:80], "grid": first["Grid Size"], "dram_bytes_per_launch": tr,
+               "note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, cold L2)"},
+              open(os.path.join(P, f"{tag}_dominant_kernel_traffic.json"), "w"), indent=1)
+    return recs
+
+if __name__ == "__main__":
+    tot, agg = launch_list(); print("launch list total", tot)
+    for r in full(): print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed")})
