@@ -259,7 +259,8 @@ simt_gemm_kernel(const GemmArgs g) {
 // Host-side launcher: picks the tile shape and split-K factor.
 inline cudaError_t launch_simt_gemm(GemmArgs g, int num_sms, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-  const bool big = (g.M >= 256 && g.N >= 128) || (g.M >= 128 && g.N >= 256);
+  bool big = (g.M >= 256 && g.N >= 128) || (g.M >= 128 && g.N >= 256);
+  if (big && ((g.M + 127) / 128) * ((g.N + 127) / 128) < num_sms) big = false;      // too few 128x128 tiles to fill the chip: smaller tiles
   int bm = big ? 128 : 64, bn = big ? 128 : 64;
   int tiles = ((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn);
   // split-K only where the epilogue is a plain sum into fp32 (weight gradients)
