@@ -66,6 +66,10 @@ struct Ctx {
   }
   const float* param(int slot, int64_t elem_off = 0) const { return (const float*)params[slot] + elem_off; }
   float* pgrad(int slot, int64_t elem_off = 0) const { return grads + p.goff[slot] + elem_off; }
+  void enable_fixup(GemmArgs& g) const {       // small-batch FFMA GEMMs: split K across CTAs, last slice fixes up
+    if (p.splitk_bytes == 0 || g.M > 128) return;
+    g.partial = (float*)(ws + p.splitk_off); g.partial_bytes = p.splitk_bytes; g.counters = (unsigned*)(ws + p.counters_off);
+  }
   DropSpec drop(const Op& o) const {
     DropSpec s; s.mask = nullptr; s.seed = seed; s.offset = offset; s.state = rng_state; s.p = o.p; s.site = o.site; s.active = 0;
     if (p.d.train && o.site >= 0 && o.p > 0.f) { s.active = 1; if (masks && masks[o.site]) s.mask = masks[o.site]; }
@@ -98,6 +102,7 @@ static TRef weight_operand(const Ctx& c, const Op& o) {
 
 static int run_forward(Ctx& c) {
   const Plan& p = c.p; const int B = p.d.B;
+  if (p.splitk_bytes && !c.gemm_only) CUDA_OK(cudaMemsetAsync(c.ws + p.counters_off, 0, 4096 * sizeof(unsigned), c.st));
   for (size_t base = 0; base < p.wprep.size(); base += 32) {
     PrepArgs a{}; a.fmt = p.fmt; a.nseg = 0;
     for (size_t i = base; i < p.wprep.size() && a.nseg < 32; ++i) {
@@ -138,6 +143,7 @@ static int run_forward(Ctx& c) {
         g.A = c.value(o.in0); g.B = make_ref((void*)c.param(o.w_slot, (int64_t)o.w_row0 * o.in0.cols), o.in0.cols, FMT_F32);
         g.C = c.value(o.out); g.M = B; g.N = o.out.cols; g.K = o.in0.cols; g.a_kc = 1; g.b_kc = 1;
         g.bias = c.param(o.b_slot, o.w_row0); g.relu = o.relu; g.mask_src.p = nullptr; g.accumulate = 0; g.split_k = 1; g.colsum_a = nullptr;
+        c.enable_fixup(g);
         CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
       } break;
       case OP_LNRD: {
@@ -275,6 +281,7 @@ static int run_backward(Ctx& c) {
           h.mask_src.p = nullptr;
           if (p.acts[o.in0.buf].relu_out) h.mask_src = c.value(o.in0);
           h.accumulate = is_written(o.dx_view); h.split_k = 1; h.colsum_a = nullptr;
+          c.enable_fixup(h);
           CUDA_OK(launch_simt_gemm(h, c.dev.num_sms, c.st));
           set_written(o.dx_view);
         }

@@ -354,6 +354,8 @@ int build_plan(const fb200_desc& d, Plan& p) {
     if (o.kind == OP_LNRD || o.kind == OP_GRB) { o.stats_off = cur; cur = align(cur + (size_t)d.B * 2 * sizeof(float)); }
     if (o.kind == OP_META) { o.stats_off = cur; cur = align(cur + (size_t)d.B * 4 * sizeof(float)); }
   }
+  // small batches on the FFMA path: split-K fix-up scratch (partial tiles) + per-tile arrival counters
+  if (!p.use_tc || d.B < 256) { p.splitk_off = cur; p.splitk_bytes = (size_t)8 << 20; cur = align(cur + p.splitk_bytes); p.counters_off = cur; cur = align(cur + 4096 * sizeof(unsigned)); }
   // tail: dlogits of the fused train step (exec.cu addresses it from the end)
   cur = align(cur + (size_t)d.B * d.C * sizeof(float));
   p.ws_bytes = cur + 256;

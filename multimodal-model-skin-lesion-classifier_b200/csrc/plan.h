@@ -81,6 +81,7 @@ struct Plan {
   int64_t goff[NUM_SLOTS];           // element offset in the flat gradient buffer, -1 if not live
   int64_t grad_elems = 0;
   size_t ws_bytes = 0;
+  size_t splitk_off = 0, splitk_bytes = 0, counters_off = 0;   // FFMA split-K fix-up scratch (small batches)
   float drop_p[FB200_NUM_DROPOUT_SITES] = {};
   int drop_cols[FB200_NUM_DROPOUT_SITES] = {};
   double flops = 0, bytes = 0; int64_t live_params = 0;

@@ -23,6 +23,11 @@ struct GemmArgs {
   int accumulate;          // C += result (non-atomic read-modify-write)
   int split_k;             // >1: grid.z slices of K, results added with fp32 atomics (C must be FMT_F32, pre-zeroed or accumulate semantics)
   float* colsum_a;         // TN mode: colsum_a[m] += sum_k A(m,k)  (atomic), or nullptr
+  // split-K with fix-up (small batches: the only parallelism left is along K): every slice parks its partial tile
+  // in `partial`, the last slice to arrive (per-tile counter) sums them and runs the normal epilogue
+  float* partial;          // [split][tiles][BM*BN] scratch, or nullptr -> atomic split-K
+  unsigned* counters;      // [tiles], zero before the launch; the finishing CTA resets its counter
+  size_t partial_bytes;    // capacity of `partial`
 };
 
 template <int BM, int BN, int BK, int TM, int TN>
@@ -201,6 +206,46 @@ simt_gemm_kernel(const GemmArgs g) {
     buf ^= 1;
   }
 
+  // ---- split-K fix-up: park the partial tile, the last arriving slice reduces and continues to the epilogue
+  const bool fixup = g.split_k > 1 && g.partial != nullptr;
+  if (fixup) {
+    __shared__ int s_last;
+    const int tiles = gridDim.x * gridDim.y, tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    float* mine = g.partial + ((size_t)blockIdx.z * tiles + tile_id) * (BM * BN);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int h = 0; h < HN; ++h) {
+        const int lr = (i / 4) * (BM / HM) + ty * 4 + (i % 4), lc = h * (BN / HN) + tx * 4;
+        *(float4*)(mine + lr * BN + lc) = make_float4(acc[i][h * 4], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]);
+      }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned prev = atomicAdd(g.counters + tile_id, 1u);
+      s_last = (prev == (unsigned)g.split_k - 1);
+      if (s_last) g.counters[tile_id] = 0;                 // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // fixed summation order (slice 0, 1, 2, ...) whoever arrives last: results stay bit-reproducible run to run
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int z = 0; z < g.split_k; ++z) {
+      const float* other = g.partial + ((size_t)z * tiles + tile_id) * (BM * BN);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int h = 0; h < HN; ++h) {
+          const int lr = (i / 4) * (BM / HM) + ty * 4 + (i % 4), lc = h * (BN / HN) + tx * 4;
+          const float4 o = __ldcg((const float4*)(other + lr * BN + lc));
+          acc[i][h * 4] += o.x; acc[i][h * 4 + 1] += o.y; acc[i][h * 4 + 2] += o.z; acc[i][h * 4 + 3] += o.w;
+        }
+    }
+  }
   // ---- epilogue
   const bool c_vec = (g.C.ld % 4 == 0) && ((((uintptr_t)g.C.p) & 15) == 0 || g.C.fmt == FMT_BF16 && (((uintptr_t)g.C.p) & 7) == 0) &&
                      (g.mask_src.p == nullptr || g.mask_src.ld % 4 == 0);
@@ -213,7 +258,7 @@ simt_gemm_kernel(const GemmArgs g) {
       int64_t n = n0 + h * (BN / HN) + tx * 4;
       if (n >= g.N) continue;
       float v[4] = {acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]};
-      if (g.split_k > 1) {
+      if (g.split_k > 1 && !fixup) {
         float* c = (float*)g.C.p + m * g.C.ld + n;
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (n + j < g.N) atomicAdd(c + j, v[j]);
@@ -263,14 +308,23 @@ inline cudaError_t launch_simt_gemm(GemmArgs g, int num_sms, cudaStream_t st) {
   if (big && ((g.M + 127) / 128) * ((g.N + 127) / 128) < num_sms) big = false;      // too few 128x128 tiles to fill the chip: smaller tiles
   int bm = big ? 128 : 64, bn = big ? 128 : 64;
   int tiles = ((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn);
-  // split-K only where the epilogue is a plain sum into fp32 (weight gradients)
   int split = 1;
-  if (g.split_k != 1 && g.C.fmt == FMT_F32 && !g.bias && !g.relu && !g.mask_src.p) {
+  if (g.partial && g.counters && tiles <= 4096) {
+    // fix-up split-K (any epilogue): fill ~2 waves, keep >= 2 k-steps of 16 per slice
+    int want = (2 * num_sms + tiles - 1) / tiles;
+    int maxs = g.K / 32; if (maxs < 1) maxs = 1;
+    split = want > maxs ? maxs : want;
+    const int cap = (int)(g.partial_bytes / ((size_t)tiles * bm * bn * sizeof(float)));
+    if (split > cap) split = cap;
+    if (split < 2) { split = 1; }
+  } else if (g.split_k != 1 && g.C.fmt == FMT_F32 && !g.bias && !g.relu && !g.mask_src.p) {
+    // atomic split-K only where the epilogue is a plain sum into fp32 (weight gradients)
     int want = (2 * num_sms + tiles - 1) / tiles;
     int maxs = (g.K + 255) / 256;               // keep >= 256 reduction elements per slice
     split = want < 1 ? 1 : (want > maxs ? maxs : want);
     if (split < 1) split = 1;
   }
+  if (split == 1) { g.partial = nullptr; }
   g.split_k = split;
   dim3 grid((g.N + bn - 1) / bn, (g.M + bm - 1) / bm, split);
   if (big) simt_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, st>>>(g);
