@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--dtype", default=None, choices=[None, "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"], help="GEMM engine policy (auto: tcgen05 from B > 128 in fp32, always in bf16)")
     ap.add_argument("--sweep", default="", help="comma-separated extra per-GPU batch sizes reported under 'sweep'")
     return ap.parse_args()
 
@@ -171,7 +172,8 @@ def main():
     def build(Bsz):
         torch.manual_seed(1234)
         model = fb.MultimodalModel(Cn, 8, dev, f"identity:{F}", "one-hot-encoder" if tm == 0 else "tab-transformer",
-                                   vocab_size=V if V else 91, text_encoder_dim_output=T, attention_mecanism=mech, compute_dtype=dtype).to(dev)
+                                   vocab_size=V if V else 91, text_encoder_dim_output=T, attention_mecanism=mech, compute_dtype=dtype,
+                                   engine_flags={"auto": 0, "simt": 4, "tc": 8}[args.engine]).to(dev)
         model.train()
         return model
 
@@ -312,7 +314,7 @@ def main():
     e2e_value, h2d, d2h = run_e2e(B, K, W)
 
     # ---- roofline of the dominant kernel (the GEMM), replayed live through the C ABI with CUDA events
-    desc = fb.make_desc(mech, B, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype, train=True)
+    desc = fb.make_desc(mech, B, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype, train=True, flags={"auto": 0, "simt": 4, "tc": 8}[args.engine])
     flops, nbytes, plive = _lib.algorithmic_work(desc)
     peaks = {}
     try:

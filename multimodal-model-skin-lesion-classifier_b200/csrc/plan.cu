@@ -192,8 +192,8 @@ int build_plan(const fb200_desc& d, Plan& p) {
     p.error = "fusion strings that concatenate two modalities need n = 2"; return FB200_EBADARG;
   }
   // engine policy: bf16 always rides the tensor cores; fp32 switches to the 3xTF32 tensor path once the
-  // batch is large enough to be compute-bound (below that the exact FFMA kernel streams fp32 weights once)
-  p.use_tc = !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B >= 256);
+  // batch exceeds 128 rows (measured crossover; below that the exact FFMA kernel with split-K fix-up wins)
+  p.use_tc = !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B > 128);
   p.fmt = d.dtype == FB200_BF16 ? FMT_BF16 : FMT_F32;    // fp32-strict keeps everything fp32 in memory (hi/lo split happens in smem)
 
   Builder b(p);
@@ -355,7 +355,7 @@ int build_plan(const fb200_desc& d, Plan& p) {
     if (o.kind == OP_META) { o.stats_off = cur; cur = align(cur + (size_t)d.B * 4 * sizeof(float)); }
   }
   // small batches on the FFMA path: split-K fix-up scratch (partial tiles) + per-tile arrival counters
-  if (!p.use_tc || d.B < 256) { p.splitk_off = cur; p.splitk_bytes = (size_t)8 << 20; cur = align(cur + p.splitk_bytes); p.counters_off = cur; cur = align(cur + 4096 * sizeof(unsigned)); }
+  if (!p.use_tc || d.B <= 128) { p.splitk_off = cur; p.splitk_bytes = (size_t)8 << 20; cur = align(cur + p.splitk_bytes); p.counters_off = cur; cur = align(cur + 4096 * sizeof(unsigned)); }
   // tail: dlogits of the fused train step (exec.cu addresses it from the end)
   cur = align(cur + (size_t)d.B * d.C * sizeof(float));
   p.ws_bytes = cur + 256;
