@@ -188,6 +188,14 @@ int fb200_head_train_step(const fb200_desc* d, const void* const* params,
                           void* logits, float* loss_out, void* grads,
                           void* d_img_feat, void* d_text_in, void* ws, void* stream);
 
+/* Fused multi-tensor Adam step with torch.optim.Adam semantics (coupled L2 weight decay, bias correction, eps
+ * outside the square root) - the optimizer the reference builds right after the path: optim.Adam(model.parameters(),
+ * lr=5e-5, weight_decay=1e-4) (train_pad_20.py:54) and steps at :113.  Host arrays of ntensors device pointers;
+ * `step` is the 1-based step count; grads are multiplied by grad_scale first (1/world_size style rescaling). */
+int fb200_adam_step(int ntensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                    const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                    float grad_scale, void* stream);
+
 /* ---- primitives (exported for unit parity tests and micro-benchmarks) --------------- */
 /* C[M,N] (+)= op(A) * op(B) (+ bias) with fp32 tensors.
  * layout: 0 = NT  C = A[M,K] * B[N,K]^T   (nn.Linear forward)

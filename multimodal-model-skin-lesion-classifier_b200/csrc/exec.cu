@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <algorithm>
+#include <cmath>
 
 namespace fb200 {
 
@@ -522,6 +523,31 @@ __global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { state[1] += 
 
 /* debug: device buffer of >= 8*k_blocks int64 receiving pipeline time stamps of CTA (0,0,0) of every tcgen05 GEMM launched afterwards; NULL disables */
 int fb200_debug_tc_trace(void* device_buf) { tc_trace_buffer() = (long long*)device_buf; return FB200_OK; }
+
+
+int fb200_adam_step(int ntensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                    const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                    float grad_scale, void* stream) {
+  if (ntensors < 0 || (ntensors && (!params || !grads || !exp_avg || !exp_avg_sq || !numel)) || step < 1) return FB200_EBADARG;
+  DeviceInfo dev; int rc = get_device_info(dev); if (rc != FB200_OK) return rc;
+  const float bc1 = 1.f - (float)std::pow((double)beta1, (double)step), bc2 = 1.f - (float)std::pow((double)beta2, (double)step);
+  for (int base = 0; base < ntensors; base += 48) {
+    AdamBatch a{}; a.nseg = 0; a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.bc1 = bc1; a.bc2 = bc2; a.grad_scale = grad_scale;
+    int64_t maxn = 0;
+    for (int i = base; i < ntensors && a.nseg < 48; ++i) {
+      if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i] || numel[i] < 0) return FB200_EBADARG;
+      if (numel[i] == 0) continue;
+      if (a.nseg == 0 && !is_device_ptr(params[i])) return FB200_EUNSUPPORTED;
+      a.seg[a.nseg++] = AdamSeg{(float*)params[i], (const float*)grads[i], (float*)exp_avg[i], (float*)exp_avg_sq[i], numel[i]};
+      if (numel[i] > maxn) maxn = numel[i];
+    }
+    if (a.nseg == 0) continue;
+    int gx = (int)((maxn / 4 + 255) / 256); if (gx > dev.num_sms * 2) gx = dev.num_sms * 2; if (gx < 1) gx = 1;
+    adam_kernel<<<dim3(gx, a.nseg), 256, 0, (cudaStream_t)stream>>>(a);
+    CUDA_OK(cudaGetLastError());
+  }
+  return FB200_OK;
+}
 
 int fb200_rng_advance(void* rng_state, uint64_t increment, void* stream) {
   if (!rng_state) return FB200_EBADARG;

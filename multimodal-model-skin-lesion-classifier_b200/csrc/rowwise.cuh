@@ -604,6 +604,36 @@ inline cudaError_t launch_smalln_bwd(const SmallNArgs& a, int num_sms, cudaStrea
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------ fused Adam (multi-tensor)
+// torch.optim.Adam semantics as the reference uses it (Adam(lr=5e-5, weight_decay=1e-4), train_pad_20.py:54):
+// coupled L2 (g += wd * p), bias-corrected moments, eps outside the sqrt.  One launch updates up to 48 tensors.
+struct AdamSeg { float* p; const float* g; float* m; float* v; int64_t n; };
+struct AdamBatch { AdamSeg seg[48]; int nseg; float lr, b1, b2, eps, wd, bc1, bc2, grad_scale; };
+__global__ void __launch_bounds__(256) adam_kernel(const AdamBatch a) {
+  const AdamSeg sg = a.seg[blockIdx.y];
+  const float step_size = a.lr / a.bc1, inv_sqrt_bc2 = rsqrtf(a.bc2);
+  const int64_t n4 = sg.n / 4;
+  const bool vec = ((((uintptr_t)sg.p) | ((uintptr_t)sg.g) | ((uintptr_t)sg.m) | ((uintptr_t)sg.v)) & 15) == 0;
+  auto upd = [&](float& p, float g, float& m, float& v) {
+    g = g * a.grad_scale + a.wd * p;
+    m = a.b1 * m + (1.f - a.b1) * g;
+    v = a.b2 * v + (1.f - a.b2) * g * g;
+    p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + a.eps);
+  };
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 p = ((float4*)sg.p)[i], m = ((float4*)sg.m)[i], v = ((float4*)sg.v)[i];
+      const float4 g = __ldg((const float4*)sg.g + i);
+      upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+      ((float4*)sg.p)[i] = p; ((float4*)sg.m)[i] = m; ((float4*)sg.v)[i] = v;
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += (int64_t)gridDim.x * blockDim.x) upd(sg.p[i], sg.g[i], sg.m[i], sg.v[i]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += (int64_t)gridDim.x * blockDim.x) upd(sg.p[i], sg.g[i], sg.m[i], sg.v[i]);
+  }
+}
+
 // ------------------------------------------------------------------ format conversion
 // fp32 [rows, cols] (ld_in) -> FMT_PAIR / FMT_BF16 / FMT_F32 copy (ld_out); any alignment.
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ in, int ld_in, TRef out, int64_t rows, int cols) {

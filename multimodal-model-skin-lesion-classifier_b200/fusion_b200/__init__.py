@@ -11,5 +11,6 @@ from . import _lib
 from ._lib import Fb200Error
 from .head import FusedCrossEntropyLoss, FusedHeadFunction, cross_entropy, make_desc
 from .model import GraphedTrainStep, MultimodalModel
+from .optim import FusedAdam
 
-__all__ = ["MultimodalModel", "GraphedTrainStep", "FusedCrossEntropyLoss", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]
+__all__ = ["MultimodalModel", "GraphedTrainStep", "FusedAdam", "FusedCrossEntropyLoss", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]
