@@ -202,6 +202,7 @@ def main():
         cw = class_weights(ys)
 
         use_graph = not args.no_graph
+        live_ranges = _lib.grad_live_ranges(fb.make_desc(mech, Bsz, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype))
         denoms = [None] * nb
         if world > 1:                                            # global weighted-CE denominator, static buffers
             denoms = [torch.zeros(1, device=dev) for _ in range(nb)]
@@ -222,7 +223,7 @@ def main():
                 loss, _ = model.forward_loss(xs[j], ts[j], ys[j], cw, denom=denoms[j])
                 flat = model.flat_grad
             if world > 1:
-                dist.all_reduce(flat)                            # summed: the global denominator already averages
+                fb.dp.allreduce_gradients(flat, ranges=live_ranges)   # SUM: the global denominator already averages; only live slices travel
             return loss
 
         for i in range(warm):
@@ -273,6 +274,7 @@ def main():
                 s["ready"].record(copy_stream)
 
         use_graph = not args.no_graph
+        live_ranges2 = _lib.grad_live_ranges(fb.make_desc(mech, Bsz, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype))
         for s in slots:
             s["denom"] = torch.zeros(1, device=dev) if world > 1 else None
             s["graph"] = fb.GraphedTrainStep(m2, s["x"], s["t"], s["y"], cw, denom=s["denom"]) if use_graph else None
@@ -292,7 +294,7 @@ def main():
                 else:
                     loss, _ = m2.forward_loss(s["x"], s["t"], s["y"], cw, denom=s["denom"]); flat = m2.flat_grad
                 if world > 1:
-                    dist.all_reduce(flat)
+                    fb.dp.allreduce_gradients(flat, ranges=live_ranges2)
                 host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)       # D2H read of the step's result
                 s["free"].record(cur)
         for s in slots:

@@ -115,6 +115,9 @@ int          fb200_param_shape(const fb200_desc* d, int slot, int64_t* rows, int
  * reference leaves .grad = None for it under this mechanism. */
 int64_t      fb200_grad_offset(const fb200_desc* d, int slot);
 int64_t      fb200_grad_elems(const fb200_desc* d);  /* size of the flat gradient buffer (fp32 elements) */
+/* Element ranges [begin, end) of the flat gradient buffer that can be non-zero (the W_q / W_k rows of S=1 attention are
+ * structural zeros): writes up to cap pairs into out, returns the number of ranges.  The DP all-reduce moves only these. */
+int          fb200_grad_live_ranges(const fb200_desc* d, int64_t* out, int cap);
 int          fb200_workspace_bytes(const fb200_desc* d, size_t* bytes);
 float        fb200_dropout_p(const fb200_desc* d, int site);   /* 0 when the site is unused */
 int          fb200_dropout_shape(const fb200_desc* d, int site, int64_t* rows, int64_t* cols);

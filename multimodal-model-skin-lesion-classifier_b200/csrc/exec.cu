@@ -575,6 +575,28 @@ int fb200_debug_gemm_replay(const fb200_desc* d, const void* const* params, cons
   return run_backward(c);
 }
 
+
+int fb200_grad_live_ranges(const fb200_desc* d, int64_t* out, int cap) {
+  if (!d || !out || cap < 1) return FB200_EBADARG;
+  Plan p; int rc = build_plan(*d, p); if (rc != FB200_OK) return rc;
+  // per slot: rows that can be non-zero.  in_proj_weight / in_proj_bias of an S=1 attention only ever get their V third.
+  std::vector<std::pair<int64_t, int64_t>> r;
+  bool is_inproj[NUM_SLOTS] = {};
+  for (int base : {(int)S_ISA, (int)S_TSA, (int)S_ICA, (int)S_TCA, (int)S_IRES + 2, (int)S_TRES + 2}) { is_inproj[base] = true; is_inproj[base + 1] = true; }
+  for (int s = 0; s < NUM_SLOTS; ++s) {
+    if (p.goff[s] < 0) continue;
+    Shape sh = slot_shape(*d, s);
+    const int64_t n = sh.rows * (sh.cols ? sh.cols : 1);
+    int64_t b = p.goff[s], e = p.goff[s] + n;
+    if (is_inproj[s]) b += 2 * (n / 3);
+    if (!r.empty() && r.back().second >= b - 4) r.back().second = e;      // merge neighbours (alignment padding included)
+    else r.push_back({b, e});
+  }
+  int n = 0;
+  for (auto& x : r) { if (n < cap) { out[2 * n] = x.first; out[2 * n + 1] = x.second; } ++n; }
+  return n;
+}
+
 int fb200_head_forward(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
                        const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state, void* logits, void* ws, void* stream) {
   Plan plan; DeviceInfo dev;

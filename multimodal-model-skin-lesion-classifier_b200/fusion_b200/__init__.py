@@ -7,7 +7,7 @@ or, keeping the reference's own import line (train_pad_20.py:6):
 
     from models import multimodalIntraInterModal      # fusion_b200/compat adds this package
 """
-from . import _lib
+from . import _lib, dp
 from ._lib import Fb200Error
 from .head import FusedCrossEntropyLoss, FusedHeadFunction, cross_entropy, make_desc
 from .model import GraphedTrainStep, MultimodalModel

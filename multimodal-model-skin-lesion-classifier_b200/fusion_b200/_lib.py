@@ -65,6 +65,7 @@ def lib():
     sig("fb200_grad_offset", i64, dp, i32)
     sig("fb200_grad_elems", i64, dp)
     sig("fb200_workspace_bytes", i32, dp, C.POINTER(sz))
+    sig("fb200_grad_live_ranges", i32, dp, C.POINTER(i64), i32)
     sig("fb200_dropout_p", C.c_float, dp, i32)
     sig("fb200_dropout_shape", i32, dp, i32, C.POINTER(i64), C.POINTER(i64))
     sig("fb200_algorithmic_work", i32, dp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64))
@@ -177,4 +178,23 @@ def dropout_sites(desc: Desc):
             r, c = C.c_int64(), C.c_int64()
             check(L.fb200_dropout_shape(C.byref(desc), s, C.byref(r), C.byref(c)), "fb200_dropout_shape")
             out[s] = (p, r.value, c.value)
+    return out
+
+
+_ranges_cache = {}
+
+
+def grad_live_ranges(desc: Desc):
+    """[(begin, end)] element ranges of the flat gradient buffer that can be non-zero."""
+    key = desc_key(desc)[:10]
+    hit = _ranges_cache.get(key)
+    if hit is not None:
+        return hit
+    cap = 64
+    arr = (C.c_int64 * (2 * cap))()
+    n = lib().fb200_grad_live_ranges(C.byref(desc), arr, cap)
+    if n < 0:
+        raise Fb200Error(n, "fb200_grad_live_ranges")
+    out = [(arr[2 * i], arr[2 * i + 1]) for i in range(min(n, cap))]
+    _ranges_cache[key] = out
     return out

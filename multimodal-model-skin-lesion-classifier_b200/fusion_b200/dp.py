@@ -27,10 +27,20 @@ def global_denominator(labels, class_weights, group=None, out=None):
     return w
 
 
-def allreduce_gradients(flat_grad, group=None, async_op=False):
-    """SUM all-reduce of the head's flat gradient bucket (in place)."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+def allreduce_gradients(flat_grad, group=None, async_op=False, ranges=None):
+    """SUM all-reduce of the head's flat gradient bucket (in place).
+
+    ``ranges`` ([(begin, end)] from ``_lib.grad_live_ranges``): move only the slices that can be non-zero - the
+    W_q / W_k rows of every S=1 attention are structural zeros (a third less traffic for `crossattention`).
+    The live slices are packed into one staging tensor, reduced with ONE collective and scattered back."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return None
+    if not ranges or len(ranges) == 1 and ranges[0] == (0, flat_grad.numel()):
         return dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    views = [flat_grad[b:e] for b, e in ranges]
+    staging = torch.cat(views)
+    dist.all_reduce(staging, op=dist.ReduceOp.SUM, group=group)
+    torch._foreach_copy_(views, list(staging.split([v.numel() for v in views])))
     return None
 
 

@@ -43,7 +43,12 @@ def _worker(rank, world, port, mech, q):
     for s, off in offs.items():
         g = o["grads"][names[s]]
         flat[off: off + g.size] = torch.from_numpy(g.ravel())
-    dp.allreduce_gradients(flat)
+    ranges = _lib.grad_live_ranges(d)
+    covered = torch.zeros(total, dtype=torch.bool)
+    for b, e in ranges:
+        covered[b:e] = True
+    assert float(flat[~covered].abs().max()) == 0.0 if (~covered).any() else True     # what is not shipped is structurally zero
+    dp.allreduce_gradients(flat, ranges=ranges)
     num = torch.tensor([o["num"]]); dist.all_reduce(num)
     if rank == 0:
         full = ho.head_forward_backward(cfg, params, x, tin, labels, cw, masks)
