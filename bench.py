@@ -211,11 +211,16 @@ def main():
             for j in range(nb):
                 graphs.append(fb.GraphedTrainStep(model, xs[j], ts[j], ys[j], cw, denom=denoms[j]))
 
+        # The global weighted-CE denominator of a batch only needs its labels, which the loader has one step ahead:
+        # it is all-reduced on a side stream while the previous step computes (dp.DenominatorPrefetcher).
+        pref = fb.dp.DenominatorPrefetcher(dev, nb) if world > 1 else None
+
         def step(i):
             j = i % nb
             if world > 1:
-                denoms[j].copy_(cw[ys[j]].sum().reshape(1))
-                dist.all_reduce(denoms[j])
+                if i == 0:
+                    pref.issue(j, ys[j], cw, denoms[j])
+                pref.wait(j)
             if use_graph:
                 loss = graphs[j].run()
                 flat = graphs[j].flat_grad
@@ -223,6 +228,9 @@ def main():
                 loss, _ = model.forward_loss(xs[j], ts[j], ys[j], cw, denom=denoms[j])
                 flat = model.flat_grad
             if world > 1:
+                pref.mark_consumed(j)
+                jn = (i + 1) % nb
+                pref.issue(jn, ys[jn], cw, denoms[jn])
                 fb.dp.allreduce_gradients(flat, ranges=live_ranges)   # SUM: the global denominator already averages; only live slices travel
             return loss
 
@@ -287,7 +295,7 @@ def main():
                     prefetch(i + 1)
                 s = slots[i % 2]
                 cur.wait_event(s["ready"])
-                if world > 1:
+                if world > 1:                                   # labels arrive with the H2D copy: the denominator cannot be earlier than that
                     s["denom"].copy_(cw[s["y"]].sum().reshape(1)); dist.all_reduce(s["denom"])
                 if use_graph:
                     loss = s["graph"].run(); flat = s["graph"].flat_grad

@@ -44,6 +44,32 @@ def allreduce_gradients(flat_grad, group=None, async_op=False, ranges=None):
     return None
 
 
+class DenominatorPrefetcher:
+    """All-reduces the weighted-CE denominator of the NEXT batch on a side stream while the current step runs.
+    `slots` static device buffers rotate; a slot is rewritten only after the step that read it has finished."""
+
+    def __init__(self, device, slots, group=None):
+        self.stream = torch.cuda.Stream(device=device)
+        self.ready = [torch.cuda.Event() for _ in range(slots)]
+        self.consumed = [None] * slots
+        self.group = group
+
+    def issue(self, slot, labels, class_weights, out):
+        with torch.cuda.stream(self.stream):
+            if self.consumed[slot] is not None:
+                self.stream.wait_event(self.consumed[slot])
+            global_denominator(labels, class_weights, self.group, out=out)
+            self.ready[slot].record(self.stream)
+
+    def wait(self, slot):
+        torch.cuda.current_stream().wait_event(self.ready[slot])
+
+    def mark_consumed(self, slot):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.consumed[slot] = ev
+
+
 def shard_rows(n_rows, rank, world):
     """Contiguous row range [lo, hi) of this rank (rank r gets rows r*B/N .. (r+1)*B/N)."""
     base, rem = divmod(n_rows, world)
