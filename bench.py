@@ -270,8 +270,8 @@ def main():
         hx, ht, hy = make_pool(Bsz, nbh, pinned=True)
         cw = class_weights(hy)
         copy_stream = torch.cuda.Stream(device=dev)
-        slots = [dict(x=torch.empty(Bsz, F, device=dev), t=torch.empty(Bsz, ht[0].shape[1], device=dev),
-                      y=torch.empty(Bsz, dtype=torch.int64, device=dev), ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        slots = [dict(x=torch.zeros(Bsz, F, device=dev), t=torch.zeros(Bsz, ht[0].shape[1], device=dev),
+                      y=torch.zeros(Bsz, dtype=torch.int64, device=dev), ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
         host_loss = torch.empty(steps + warm, dtype=torch.float32).pin_memory()
 
         def prefetch(i):

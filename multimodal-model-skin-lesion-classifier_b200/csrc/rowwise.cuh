@@ -473,8 +473,10 @@ __global__ void __launch_bounds__(256) ce_pass1_kernel(const float* __restrict__
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
     if (live) {
-      const int y = (int)labels[row];
-      const float w = class_w ? class_w[y] : 1.f;
+      const int64_t yl = labels[row];
+      const bool valid = yl >= 0 && yl < C;                 // anything else is ignored (covers ignore_index = -100; never indexes out of range)
+      const int y = valid ? (int)yl : 0;
+      const float w = valid ? (class_w ? class_w[y] : 1.f) : 0.f;
       const float inv = 1.f / se;
       if (dlogits) for (int c = sub; c < C; c += 8) dlogits[row * C + c] = w * (expf(z[c] - mx) * inv - (c == y ? 1.f : 0.f));
       if (sub == 0) { num += w * (logf(se) + mx - z[y]); den += w; }

@@ -318,16 +318,19 @@ def weighted_cross_entropy(logits, labels, class_w=None, denom=None):
     z = logits
     B, C = z.shape
     w = np.ones(C, dtype=z.dtype) if class_w is None else class_w.astype(z.dtype)
+    labels = np.asarray(labels)
+    valid = (labels >= 0) & (labels < C)            # nn.CrossEntropyLoss ignore_index (-100): ignored rows weigh nothing
+    safe = np.where(valid, labels, 0)
     zmax = z.max(axis=1, keepdims=True)
     e = np.exp(z - zmax)
     se = e.sum(axis=1, keepdims=True)
     lse = (np.log(se) + zmax)[:, 0]
-    wy = w[labels]
-    num = (wy * (lse - z[np.arange(B), labels])).sum()
+    wy = np.where(valid, w[safe], 0).astype(z.dtype)
+    num = (wy * (lse - z[np.arange(B), safe])).sum()
     den = wy.sum() if denom is None else z.dtype.type(denom)
     sm = e / se
     onehot = np.zeros_like(z)
-    onehot[np.arange(B), labels] = 1
+    onehot[np.arange(B), safe] = 1
     dz = (wy / den)[:, None] * (sm - onehot)
     return num / den, dz, num, wy.sum()
 

@@ -140,3 +140,17 @@ def test_tcgen05_split_k_weight_gradient():
     _lib.check(L.fb200_gemm(2, 1, M, N, K, vp(A), M, vp(Bm), N, vp(Cc), N, None, 0, 0, vp(ws), ws.numel(), None))
     torch.cuda.synchronize()
     assert parity.rel_err(Cc.cpu().numpy(), a.astype(np.float64).T @ b.astype(np.float64)) < 3e-6
+
+
+def test_cross_entropy_ignores_out_of_range_labels():
+    """ignore_index semantics (-100, or any label outside [0, C)): no contribution, never an out-of-range read."""
+    rng = np.random.default_rng(5)
+    z = rng.standard_normal((64, 6)).astype(np.float32)
+    y = rng.integers(0, 6, 64); y[3] = -100; y[10] = 6; y[11] = 2 ** 40
+    w = (rng.random(6) + 0.5).astype(np.float32)
+    out, dl = fb.cross_entropy(torch.from_numpy(z).cuda(), torch.from_numpy(y).cuda(), torch.from_numpy(w).cuda())
+    loss, dz, num, den = ho.weighted_cross_entropy(z.astype(np.float64), y, w.astype(np.float64))
+    assert abs(out.cpu().numpy()[0] - loss) < 1e-5 * abs(loss)
+    assert parity.rel_err(dl.cpu().numpy(), dz) < 1e-5 and (dl.cpu().numpy()[[3, 10, 11]] == 0).all()
+    ref = torch.nn.functional.cross_entropy(torch.from_numpy(z), torch.from_numpy(np.where((y >= 0) & (y < 6), y, -100)), weight=torch.from_numpy(w))
+    assert abs(float(ref) - loss) < 1e-5
