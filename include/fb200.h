@@ -191,6 +191,15 @@ int fb200_head_train_step(const fb200_desc* d, const void* const* params,
                           void* logits, float* loss_out, void* grads,
                           void* d_img_feat, void* d_text_in, void* ws, void* stream);
 
+/* The other losses the reference's loops use, forward + dlogits in one launch, mean reduction folded in:
+ * kind 1 = FocalLoss(alpha, gamma) (models/focalLoss.py:6-26; targets = int64 labels [B], weight = alpha [C] or NULL)
+ * kind 2 = SoftTargetCrossEntropy(weight) (models/softtargetsCrossEntropy.py:5-22; targets = fp32 soft labels [B,C]).
+ * loss_out: device float; dlogits: [B,C] fp32 out or NULL. */
+int fb200_aux_loss(int kind, const void* logits, const void* targets, const float* weight, float gamma, int B, int C,
+                   float* loss_out, void* dlogits, void* stream);
+/* Evaluation tail: probs = softmax(logits) and pred = argmax (utils/model_metrics.py:57-58); either output may be NULL. */
+int fb200_softmax_argmax(const void* logits, int B, int C, void* probs, int64_t* pred, void* stream);
+
 /* Fused multi-tensor Adam step with torch.optim.Adam semantics (coupled L2 weight decay, bias correction, eps
  * outside the square root) - the optimizer the reference builds right after the path: optim.Adam(model.parameters(),
  * lr=5e-5, weight_decay=1e-4) (train_pad_20.py:54) and steps at :113.  Host arrays of ntensors device pointers;

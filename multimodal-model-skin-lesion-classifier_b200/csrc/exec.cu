@@ -525,6 +525,29 @@ __global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { state[1] += 
 int fb200_debug_tc_trace(void* device_buf) { tc_trace_buffer() = (long long*)device_buf; return FB200_OK; }
 
 
+
+int fb200_aux_loss(int kind, const void* logits, const void* targets, const float* weight, float gamma, int B, int C,
+                   float* loss_out, void* dlogits, void* stream) {
+  if (!logits || !targets || !loss_out || B < 1 || C < 1 || (kind != 1 && kind != 2)) return FB200_EBADARG;
+  if (!is_device_ptr(logits)) return FB200_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_OK(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  int grid = (B + 31) / 32; if (grid > 1184) grid = 1184;
+  aux_loss_kernel<<<grid, 256, 0, st>>>(kind, (const float*)logits, kind == 1 ? (const int64_t*)targets : nullptr,
+                                        kind == 2 ? (const float*)targets : nullptr, weight, gamma, B, C, loss_out, (float*)dlogits);
+  CUDA_OK(cudaGetLastError());
+  return FB200_OK;
+}
+
+int fb200_softmax_argmax(const void* logits, int B, int C, void* probs, int64_t* pred, void* stream) {
+  if (!logits || B < 1 || C < 1 || (!probs && !pred)) return FB200_EBADARG;
+  if (!is_device_ptr(logits)) return FB200_EUNSUPPORTED;
+  int grid = (B + 31) / 32; if (grid > 1184) grid = 1184;
+  softmax_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)logits, B, C, (float*)probs, pred);
+  CUDA_OK(cudaGetLastError());
+  return FB200_OK;
+}
+
 int fb200_adam_step(int ntensors, void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
                     const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
                     float grad_scale, void* stream) {

@@ -636,6 +636,85 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamBatch a) {
   }
 }
 
+
+// ------------------------------------------------------------------ the other losses of the reference loops
+// kind 1: FocalLoss(alpha, gamma, reduction='mean')           (models/focalLoss.py:6-26, train_derm7pt.py:52)
+//         ce = lse(z) - z_y ; pt = exp(-ce) ; F = alpha_y (1-pt)^gamma ce ; loss = mean_i F_i
+// kind 2: SoftTargetCrossEntropy(weight)                       (models/softtargetsCrossEntropy.py:5-22)
+//         loss = mean_i ( - sum_c t_ic w_c log_softmax(z_i)_c )
+// One thread-group of 8 lanes per row like the weighted CE; the 1/B of the mean is folded in, so one pass suffices.
+__global__ void __launch_bounds__(256) aux_loss_kernel(int kind, const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                                       const float* __restrict__ soft, const float* __restrict__ wvec, float gamma,
+                                                       int B, int C, float* __restrict__ loss_out, float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31, sub = lane & 7;
+  const float invB = 1.f / (float)B;
+  float acc = 0.f;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < (((int64_t)B + 3) & ~3LL); row += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const bool live = row < B;
+    const float* z = logits + (live ? row : 0) * C;
+    float mx = -INFINITY;
+    for (int c = sub; c < C; c += 8) mx = fmaxf(mx, z[c]);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int c = sub; c < C; c += 8) se += expf(z[c] - mx);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float lse = logf(se) + mx, inv = 1.f / se;
+    if (kind == 1) {
+      const int64_t yl = live ? labels[row] : 0;
+      const bool valid = live && yl >= 0 && yl < C;
+      const int y = valid ? (int)yl : 0;
+      const float ce = lse - z[y];
+      const float pt = expf(-ce), om = 1.f - pt;
+      const float a = wvec ? wvec[y] : 1.f;
+      const float omg = powf(om, gamma);
+      const float f = a * omg * ce;
+      // dF/dce = a [ (1-pt)^g + ce g (1-pt)^(g-1) pt ]
+      const float dfdce = a * (omg + (om > 0.f ? ce * gamma * powf(om, gamma - 1.f) * pt : 0.f));
+      if (valid) {
+        if (dlogits) for (int c = sub; c < C; c += 8) dlogits[row * C + c] = dfdce * invB * (expf(z[c] - mx) * inv - (c == y ? 1.f : 0.f));
+        if (sub == 0) acc += f * invB;
+      } else if (live && dlogits) { for (int c = sub; c < C; c += 8) dlogits[row * C + c] = 0.f; }
+    } else {
+      const float* t = soft + (live ? row : 0) * C;
+      float tw = 0.f, part = 0.f;
+      for (int c = sub; c < C; c += 8) { const float twc = t[c] * (wvec ? wvec[c] : 1.f); tw += twc; part += twc * (z[c] - lse); }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) { tw += __shfl_xor_sync(0xffffffffu, tw, o); part += __shfl_xor_sync(0xffffffffu, part, o); }
+      if (live) {
+        if (dlogits) for (int c = sub; c < C; c += 8) dlogits[row * C + c] = invB * (expf(z[c] - mx) * inv * tw - t[c] * (wvec ? wvec[c] : 1.f));
+        if (sub == 0) acc -= part * invB;
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) atomicAdd(loss_out, acc);
+}
+// softmax probabilities + argmax for evaluation (utils/model_metrics.py:57-58, utils/save_predictions.py:93-94)
+__global__ void __launch_bounds__(256) softmax_argmax_kernel(const float* __restrict__ logits, int B, int C, float* __restrict__ probs, int64_t* __restrict__ pred) {
+  const int lane = threadIdx.x & 31, sub = lane & 7;
+  for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < (((int64_t)B + 3) & ~3LL); row += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const bool live = row < B;
+    const float* z = logits + (live ? row : 0) * C;
+    float mx = -INFINITY; int am = 0x7fffffff;
+    for (int c = sub; c < C; c += 8) if (z[c] > mx) { mx = z[c]; am = c; }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o); const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+      if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }          // first maximum wins, like torch.argmax
+    }
+    float se = 0.f;
+    for (int c = sub; c < C; c += 8) se += expf(z[c] - mx);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (live) {
+      if (probs) for (int c = sub; c < C; c += 8) probs[row * C + c] = expf(z[c] - mx) / se;
+      if (pred && sub == 0) pred[row] = am;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ format conversion
 // fp32 [rows, cols] (ld_in) -> FMT_PAIR / FMT_BF16 / FMT_F32 copy (ld_out); any alignment.
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ in, int ld_in, TRef out, int64_t rows, int cols) {

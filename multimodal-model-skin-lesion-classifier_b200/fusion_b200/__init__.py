@@ -9,8 +9,9 @@ or, keeping the reference's own import line (train_pad_20.py:6):
 """
 from . import _lib, dp
 from ._lib import Fb200Error
-from .head import FusedCrossEntropyLoss, FusedHeadFunction, cross_entropy, make_desc
+from .head import (FusedCrossEntropyLoss, FusedFocalLoss, FusedHeadFunction, FusedSoftTargetCrossEntropy, cross_entropy,
+                   make_desc, softmax_argmax)
 from .model import GraphedTrainStep, MultimodalModel
 from .optim import FusedAdam
 
-__all__ = ["MultimodalModel", "GraphedTrainStep", "FusedAdam", "FusedCrossEntropyLoss", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]
+__all__ = ["MultimodalModel", "GraphedTrainStep", "FusedAdam", "FusedCrossEntropyLoss", "FusedFocalLoss", "FusedSoftTargetCrossEntropy", "softmax_argmax", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]

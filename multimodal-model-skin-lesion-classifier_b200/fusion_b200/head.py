@@ -165,3 +165,63 @@ class FusedCrossEntropyLoss(torch.nn.Module):
 
     def forward(self, logits, labels, denom=None):
         return _FusedCEFunction.apply(logits, labels, self.weight, denom)
+
+
+class _AuxLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, weight, kind, gamma):
+        L = _lib.lib()
+        if not logits.is_cuda:
+            raise _lib.Fb200Error(-2, "logits must be a CUDA tensor")
+        z = logits.detach().contiguous().float()
+        t = targets.to(device=z.device, dtype=torch.int64 if kind == 1 else torch.float32).contiguous()
+        w = None if weight is None else weight.to(device=z.device, dtype=torch.float32).contiguous()
+        out = torch.empty(1, dtype=torch.float32, device=z.device)
+        dl = torch.empty_like(z)
+        with torch.cuda.device(z.device):
+            _lib.check(L.fb200_aux_loss(kind, _ptr(z), _ptr(t), _ptr(w), float(gamma), z.shape[0], z.shape[1], _ptr(out), _ptr(dl), _stream()), "fb200_aux_loss")
+        ctx.save_for_backward(dl)
+        return out[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dloss):
+        (dl,) = ctx.saved_tensors
+        return dl * dloss, None, None, None, None
+
+
+class FusedFocalLoss(torch.nn.Module):
+    """Drop-in for the reference's FocalLoss(alpha, gamma, reduction='mean') (models/focalLoss.py:6-26)."""
+
+    def __init__(self, alpha=None, gamma=2, reduction="mean"):
+        super().__init__()
+        if reduction != "mean":
+            raise ValueError("the fused focal loss implements reduction='mean' (what the reference's loops use)")
+        self.alpha, self.gamma, self.reduction = alpha, gamma, reduction
+
+    def forward(self, inputs, targets):
+        return _AuxLossFunction.apply(inputs, targets, self.alpha, 1, self.gamma)
+
+
+class FusedSoftTargetCrossEntropy(torch.nn.Module):
+    """Drop-in for SoftTargetCrossEntropy(weight) (models/softtargetsCrossEntropy.py:5-22)."""
+
+    def __init__(self, weight=None):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, inputs, targets):
+        return _AuxLossFunction.apply(inputs, targets, self.weight, 2, 0.0)
+
+
+def softmax_argmax(logits):
+    """(probs [B,C], preds [B]) in one kernel - the evaluation tail of utils/model_metrics.py:57-58."""
+    L = _lib.lib()
+    if not logits.is_cuda:
+        raise _lib.Fb200Error(-2, "logits must be a CUDA tensor")
+    z = logits.detach().contiguous().float()
+    probs = torch.empty_like(z)
+    pred = torch.empty(z.shape[0], dtype=torch.int64, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(L.fb200_softmax_argmax(_ptr(z), z.shape[0], z.shape[1], _ptr(probs), _ptr(pred), _stream()), "fb200_softmax_argmax")
+    return probs, pred
