@@ -162,10 +162,10 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   // The tensor-core accumulator truncates on every accumulate, a bias that grows linearly with the number
   // of MMAs chained into one TMEM accumulator (measured: 3e-5 relative at K = 4096 in 3xTF32).  The
-  // fp32-strict kind therefore accumulates at most CHUNK_KB k-blocks (K = 128) in TMEM, and the epilogue
+  // fp32-strict kind therefore accumulates at most CHUNK_KB k-blocks (K = 64) in TMEM, and the epilogue
   // warps promote each chunk into fp32 registers (round-to-nearest FADD) while the MMA warp already
   // fills the other of two TMEM accumulators.
-  static constexpr int CHUNK_KB = KIND == 1 ? 4 : (1 << 30);
+  static constexpr int CHUNK_KB = KIND == 1 ? 2 : (1 << 30);
   static constexpr int ACC_BUFS = KIND == 1 ? 2 : 1;
   static constexpr int ACC_COLS = ACC_BUFS * BN;
   static constexpr int TMEM_NEED = ACC_COLS + (ATM ? STAGES * A_TMEM_COLS : 0);
@@ -311,7 +311,9 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        auto rnd = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };   // tf32 RN (ties away) on the bit pattern
+        // tf32 round-to-nearest (ties away) on the bit pattern; lo is rounded too - the tensor core would otherwise
+        // TRUNCATE its low mantissa bits, a one-sided error that does not average out over K
+        auto rnd = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };
         if (ATM) {
           // B: split in place (elementwise, swizzle-oblivious); explicit ld/st.shared
 #pragma unroll 8
@@ -321,7 +323,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
             const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(x.x - h.x), "f"(x.y - h.y), "f"(x.z - h.z), "f"(x.w - h.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(rnd(x.x - h.x)), "f"(rnd(x.y - h.y)), "f"(rnd(x.z - h.z)), "f"(rnd(x.w - h.w)) : "memory");
           }
           // A: thread = output row m (TMEM lane 32q + lane); gather its BK values of K, split, store hi | lo to TMEM.
           uint32_t hi[32], lo[32];
@@ -335,7 +337,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
               float x;
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(base + r * 128 + ((gsel ^ (r & 3)) << 5)));
               const float h = rnd(x);
-              hi[r] = __float_as_uint(h); lo[r] = __float_as_uint(x - h);
+              hi[r] = __float_as_uint(h); lo[r] = __float_as_uint(rnd(x - h));
             }
           } else {
             // K-major tile: row m at m*128 B with its eight 16-byte chunks XOR-swizzled by (m & 7)
@@ -346,7 +348,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + r * 128 + ((j ^ (r & 7)) << 4)));
               const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
               hi[4 * j] = __float_as_uint(h.x); hi[4 * j + 1] = __float_as_uint(h.y); hi[4 * j + 2] = __float_as_uint(h.z); hi[4 * j + 3] = __float_as_uint(h.w);
-              lo[4 * j] = __float_as_uint(x.x - h.x); lo[4 * j + 1] = __float_as_uint(x.y - h.y); lo[4 * j + 2] = __float_as_uint(x.z - h.z); lo[4 * j + 3] = __float_as_uint(x.w - h.w);
+              lo[4 * j] = __float_as_uint(rnd(x.x - h.x)); lo[4 * j + 1] = __float_as_uint(rnd(x.y - h.y)); lo[4 * j + 2] = __float_as_uint(rnd(x.z - h.z)); lo[4 * j + 3] = __float_as_uint(rnd(x.w - h.w));
             }
           }
           const uint32_t a_tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ACC_COLS + s * Cfg::A_TMEM_COLS);
@@ -366,7 +368,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
             const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(x.x - h.x), "f"(x.y - h.y), "f"(x.z - h.z), "f"(x.w - h.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(rnd(x.x - h.x)), "f"(rnd(x.y - h.y)), "f"(rnd(x.z - h.z)), "f"(rnd(x.w - h.w)) : "memory");
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // generic-proxy writes -> visible to tcgen05 (async proxy)
