@@ -162,10 +162,10 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   // The tensor-core accumulator truncates on every accumulate, a bias that grows linearly with the number
   // of MMAs chained into one TMEM accumulator (measured: 3e-5 relative at K = 4096 in 3xTF32).  The
-  // fp32-strict kind therefore accumulates at most CHUNK_KB k-blocks (K = 64) in TMEM, and the epilogue
+  // fp32-strict kind therefore accumulates at most CHUNK_KB k-blocks (K = 128) in TMEM, and the epilogue
   // warps promote each chunk into fp32 registers (round-to-nearest FADD) while the MMA warp already
   // fills the other of two TMEM accumulators.
-  static constexpr int CHUNK_KB = KIND == 1 ? 2 : (1 << 30);
+  static constexpr int CHUNK_KB = KIND == 1 ? 4 : (1 << 30);
   static constexpr int ACC_BUFS = KIND == 1 ? 2 : 1;
   static constexpr int ACC_COLS = ACC_BUFS * BN;
   static constexpr int TMEM_NEED = ACC_COLS + (ATM ? STAGES * A_TMEM_COLS : 0);
