@@ -157,6 +157,9 @@ int fb200_debug_gemm_replay(const fb200_desc* d, const void* const* params, cons
 
 /* Debug aid (not part of the drop-in surface): record clock64 stamps of the TMA / MMA pipeline of
  * CTA (0,0,0) of each later tcgen05 GEMM into device_buf (int64[8 * k_blocks]); NULL switches it off. */
+/* debug / measurement aid: programmatic dependent launch on (default; FB200_PDL=0 in the environment turns it off) or
+ * off for every kernel launched afterwards; returns the previous setting. */
+int fb200_debug_set_pdl(int on);
 int fb200_debug_tc_trace(void* device_buf);
 
 /* rng_state[1] += increment, on `stream` (one tiny kernel; graph-capturable). */

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "../../include/fb200.h"
 
 namespace fb200 {
@@ -124,6 +125,34 @@ __device__ __forceinline__ float4 drop_mult4(const DropSpec& d, int64_t row, int
   uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   uint32_t thr = (uint32_t)fminf(d.p * 4294967296.0f, 4294967040.0f);
   return make_float4(r.x >= thr ? s : 0.f, r.y >= thr ? s : 0.f, r.z >= thr ? s : 0.f, r.w >= thr ? s : 0.f);
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute: it may begin
+// (block scheduling, prologue) while its predecessor in the stream drains.  pdl_sync() at kernel entry waits until
+// every kernel this one depends on has completed and flushed its writes - no global-memory access may precede it -
+// and only THEN lets the next kernel start its own prologue.  (Releasing the dependents before the wait lets a
+// third kernel start while the first is still running; measured on B200: a reader two launches downstream then
+// occasionally saw stale data.  With wait-then-release at most two kernels overlap.)
+// FB200_PDL=0 launches without the attribute (A/B measurements).
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+inline int& pdl_flag() { static int v = -1; return v; }
+inline bool pdl_enabled() {
+  int& v = pdl_flag();
+  if (v < 0) { const char* e = getenv("FB200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.0f / (1.0f + __expf(-z)); }

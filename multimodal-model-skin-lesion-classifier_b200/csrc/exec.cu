@@ -83,7 +83,7 @@ struct Ctx {
 // tf32 hi/lo planes): weights change every optimizer step, so this runs at the top of forward.
 struct PrepSeg { const float* src; void* dst; int64_t n4; int64_t plane; };
 struct PrepArgs { PrepSeg seg[32]; int nseg; int fmt; };
-__global__ void __launch_bounds__(256) wprep_kernel(const PrepArgs a) {
+__global__ void __launch_bounds__(256) wprep_kernel(const PrepArgs a) { pdl_sync();
   const PrepSeg sg = a.seg[blockIdx.y];
   const TRef out = make_ref(sg.dst, 0, a.fmt, sg.plane);          // flat view: row 0, column = element index
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n4; i += (int64_t)gridDim.x * blockDim.x)
@@ -111,14 +111,14 @@ static int run_forward(Ctx& c) {
       PrepSeg& sg = a.seg[a.nseg++];
       sg.src = c.param(w.slot, (int64_t)w.row0 * w.cols); sg.dst = c.ws + w.off; sg.n4 = (int64_t)w.rows * w.cols / 4; sg.plane = (int64_t)w.rows * w.cols;
     }
-    if (!c.gemm_only) wprep_kernel<<<dim3(64, a.nseg), 256, 0, c.st>>>(a);
+    if (!c.gemm_only) pdl_launch(wprep_kernel, dim3(64, a.nseg), 256, 0, c.st, a);
     CUDA_OK(cudaGetLastError());
   }
   for (const Op& o : p.ops) {
     switch (o.kind) {
       case OP_CAST: {
         const TRef src = c.value(o.in0);
-        if (!c.gemm_only) convert_kernel<<<c.dev.num_sms * 4, 256, 0, c.st>>>((const float*)src.p, src.ld, c.value(o.out), B, o.out.cols);
+        if (!c.gemm_only) pdl_launch(convert_kernel, c.dev.num_sms * 4, 256, 0, c.st, (const float*)src.p, src.ld, c.value(o.out), B, o.out.cols);
       } break;
       case OP_LINEAR: {
         if (o.engine == 1) {
@@ -151,14 +151,14 @@ static int run_forward(Ctx& c) {
         LnrdArgs a{}; a.x = c.value(o.in0); a.y = c.value(o.out); a.gamma = c.param(o.ln_w[0]); a.beta = c.param(o.ln_b[0]);
         a.stats = (float*)(c.ws + o.stats_off); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
-#define CALL(NV, TPR) lnrd_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+#define CALL(NV, TPR) pdl_launch(lnrd_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
       } break;
       case OP_GATE: {
         GateArgs a{}; a.x = c.value(o.in0); a.z = c.value(o.in1); a.y = c.value(o.out); a.B = B; a.N = o.out.cols;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
-#define CALL(NV, TPR) gate_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+#define CALL(NV, TPR) pdl_launch(gate_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
       } break;
@@ -167,7 +167,7 @@ static int run_forward(Ctx& c) {
         a.gamma = c.param(o.ln_w[0]); a.beta = c.param(o.ln_b[0]); a.stats = (float*)(c.ws + o.stats_off);
         a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
-#define CALL(NV, TPR) grb_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+#define CALL(NV, TPR) pdl_launch(grb_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
       } break;
@@ -176,7 +176,7 @@ static int run_forward(Ctx& c) {
         a.gamma_f = c.param(o.ln_w[0]); a.beta_f = c.param(o.ln_b[0]); a.gamma_g = c.param(o.ln_w[1]); a.beta_g = c.param(o.ln_b[1]);
         a.stats = (float*)(c.ws + o.stats_off); a.B = B; a.N = o.out.cols;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
-#define CALL(NV, TPR) meta_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+#define CALL(NV, TPR) pdl_launch(meta_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
       } break;
@@ -293,7 +293,7 @@ static int run_backward(Ctx& c) {
         a.dgamma = c.pgrad(o.ln_w[0]); a.dbeta = c.pgrad(o.ln_b[0]); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
         if (is_written(o.in0)) return FB200_EUNSUPPORTED;     // LN input has exactly one consumer in every program
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
-#define CALL(NV, TPR) lnrd_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+#define CALL(NV, TPR) pdl_launch(lnrd_bwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
         set_written(o.in0);
@@ -303,7 +303,7 @@ static int run_backward(Ctx& c) {
         a.dx_accumulate = is_written(o.in0); a.B = B; a.N = o.out.cols;
         if (is_written(o.in1)) return FB200_EUNSUPPORTED;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
-#define CALL(NV, TPR) gate_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+#define CALL(NV, TPR) pdl_launch(gate_bwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
         set_written(o.in0); set_written(o.in1);
@@ -315,7 +315,7 @@ static int run_backward(Ctx& c) {
         a.dgamma = c.pgrad(o.ln_w[0]); a.dbeta = c.pgrad(o.ln_b[0]); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
         if (is_written(o.in1) || is_written(o.in2)) return FB200_EUNSUPPORTED;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
-#define CALL(NV, TPR) grb_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+#define CALL(NV, TPR) pdl_launch(grb_bwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
         set_written(o.in0); set_written(o.in1); set_written(o.in2);
@@ -331,7 +331,7 @@ static int run_backward(Ctx& c) {
         a.B = B; a.N = o.out.cols;
         if (is_written(o.in1) || is_written(o.in2)) return FB200_EUNSUPPORTED;
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
-#define CALL(NV, TPR) meta_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, c.st>>>(a)
+#define CALL(NV, TPR) pdl_launch(meta_bwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
 #undef CALL
         if (a.dv.p) set_written(o.in0);
@@ -354,7 +354,7 @@ static int run_backward(Ctx& c) {
     ColsumBatch cb{}; cb.B = B; cb.nseg = 0;
     for (size_t i = base; i < colsums.size() && cb.nseg < 24; ++i) cb.seg[cb.nseg++] = colsums[i];
     int gx = (B + 63) / 64; if (gx > 8 * c.dev.num_sms / cb.nseg + 1) gx = 8 * c.dev.num_sms / cb.nseg + 1; if (gx < 1) gx = 1;   // ~64 rows per CTA
-    if (!c.gemm_only) colsum_batch_kernel<<<dim3(gx, cb.nseg), 256, 0, c.st>>>(cb);
+    if (!c.gemm_only) pdl_launch(colsum_batch_kernel, dim3(gx, cb.nseg), 256, 0, c.st, cb);
     CUDA_OK(cudaGetLastError());
   }
   // inputs nobody differentiated through still owe the caller a defined gradient
@@ -386,10 +386,10 @@ static int ce_launch(const void* logits, const int64_t* labels, const float* cla
   CUDA_OK(cudaMemsetAsync(loss_out, 0, 3 * sizeof(float), st));
   int rows_per_cta = 256 / 8;
   int grid = (B + rows_per_cta - 1) / rows_per_cta; if (grid > 1184) grid = 1184;
-  ce_pass1_kernel<<<grid, 256, 0, st>>>((const float*)logits, labels, class_w, B, C, loss_out, (float*)dlogits);
+  pdl_launch(ce_pass1_kernel, grid, 256, 0, st, (const float*)logits, labels, class_w, B, C, loss_out, (float*)dlogits);
   CUDA_OK(cudaGetLastError());
   int n = B * C; int g2 = (n + 255) / 256; if (g2 > 1184) g2 = 1184;
-  ce_pass2_kernel<<<g2, 256, 0, st>>>(denom, n, loss_out, (float*)dlogits);
+  pdl_launch(ce_pass2_kernel, g2, 256, 0, st, denom, n, loss_out, (float*)dlogits);
   CUDA_OK(cudaGetLastError());
   return FB200_OK;
 }
@@ -519,9 +519,10 @@ int fb200_list_gemms(const fb200_desc* d, int32_t* out, int cap) {
   return n < cap ? n : cap;
 }
 
-__global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { state[1] += inc; }
+__global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { pdl_sync(); state[1] += inc; }
 
 /* debug: device buffer of >= 8*k_blocks int64 receiving pipeline time stamps of CTA (0,0,0) of every tcgen05 GEMM launched afterwards; NULL disables */
+int fb200_debug_set_pdl(int on) { const int prev = pdl_enabled() ? 1 : 0; pdl_flag() = on ? 1 : 0; return prev; }
 int fb200_debug_tc_trace(void* device_buf) { tc_trace_buffer() = (long long*)device_buf; return FB200_OK; }
 
 
@@ -533,7 +534,7 @@ int fb200_aux_loss(int kind, const void* logits, const void* targets, const floa
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_OK(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   int grid = (B + 31) / 32; if (grid > 1184) grid = 1184;
-  aux_loss_kernel<<<grid, 256, 0, st>>>(kind, (const float*)logits, kind == 1 ? (const int64_t*)targets : nullptr,
+  pdl_launch(aux_loss_kernel, grid, 256, 0, st, kind, (const float*)logits, kind == 1 ? (const int64_t*)targets : nullptr,
                                         kind == 2 ? (const float*)targets : nullptr, weight, gamma, B, C, loss_out, (float*)dlogits);
   CUDA_OK(cudaGetLastError());
   return FB200_OK;
@@ -543,7 +544,7 @@ int fb200_softmax_argmax(const void* logits, int B, int C, void* probs, int64_t*
   if (!logits || B < 1 || C < 1 || (!probs && !pred)) return FB200_EBADARG;
   if (!is_device_ptr(logits)) return FB200_EUNSUPPORTED;
   int grid = (B + 31) / 32; if (grid > 1184) grid = 1184;
-  softmax_argmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)logits, B, C, (float*)probs, pred);
+  pdl_launch(softmax_argmax_kernel, grid, 256, 0, (cudaStream_t)stream, (const float*)logits, B, C, (float*)probs, pred);
   CUDA_OK(cudaGetLastError());
   return FB200_OK;
 }
@@ -566,7 +567,7 @@ int fb200_adam_step(int ntensors, void* const* params, const void* const* grads,
     }
     if (a.nseg == 0) continue;
     int gx = (int)((maxn / 4 + 255) / 256); if (gx > dev.num_sms * 2) gx = dev.num_sms * 2; if (gx < 1) gx = 1;
-    adam_kernel<<<dim3(gx, a.nseg), 256, 0, (cudaStream_t)stream>>>(a);
+    pdl_launch(adam_kernel, dim3(gx, a.nseg), 256, 0, (cudaStream_t)stream, a);
     CUDA_OK(cudaGetLastError());
   }
   return FB200_OK;
@@ -575,7 +576,7 @@ int fb200_adam_step(int ntensors, void* const* params, const void* const* grads,
 int fb200_rng_advance(void* rng_state, uint64_t increment, void* stream) {
   if (!rng_state) return FB200_EBADARG;
   if (!is_device_ptr(rng_state)) return FB200_EUNSUPPORTED;
-  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((uint64_t*)rng_state, increment);
+  pdl_launch(rng_advance_kernel, 1, 1, 0, (cudaStream_t)stream, (uint64_t*)rng_state, increment);
   CUDA_OK(cudaGetLastError());
   return FB200_OK;
 }
@@ -715,7 +716,7 @@ int fb200_ln_relu_dropout_fwd(const float* x, const float* gamma, const float* b
   a.B = B; a.N = N;
   const int grid = row_grid_for(B, N, dev.num_sms);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(NV, TPR) lnrd_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, st>>>(a)
+#define CALL(NV, TPR) pdl_launch(lnrd_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, st, a)
   FB200_ROW_DISPATCH(N, CALL);
 #undef CALL
   CUDA_OK(cudaGetLastError());
@@ -734,7 +735,7 @@ int fb200_ln_relu_dropout_bwd(const float* x, const float* y, const float* gamma
   a.gamma = gamma; a.stats = (float*)stats; a.dgamma = dgamma; a.dbeta = dbeta;
   a.drop.mask = nullptr; a.drop.state = nullptr; a.drop.p = p; a.drop.active = (train && p > 0.f) ? 1 : 0; a.B = B; a.N = N;
   const int grid = row_grid_for(B, N, dev.num_sms);
-#define CALL(NV, TPR) lnrd_bwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, st>>>(a)
+#define CALL(NV, TPR) pdl_launch(lnrd_bwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, st, a)
   FB200_ROW_DISPATCH(N, CALL);
 #undef CALL
   CUDA_OK(cudaGetLastError());
@@ -750,7 +751,7 @@ int fb200_metablock_fwd(const float* v, const float* f, const float* g, const fl
   a.gamma_f = gamma_f; a.beta_f = beta_f; a.gamma_g = gamma_g; a.beta_g = beta_g; a.stats = stats; a.B = B; a.N = N;
   const int grid = row_grid_for(B, N, dev.num_sms);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(NV, TPR) meta_fwd_kernel<NV, TPR><<<grid, ROW_WARPS * 32, 0, st>>>(a)
+#define CALL(NV, TPR) pdl_launch(meta_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, st, a)
   FB200_ROW_DISPATCH(N, CALL);
 #undef CALL
   CUDA_OK(cudaGetLastError());

@@ -122,7 +122,7 @@ struct LnrdArgs {
 };
 
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_fwd_kernel(const LnrdArgs a) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_fwd_kernel(const LnrdArgs a) { pdl_sync();
   const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
   float4 gam[NV], bet[NV];
   row_load_param<NV, TPR>(G, a.gamma, a.N, gam);
@@ -190,7 +190,7 @@ __device__ __forceinline__ void normalize(const Grp<TPR>& G, float4 (&v)[NV], fl
 }
 
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_bwd_kernel(const LnrdArgs a) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_bwd_kernel(const LnrdArgs a) { pdl_sync();
   __shared__ __align__(16) float red[ROW_WARPS * 512];
   const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
   float4 gam[NV], dgam[NV], dbet[NV];
@@ -224,7 +224,7 @@ struct GateArgs {
   int B, N;
 };
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) gate_fwd_kernel(const GateArgs a) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) gate_fwd_kernel(const GateArgs a) { pdl_sync();
   const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
   for (int64_t row = G.row0; row < a.B; row += G.rstep) {
     float4 x[NV], z[NV];
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) gate_fwd_kernel(const GateArgs
   }
 }
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) gate_bwd_kernel(const GateArgs a) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) gate_bwd_kernel(const GateArgs a) { pdl_sync();
   const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
   for (int64_t row = G.row0; row < a.B; row += G.rstep) {
     float4 x[NV], z[NV], dy[NV], dx[NV];
@@ -272,7 +272,7 @@ struct GrbArgs {
   int B, N;
 };
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p) { pdl_sync();
   const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
   float4 gam[NV], bet[NV];
   row_load_param<NV, TPR>(G, p.gamma, p.N, gam);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p
   }
 }
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) grb_bwd_kernel(const GrbArgs p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) grb_bwd_kernel(const GrbArgs p) { pdl_sync();
   __shared__ __align__(16) float red[ROW_WARPS * 512];
   const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
   float4 gam[NV], dgam[NV], dbet[NV];
@@ -364,7 +364,7 @@ struct MetaArgs {
   int B, N;
 };
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) meta_fwd_kernel(const MetaArgs p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) meta_fwd_kernel(const MetaArgs p) { pdl_sync();
   const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
   for (int64_t row = G.row0; row < p.B; row += G.rstep) {
     float4 f[NV], g[NV], v[NV], pr[NV];
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) meta_fwd_kernel(const MetaArgs
 }
 // Backward in two sweeps per row so that at most ~6 row-vectors are live (F up to 4096).
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) meta_bwd_kernel(const MetaArgs p) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) meta_bwd_kernel(const MetaArgs p) { pdl_sync();
   __shared__ __align__(16) float red[ROW_WARPS * 512];
   const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
   float4 dgf[NV], dbf[NV], dgg[NV], dbg[NV];
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) meta_bwd_kernel(const MetaArgs
 // Pass 2: scale by 1/denominator (this batch's, or the global one under data parallelism).
 __global__ void __launch_bounds__(256) ce_pass1_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                                                        const float* __restrict__ class_w, int B, int C,
-                                                       float* __restrict__ loss_out, float* __restrict__ dlogits) {
+                                                       float* __restrict__ loss_out, float* __restrict__ dlogits) { pdl_sync();
   const int lane = threadIdx.x & 31;
   const int sub = lane & 7;
   float num = 0.f, den = 0.f;
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(256) ce_pass1_kernel(const float* __restrict__
   if (lane == 0) { atomicAdd(loss_out + 1, num); atomicAdd(loss_out + 2, den); }
 }
 __global__ void __launch_bounds__(256) ce_pass2_kernel(const float* __restrict__ denom, int n, float* __restrict__ loss_out,
-                                                       float* __restrict__ dlogits) {
+                                                       float* __restrict__ dlogits) { pdl_sync();
   const float den = denom ? *denom : loss_out[2];
   const float inv = 1.f / den;
   if (blockIdx.x == 0 && threadIdx.x == 0) loss_out[0] = loss_out[1] * inv;
@@ -507,7 +507,7 @@ struct SmallNArgs {
   int B, K, C;
 };
 template <int MAXC>
-__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_fwd_kernel(const SmallNArgs a) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_fwd_kernel(const SmallNArgs a) { pdl_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nch = a.K / 4;
   for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < a.B; row += (int64_t)gridDim.x * ROW_WARPS) {
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_fwd_kernel(const SmallN
   }
 }
 template <int MAXC, int CH>      // CH = 128-bit chunks of K per lane (K <= 128 * CH)
-__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallNArgs a) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallNArgs a) { pdl_sync();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nch = a.K / 4;
   float4 dw[MAXC][CH];
@@ -594,15 +594,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallN
 inline bool smalln_ok(int C, int K) { return C <= 8 && K % 4 == 0 && K <= 512; }
 inline cudaError_t launch_smalln_fwd(const SmallNArgs& a, int num_sms, cudaStream_t st) {
   int grid = (a.B + ROW_WARPS * 2 - 1) / (ROW_WARPS * 2); if (grid > num_sms * 4) grid = num_sms * 4; if (grid < 1) grid = 1;
-  smalln_fwd_kernel<8><<<grid, ROW_WARPS * 32, 0, st>>>(a);
+  pdl_launch(smalln_fwd_kernel<8>, grid, ROW_WARPS * 32, 0, st, a);
   return cudaGetLastError();
 }
 inline cudaError_t launch_smalln_bwd(const SmallNArgs& a, int num_sms, cudaStream_t st) {
   int grid = (a.B + ROW_WARPS * 2 - 1) / (ROW_WARPS * 2); if (grid > num_sms * 2) grid = num_sms * 2; if (grid < 1) grid = 1;
   const size_t smem = (size_t)(a.C * a.K + a.C) * sizeof(float);          // <= 8 * 512 * 4 + 32 = 16.4 KB
-  if (a.K <= 128) smalln_bwd_kernel<8, 1><<<grid, ROW_WARPS * 32, smem, st>>>(a);
-  else if (a.K <= 256) smalln_bwd_kernel<8, 2><<<grid, ROW_WARPS * 32, smem, st>>>(a);
-  else smalln_bwd_kernel<8, 4><<<grid, ROW_WARPS * 32, smem, st>>>(a);
+  if (a.K <= 128) pdl_launch(smalln_bwd_kernel<8, 1>, grid, ROW_WARPS * 32, smem, st, a);
+  else if (a.K <= 256) pdl_launch(smalln_bwd_kernel<8, 2>, grid, ROW_WARPS * 32, smem, st, a);
+  else pdl_launch(smalln_bwd_kernel<8, 4>, grid, ROW_WARPS * 32, smem, st, a);
   return cudaGetLastError();
 }
 
@@ -612,7 +612,7 @@ inline cudaError_t launch_smalln_bwd(const SmallNArgs& a, int num_sms, cudaStrea
 // coupled L2 (g += wd * p), bias-corrected moments, eps outside the sqrt.  One launch updates up to 48 tensors.
 struct AdamSeg { float* p; const float* g; float* m; float* v; int64_t n; };
 struct AdamBatch { AdamSeg seg[48]; int nseg; float lr, b1, b2, eps, wd, bc1, bc2, grad_scale; };
-__global__ void __launch_bounds__(256) adam_kernel(const AdamBatch a) {
+__global__ void __launch_bounds__(256) adam_kernel(const AdamBatch a) { pdl_sync();
   const AdamSeg sg = a.seg[blockIdx.y];
   const float step_size = a.lr / a.bc1, inv_sqrt_bc2 = rsqrtf(a.bc2);
   const int64_t n4 = sg.n / 4;
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamBatch a) {
 // One thread-group of 8 lanes per row like the weighted CE; the 1/B of the mean is folded in, so one pass suffices.
 __global__ void __launch_bounds__(256) aux_loss_kernel(int kind, const float* __restrict__ logits, const int64_t* __restrict__ labels,
                                                        const float* __restrict__ soft, const float* __restrict__ wvec, float gamma,
-                                                       int B, int C, float* __restrict__ loss_out, float* __restrict__ dlogits) {
+                                                       int B, int C, float* __restrict__ loss_out, float* __restrict__ dlogits) { pdl_sync();
   const int lane = threadIdx.x & 31, sub = lane & 7;
   const float invB = 1.f / (float)B;
   float acc = 0.f;
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(256) aux_loss_kernel(int kind, const float* __
   if (lane == 0) atomicAdd(loss_out, acc);
 }
 // softmax probabilities + argmax for evaluation (utils/model_metrics.py:57-58, utils/save_predictions.py:93-94)
-__global__ void __launch_bounds__(256) softmax_argmax_kernel(const float* __restrict__ logits, int B, int C, float* __restrict__ probs, int64_t* __restrict__ pred) {
+__global__ void __launch_bounds__(256) softmax_argmax_kernel(const float* __restrict__ logits, int B, int C, float* __restrict__ probs, int64_t* __restrict__ pred) { pdl_sync();
   const int lane = threadIdx.x & 31, sub = lane & 7;
   for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < (((int64_t)B + 3) & ~3LL); row += ((int64_t)gridDim.x * blockDim.x) >> 3) {
     const bool live = row < B;
@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(256) softmax_argmax_kernel(const float* __rest
 
 // ------------------------------------------------------------------ format conversion
 // fp32 [rows, cols] (ld_in) -> FMT_PAIR / FMT_BF16 / FMT_F32 copy (ld_out); any alignment.
-__global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ in, int ld_in, TRef out, int64_t rows, int cols) {
+__global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ in, int ld_in, TRef out, int64_t rows, int cols) { pdl_sync();
   int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / cols; int c = (int)(i - r * cols);
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ 
 
 // column sums of a [rows, N] matrix into fp32 dst (atomic): bias gradients for the tcgen05 path
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) colsum_kernel(TRef x, int B, int N, float* dst) {
+__global__ void __launch_bounds__(ROW_WARPS * 32) colsum_kernel(TRef x, int B, int N, float* dst) { pdl_sync();
   __shared__ __align__(16) float red[ROW_WARPS * 512];
   const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
   float4 acc[NV];
@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) colsum_kernel(TRef x, int B, i
 // access is a coalesced 128-bit load; partial sums go out as fp32 atomics (db is pre-zeroed).
 struct ColsumSeg { TRef x; int N; float* dst; };
 struct ColsumBatch { ColsumSeg seg[24]; int nseg; int B; };
-__global__ void __launch_bounds__(256) colsum_batch_kernel(const ColsumBatch a) {
+__global__ void __launch_bounds__(256) colsum_batch_kernel(const ColsumBatch a) { pdl_sync();
   __shared__ __align__(16) float4 red[256];
   const ColsumSeg sg = a.seg[blockIdx.y];
   const int nv = sg.N / 4;                                   // float4 columns

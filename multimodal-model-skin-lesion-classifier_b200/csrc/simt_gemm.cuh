@@ -124,7 +124,7 @@ __device__ __forceinline__ void store_tile(float* sm, int kc, float (*regs)[4], 
 
 template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
-simt_gemm_kernel(const GemmArgs g) {
+simt_gemm_kernel(const GemmArgs g) { pdl_sync();
   constexpr int THREADS = (BM / TM) * (BN / TN);
   constexpr int PAD = 4;
   constexpr int LDA = BM + PAD, LDB = BN + PAD;
@@ -327,8 +327,8 @@ inline cudaError_t launch_simt_gemm(GemmArgs g, int num_sms, cudaStream_t st) {
   if (split == 1) { g.partial = nullptr; }
   g.split_k = split;
   dim3 grid((g.N + bn - 1) / bn, (g.M + bm - 1) / bm, split);
-  if (big) simt_gemm_kernel<128, 128, 16, 8, 8><<<grid, 256, 0, st>>>(g);
-  else     simt_gemm_kernel<64, 64, 16, 4, 4><<<grid, 256, 0, st>>>(g);
+  if (big) pdl_launch(simt_gemm_kernel<128, 128, 16, 8, 8>, grid, 256, 0, st, g);
+  else     pdl_launch(simt_gemm_kernel<64, 64, 16, 4, 4>, grid, 256, 0, st, g);
   return cudaGetLastError();
 }
 

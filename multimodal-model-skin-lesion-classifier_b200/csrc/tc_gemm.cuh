@@ -2,27 +2,31 @@
 //
 //   C[M,N] (+)= A x B      fp32 accumulation in tensor memory
 //   kind bf16   : tcgen05.mma.kind::f16, bf16 operands
-//   kind tf32x3 : fp32-strict.  TMA lands raw fp32 tiles in shared memory; the four epilogue warps
-//                 split every tile IN PLACE into hi = tf32(x) and lo = x - hi (second buffer, same
-//                 swizzled offsets), and the MMA thread issues three tcgen05.mma.kind::tf32 per
-//                 k-slice (hi*hi + lo*hi + hi*lo): fp32 products to ~2^-21 while HBM / L2 only ever
-//                 carry 4 bytes per element and no operand is pre-processed in memory.
+//   kind tf32x3 : fp32-strict.  TMA lands raw fp32 tiles in shared memory.  The tensor core truncates a tf32
+//                 operand to its top 19 bits, so the raw tile IS hi = trunc(x); the worker warps compute
+//                 lo = rn_tf32(x - hi) (A: into tensor memory next to the raw values, B: into a second smem
+//                 buffer at the same swizzled offsets) and the MMA thread issues three
+//                 tcgen05.mma.kind::tf32 per k-slice (hi*hi + lo*hi + hi*lo): fp32 products to ~2^-21
+//                 while HBM / L2 only ever carry 4 bytes per element and no operand is pre-processed in memory.
 //   layouts     : each operand is either K-major (reduction dim contiguous) or MN-major, so
 //                 forward (X W^T), dX (dY W) and dW (dY^T X) all read the SAME row-major
 //                 tensors straight from HBM through TMA - nothing is ever transposed in memory.
 //
-// CTA = 192 threads: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// single-thread MMA issuer, warps 2..5 = epilogue (TMEM -> registers -> global, fused bias /
-// ReLU / ReLU-mask / accumulate / split-K reduction).  One 128 x BLOCK_N output tile per CTA,
+// CTA = 320 threads: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2..9 = workers (operand split, chunk promotion, epilogue:
+// TMEM -> registers -> smem -> global, fused bias / ReLU / ReLU-mask / accumulate / split-K reduction).  One 128 x BLOCK_N output tile per CTA,
 // STAGES-deep smem ring of 128-byte-swizzled tiles guarded by full/empty mbarriers.
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace fb200 {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 192;
+constexpr int TC_NH = 2;                          // worker warps per TMEM lane quarter: each owns 1/TC_NH of the columns
+constexpr int TC_WORKERS = 4 * TC_NH;             // split + promote + epilogue warps
+constexpr int TC_THREADS = 64 + 32 * TC_WORKERS;  // + TMA producer warp + MMA warp
 
 struct TcEpilogue {
   TRef C;                 // output view (any Fmt)
@@ -107,6 +111,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
         "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -196,9 +207,9 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], TC_WORKERS); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);                     // one arrive per epilogue warp
+    mbar_init(&tmem_empty[0], TC_WORKERS); mbar_init(&tmem_empty[1], TC_WORKERS);   // one arrive per worker warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -206,6 +217,10 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
+  // previous kernel in the stream; wait until every kernel this one depends on has completed and flushed before the
+  // first global-memory access, then let the next kernel start ITS prologue.
+  pdl_sync();
   if (tr && threadIdx.x == 0) tr[13] = clock64();                                    // trace: setup done
 
   if (warp == 0) {
@@ -282,21 +297,26 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       }
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    // ===== workers: warps 2..9.  A warp may only touch TMEM lanes [32 (warp % 4), +32); the TC_NH warps that share a
+    //       lane quarter split the columns between them (h = which part).  Two warps per scheduler: the operand split is
+    //       issue/latency bound, one warp per scheduler left the tensor pipe waiting for it (1275 cycles per k-block
+    //       against 817 of MMA work). =====
     const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    constexpr int HN = BN / TC_NH;                                                   // accumulator columns per thread
     const int num_chunks = (num_kb + Cfg::CHUNK_KB - 1) / Cfg::CHUNK_KB;
-    float acc[BN];
+    float acc[HN];
 #pragma unroll
-    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int j = 0; j < HN; ++j) acc[j] = 0.f;
     // chunk accumulator (TMEM) -> fp32 registers, then hand the TMEM buffer back to the MMA thread
     auto promote = [&](int ch) {
       const int ab = ch & (Cfg::ACC_BUFS - 1);
       mbar_wait(&tmem_full[ab], (ch / Cfg::ACC_BUFS) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < HN; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c0), r);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * HN + c0), r);
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
       }
@@ -305,84 +325,89 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[ab])) : "memory");
     };
     int next_promote = 0;
-    if (KIND == 1) {
-      const int t128 = threadIdx.x - 64;                                            // 0..127 over the four warps
+    if constexpr (KIND == 1) {
+      const int tw = threadIdx.x - 64;                                              // 0 .. 32 * TC_WORKERS - 1
+      constexpr int KH = Cfg::BK / TC_NH;                                           // K values of the A tile this thread splits
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        // tf32 round-to-nearest (ties away) on the bit pattern; lo is rounded too - the tensor core would otherwise
-        // TRUNCATE its low mantissa bits, a one-sided error that does not average out over K
+        // The tensor core TRUNCATES the low 13 mantissa bits of a tf32 operand.  So the raw fp32 value IS the hi
+        // operand (hi = trunc(x), no ALU work and no smem rewrite), lo = x - trunc(x) is exact in fp32, and only lo
+        // is rounded to nearest (ties away) on the bit pattern: a truncated lo would be a one-sided error that does
+        // not average out over K.  x = hi + lo to 2^-22 |x|, unbiased.
         auto rnd = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };
+        auto low = [&rnd](float x) { return rnd(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); };
         if (ATM) {
-          // B: split in place (elementwise, swizzle-oblivious); explicit ld/st.shared
-#pragma unroll 8
-          for (int v = t128; v < Cfg::B_BYTES / 16; v += 128) {
-            const uint32_t hi_a = st + Cfg::B_OFF + v * 16, lo_a = hi_a + Cfg::B_BYTES;
-            float4 x;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
-            const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(rnd(x.x - h.x)), "f"(rnd(x.y - h.y)), "f"(rnd(x.z - h.z)), "f"(rnd(x.w - h.w)) : "memory");
-          }
-          // A: thread = output row m (TMEM lane 32q + lane); gather its BK values of K, split, store hi | lo to TMEM.
-          uint32_t hi[32], lo[32];
+          // A: thread = output row m (TMEM lane 32q + lane); gather its KH values of K, split, store hi | lo to TMEM.
+          uint32_t hi[KH], lo[KH];
           if (A_MN) {
             // MN-major tile (dW: A = dY^T): chunk q holds m in [32q, 32q+32); K row r is 128 B with its four
             // 32-byte groups XOR-swizzled by (r & 3).  One 4-byte load per K value, conflict-free across the warp.
             const uint32_t base = st + q * (Cfg::BK * 128) + (lane & 7) * 4;
             const int gsel = lane >> 3;
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
+            for (int rr = 0; rr < KH; ++rr) {
+              const int r = h * KH + rr;
               float x;
               asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(base + r * 128 + ((gsel ^ (r & 3)) << 5)));
-              const float h = rnd(x);
-              hi[r] = __float_as_uint(h); lo[r] = __float_as_uint(rnd(x - h));
+              hi[rr] = __float_as_uint(x); lo[rr] = __float_as_uint(low(x));
             }
           } else {
             // K-major tile: row m at m*128 B with its eight 16-byte chunks XOR-swizzled by (m & 7)
             const int r = q * 32 + lane;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int jj = 0; jj < KH / 4; ++jj) {
+              const int j = h * (KH / 4) + jj;
               float4 x;
               asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + r * 128 + ((j ^ (r & 7)) << 4)));
-              const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
-              hi[4 * j] = __float_as_uint(h.x); hi[4 * j + 1] = __float_as_uint(h.y); hi[4 * j + 2] = __float_as_uint(h.z); hi[4 * j + 3] = __float_as_uint(h.w);
-              lo[4 * j] = __float_as_uint(rnd(x.x - h.x)); lo[4 * j + 1] = __float_as_uint(rnd(x.y - h.y)); lo[4 * j + 2] = __float_as_uint(rnd(x.z - h.z)); lo[4 * j + 3] = __float_as_uint(rnd(x.w - h.w));
+              hi[4 * jj] = __float_as_uint(x.x); hi[4 * jj + 1] = __float_as_uint(x.y); hi[4 * jj + 2] = __float_as_uint(x.z); hi[4 * jj + 3] = __float_as_uint(x.w);
+              lo[4 * jj] = __float_as_uint(low(x.x)); lo[4 * jj + 1] = __float_as_uint(low(x.y)); lo[4 * jj + 2] = __float_as_uint(low(x.z)); lo[4 * jj + 3] = __float_as_uint(low(x.w));
             }
           }
-          const uint32_t a_tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ACC_COLS + s * Cfg::A_TMEM_COLS);
-          tmem_st32(a_tm, hi);
-          tmem_st32(a_tm + Cfg::BK, lo);
+          const uint32_t a_tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ACC_COLS + s * Cfg::A_TMEM_COLS + h * KH);
+          static_assert(KH == 16, "tcgen05.st shape below is x16");
+          tmem_st16(a_tm, hi);
+          tmem_st16(a_tm + Cfg::BK, lo);
+          // B: the raw tile stays where TMA put it (= hi); the lo plane goes to the second buffer at the same swizzled
+          // offsets (elementwise, swizzle-oblivious); explicit ld/st.shared.  Issued between the TMEM stores and
+          // their wait so that the store latency is covered.
+#pragma unroll 4
+          for (int v = tw; v < Cfg::B_BYTES / 16; v += 32 * TC_WORKERS) {
+            const uint32_t hi_a = st + Cfg::B_OFF + v * 16, lo_a = hi_a + Cfg::B_BYTES;
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(low(x.x)), "f"(low(x.y)), "f"(low(x.z)), "f"(low(x.w)) : "memory");
+          }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
         } else {
           // elementwise and position preserving, hence oblivious to the swizzle / major of the tile;
           // explicit ld/st.shared (a generic pointer would go through the slow generic-address path)
-#pragma unroll 8
-          for (int v = t128; v < Cfg::TMA_BYTES / 16; v += 128) {
+#pragma unroll 4
+          for (int v = tw; v < Cfg::TMA_BYTES / 16; v += 32 * TC_WORKERS) {
             const int off = v * 16;
             const uint32_t hi_a = off < Cfg::A_BYTES ? st + off : st + Cfg::A_BYTES + off;                // B tile starts after both A planes
             const uint32_t lo_a = hi_a + (off < Cfg::A_BYTES ? Cfg::A_BYTES : Cfg::B_BYTES);
             float4 x;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
-            const float4 h = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(rnd(x.x - h.x)), "f"(rnd(x.y - h.y)), "f"(rnd(x.z - h.z)), "f"(rnd(x.w - h.w)) : "memory");
+            const float4 hv = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(hv.x), "f"(hv.y), "f"(hv.z), "f"(hv.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(rnd(x.x - hv.x)), "f"(rnd(x.y - hv.y)), "f"(rnd(x.z - hv.z)), "f"(rnd(x.w - hv.w)) : "memory");
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // generic-proxy writes -> visible to tcgen05 (async proxy)
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_bar[s])) : "memory");
-        if (tr && t128 == 0) tr[i * 8 + 4] = clock64();
+        if (tr && tw == 0) tr[i * 8 + 4] = clock64();
         // promote one chunk behind the split front so the MMA thread never starves
         if ((i % Cfg::CHUNK_KB) == Cfg::CHUNK_KB - 1 && i / Cfg::CHUNK_KB >= 1) { promote(next_promote); ++next_promote; }
       }
     }
     for (; next_promote < num_chunks; ++next_promote) promote(next_promote);
     if (tr && threadIdx.x == 64) tr[21] = clock64();                                 // trace: accumulator in registers
-    // Coalesced epilogue.  A thread holds one output ROW (TMEM lane) in registers; written as is, a warp store
-    // would touch 32 rows x 16 B (measured: 5.5 us per tile, a third of a K=512 GEMM).  The warp transposes
+    // Coalesced epilogue.  A thread holds HN columns of one output ROW (TMEM lane) in registers; written as is, a warp
+    // store would touch 32 rows x 16 B (measured: 5.5 us per tile, a third of a K=512 GEMM).  The warps transpose
     // through shared memory (the operand ring is idle by now: every MMA has retired) so that each store
     // instruction covers 512 contiguous bytes of ONE row, with bias / ReLU / mask / accumulate applied on the way.
     {
@@ -390,28 +415,31 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       static_assert(4 * 32 * LDS_ROW * 4 <= Cfg::STAGES * Cfg::STAGE_BYTES, "epilogue staging must fit in the operand ring");
       const uint32_t wbase = smem_u32(smem) + (uint32_t)(q * 32 * LDS_ROW * 4);
 #pragma unroll
-      for (int g = 0; g < BN / 4; ++g)
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wbase + (uint32_t)((lane * LDS_ROW + g * 4) * 4)),
+      for (int g = 0; g < HN / 4; ++g)
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wbase + (uint32_t)((lane * LDS_ROW + h * HN + g * 4) * 4)),
                      "f"(acc[g * 4]), "f"(acc[g * 4 + 1]), "f"(acc[g * 4 + 2]), "f"(acc[g * 4 + 3]) : "memory");
-      __syncwarp();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * TC_NH) : "memory");     // the TC_NH warps of this lane quarter
       if (tr && threadIdx.x == 64) tr[37] = clock64();                               // trace: tile parked in smem
       const int64_t row_base = (int64_t)m0 + q * 32;
       const int rows_valid = (int)((M - row_base) < 32 ? (M - row_base) : 32);
+      constexpr int RPW = 32 / TC_NH;                                                // rows each warp of the quarter stores
+      const int r_begin = h * RPW;
+      const int r_end = rows_valid < r_begin + RPW ? rows_valid : r_begin + RPW;
       const bool plain = !ep.atomic && !ep.mask_src.p && !ep.accumulate && ep.C.fmt == FMT_F32;
       const int c4 = lane;                                                           // BN = 128: lane owns 4 columns of every row
       const int n = n0 + c4 * 4;
       static_assert(BN == 128, "the epilogue maps one lane to four columns");
-      if (n < N && rows_valid > 0) {
+      if (n < N && r_end > r_begin) {
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.bias) bv = __ldg((const float4*)(ep.bias + n));
         const uint32_t rbase = wbase + (uint32_t)(c4 * 16);
         if (plain) {
-          // hot path, branch-free: with one warp per scheduler every data-dependent branch costs its full latency
+          // hot path, branch-free: every data-dependent branch costs its full latency
           // (measured: 280 cycles per row in the generic loop, 9 k cycles per tile)
           const float floor_v = ep.relu ? 0.f : -INFINITY;
           float* cp = (float*)ep.C.p + row_base * ep.C.ld + n;
-          int r = 0;
-          for (; r + 8 <= rows_valid; r += 8) {
+          int r = r_begin;
+          for (; r + 8 <= r_end; r += 8) {
             float4 v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u)
@@ -423,7 +451,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
               *(float4*)(cp + (int64_t)(r + u) * ep.C.ld) = v[u];
             }
           }
-          for (; r < rows_valid; ++r) {
+          for (; r < r_end; ++r) {
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rbase + (uint32_t)(r * LDS_ROW * 4)));
             v.x = fmaxf(v.x + bv.x, floor_v); v.y = fmaxf(v.y + bv.y, floor_v); v.z = fmaxf(v.z + bv.z, floor_v); v.w = fmaxf(v.w + bv.w, floor_v);
@@ -431,7 +459,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
           }
         } else {
 #pragma unroll 2
-          for (int r = 0; r < rows_valid; ++r) {
+          for (int r = r_begin; r < r_end; ++r) {
             const int64_t row = row_base + r;
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rbase + (uint32_t)(r * LDS_ROW * 4)));
@@ -570,8 +598,8 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   ep.atomic = split > 1 ? 1 : 0;
   ep.trace = tc_trace_buffer();
   dim3 grid(tiles_n, tiles_m, split);
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, ep, g.M, g.N, g.K, kb_per);
-  return cudaGetLastError() == cudaSuccess ? FB200_OK : FB200_ECUDA;
+  if (pdl_launch(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, ma, mb, ep, g.M, g.N, g.K, kb_per) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
+  return FB200_OK;
 }
 
 template <int KIND, int BN>
@@ -626,8 +654,8 @@ inline int tc_launch_grouped_tn(const TcGroupProblem* probs, int nprob, int K, c
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
     attr_set = true;
   }
-  kern<<<tiles, TC_THREADS, Cfg::SMEM_BYTES, st>>>(g);
-  return cudaGetLastError() == cudaSuccess ? FB200_OK : FB200_ECUDA;
+  if (pdl_launch(kern, dim3(tiles, 1, 1), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, g) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
+  return FB200_OK;
 }
 inline int launch_tc_grouped_tn(int kind, const TcGroupProblem* probs, int nprob, int K, cudaStream_t st) {
   return kind == 0 ? tc_launch_grouped_tn<0>(probs, nprob, K, st) : tc_launch_grouped_tn<1>(probs, nprob, K, st);
@@ -635,7 +663,7 @@ inline int launch_tc_grouped_tn(int kind, const TcGroupProblem* probs, int nprob
 
 // ---- fp32-in / fp32-out wrapper used by the fb200_gemm primitive (unit tests, micro-benchmarks):
 // converts A and B into the operand format inside `ws`, then runs the tcgen05 kernel.
-__global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ in, int64_t rows, int cols, int ld_in, TRef out) {
+__global__ void __launch_bounds__(256) tc_split_kernel(const float* __restrict__ in, int64_t rows, int cols, int ld_in, TRef out) { pdl_sync();
   const int64_t total4 = rows * (cols / 4);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (cols / 4); const int c = (int)(i - r * (cols / 4)) * 4;
@@ -668,8 +696,8 @@ inline int tc_gemm_f32(int layout, int engine, int M, int N, int K, const float*
     char* w = (char*)ws;
     TRef a_ref = make_ref(w, a_cols, FMT_BF16);
     TRef b_ref = make_ref(w + ((tc_operand_bytes(a_rows, a_cols) + 255) & ~size_t(255)), b_cols, FMT_BF16);
-    tc_split_kernel<<<296, 256, 0, st>>>(A, a_rows, a_cols, lda, a_ref);
-    tc_split_kernel<<<296, 256, 0, st>>>(B, b_rows, b_cols, ldb, b_ref);
+    pdl_launch(tc_split_kernel, 296, 256, 0, st, A, a_rows, a_cols, lda, a_ref);
+    pdl_launch(tc_split_kernel, 296, 256, 0, st, B, b_rows, b_cols, ldb, b_ref);
     g.A = TcOperand{a_ref.p, 0, a_cols, a_cols, (int)a_rows};
     g.B = TcOperand{b_ref.p, 0, b_cols, b_cols, (int)b_rows};
   } else {

@@ -77,6 +77,7 @@ def lib():
     sig("fb200_adam_step", i32, i32, pp, pp, pp, pp, C.POINTER(i64), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_float, vp)
     sig("fb200_debug_gemm_replay", i32, dp, pp, vp, vp, vp, vp, vp, vp)
     sig("fb200_debug_tc_trace", i32, vp)
+    sig("fb200_debug_set_pdl", i32, i32)
     sig("fb200_list_gemms", i32, dp, C.POINTER(C.c_int32), i32)
     sig("fb200_head_backward", i32, dp, pp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp)
     sig("fb200_cross_entropy", i32, vp, vp, vp, vp, i32, i32, vp, vp, vp)

@@ -1,0 +1,74 @@
+"""GPU: programmatic dependent launch must be invisible.  Every kernel of the library is launched with the
+programmatic-stream-serialization attribute and gates its first global-memory access on griddepcontrol.wait
+(csrc/common.cuh: pdl_sync).  A missing or misplaced wait shows up as a reader seeing stale data now and then:
+the same forward + backward is repeated many times with the attribute on and off and every repetition has to
+reproduce the first one up to the order of the fp32 gradient atomics (< 1e-6 observed; a stale read is O(1)),
+and the fused Adam chained between torch kernels has to be bit-identical with and without it."""
+import pytest
+import torch
+
+import fusion_b200 as fb
+from fusion_b200 import _lib
+from tests.golden import cases as C
+from tests.gpu_util import build_model, case_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _grads_once(model, x, tin, y, cw, fused):
+    model.zero_grad(set_to_none=True)
+    if fused:
+        loss, _ = model.forward_loss(x, tin, y, cw)
+    else:
+        loss = fb.FusedCrossEntropyLoss(weight=cw)(model(x, tin), y)
+        loss.backward()
+    return loss.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("mech,B,dims", [
+    ("crossattention", 32, C.SMALL_DIMS),                                        # FFMA path: split-K fix-up, bias-gradient atomics
+    ("att-intramodal+residual+cross-attention-metadados", 32, C.SMALL_DIMS),
+    ("crossattention", 256, dict(F=512, V=85, C=6)),                             # tcgen05 path, grouped weight gradients
+])
+def test_repeated_steps_agree_with_pdl(mech, B, dims, fused):
+    L = _lib.lib()
+    case = dict(cfg=dict(dims, mechanism=mech), B=B, seed=5, train=False, full_grads=False)
+    cfg, model = build_model(case, "fp32")
+    x, tin, y, cw, _ = case_inputs(cfg, case)
+    model.eval()
+    prev = L.fb200_debug_set_pdl(0)
+    try:
+        l_ref, g_ref = _grads_once(model, x, tin, y, cw, fused)
+        L.fb200_debug_set_pdl(1)
+        for _ in range(40):
+            l, g = _grads_once(model, x, tin, y, cw, fused)
+            assert abs(float(l) - float(l_ref)) < 2e-6 * abs(float(l_ref))
+            assert g.keys() == g_ref.keys()
+            for k in g_ref:
+                dev = float((g[k] - g_ref[k]).abs().max() / g_ref[k].abs().max().clamp_min(1e-30))
+                assert dev < 1e-5, (k, dev)
+    finally:
+        L.fb200_debug_set_pdl(prev)
+
+
+def test_fused_adam_bitwise_with_and_without_pdl():
+    L = _lib.lib()
+    shapes = [(512, 2048), (512,), (6, 256), (3,), (1536, 512), (7, 13), (256, 85), (256,)]
+    res = {}
+    prev = L.fb200_debug_set_pdl(0)
+    try:
+        for pdl in (0, 1):
+            L.fb200_debug_set_pdl(pdl)
+            torch.manual_seed(1)
+            ps = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+            opt = fb.FusedAdam(ps, lr=5e-3, weight_decay=1e-2)
+            for _ in range(30):
+                for p in ps:
+                    p.grad = torch.randn_like(p)            # torch kernel -> fused Adam -> torch kernel -> ...
+                opt.step()
+            torch.cuda.synchronize()
+            res[pdl] = [p.detach().clone() for p in ps]
+    finally:
+        L.fb200_debug_set_pdl(prev)
+    assert all(torch.equal(a, b) for a, b in zip(res[0], res[1]))
