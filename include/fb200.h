@@ -223,6 +223,26 @@ int fb200_gemm(int layout, int engine, int M, int N, int K,
                const float* bias, int relu, int accumulate, void* ws, size_t ws_bytes, void* stream);
 int fb200_gemm_workspace_bytes(int layout, int engine, int M, int N, int K, size_t* bytes);
 
+/* ---- multi-head attention on token sequences ------------------------------------------------------------------
+ * Replaces torch.nn.MultiheadAttention(embed_dim = D, num_heads = H, batch_first = False, dropout = 0) as the
+ * reference's sequence models call it (models/multimodalGated.py:118-206: image tokens attending to metadata tokens;
+ * models/multimodalIntraInterModal.py:78-100 builds the same module and calls it with S = 1, which the head entry
+ * points above lower to two GEMMs).  query [Sq,B,D], key / value [Skv,B,D], out [Sq,B,D], all contiguous fp32;
+ * in_proj_weight [3D,D] = [W_q; W_k; W_v], in_proj_bias [3D], out_proj_weight [D,D], out_proj_bias [D].
+ * The head-averaged attention weights the module can also return are not produced (every caller discards them).
+ * ws: fb200_mha_workspace_bytes() bytes, 256-byte aligned; forward leaves Q, K, V, the head outputs and the row
+ * log-sum-exps there for backward (the probabilities are recomputed, never stored).  dquery / dkey / dvalue may be
+ * NULL (not needed).  When query, key and value are one tensor the caller adds the three input gradients. */
+typedef struct { int32_t Sq, Skv, B, D, H, flags; } fb200_mha_desc;
+int fb200_mha_workspace_bytes(const fb200_mha_desc* d, size_t* bytes);
+int fb200_mha_forward(const fb200_mha_desc* d, const float* query, const float* key, const float* value,
+                      const float* in_proj_weight, const float* in_proj_bias, const float* out_proj_weight, const float* out_proj_bias,
+                      float* out, void* ws, void* stream);
+int fb200_mha_backward(const fb200_mha_desc* d, const float* query, const float* key, const float* value,
+                       const float* in_proj_weight, const float* out_proj_weight, const float* dout,
+                       float* dquery, float* dkey, float* dvalue, float* d_in_proj_weight, float* d_in_proj_bias,
+                       float* d_out_proj_weight, float* d_out_proj_bias, void* ws, void* stream);
+
 /* y = dropout(relu(LayerNorm(x))), rows of width N (fc_fusion[1:4], [5:8]); stats = [B,2] (mean, rstd) */
 int fb200_ln_relu_dropout_fwd(const float* x, const float* gamma, const float* beta,
                               const uint8_t* mask, float p, int train, uint64_t seed, uint64_t offset, int site,

@@ -1,0 +1,335 @@
+// attention.cuh - fused multi-head attention core for token sequences (north star: "image tokens
+// attending to metadata tokens, softmax held in registers and shared memory").
+//
+//   nn.MultiheadAttention(embed_dim = D, num_heads = H, batch_first = False) on (S, B, D) tensors, general
+//   (S_q, S_kv):   P = softmax(Q_h K_h^T / sqrt(hd)),  O_h = P V_h          (reference call sites with real token
+//   sequences: models/multimodalGated.py:118-206; the current model calls it with S = 1, which the head lowers to
+//   two GEMMs - plan.cu).  The projections around the core run on the library's GEMM engines (exec.cu).
+//
+// The probability matrix never exists in memory.  Forward keeps one running (max, sum, output row) per query in
+// registers (online softmax) while 32-key tiles of K and V stream through shared memory, and stores only O and the
+// row log-sum-exp.  Backward recomputes P from Q, K and the log-sum-exp, flash-attention style, in two passes that
+// need no atomics and are therefore bit-reproducible: one CTA per 16 queries produces dQ (and delta = rowsum(dO * O)),
+// one CTA per 16 keys produces dK and dV.
+//
+// Work split inside a CTA (4 warps, 4 rows each): score-like dot products run lanes-over-keys (each lane owns one
+// key of the tile and walks the head dimension; the tile rows are padded to hd + 1 words so the 32 lanes hit 32
+// banks), accumulations into a head-dim vector run lanes-over-d with the probability broadcast by shuffle.
+// Everything is fp32 with expf/logf: the parity bar is 1e-5 against the float64 oracle.
+#pragma once
+#include "common.cuh"
+
+namespace fb200 {
+
+constexpr int ATT_WARPS = 4;          // warps per CTA
+constexpr int ATT_R = 4;              // query (or key) rows per warp
+constexpr int ATT_ROWS = ATT_WARPS * ATT_R;
+constexpr int ATT_T = 32;             // rows of the streamed tile = one per lane
+
+struct AttnArgs {
+  const float* Q; const float* K; const float* V; int ldq, ldk, ldv;   // projected [S*B, D] views: row = s*B + b, head h = columns [h*hd, +hd)
+  float* O; int ldo;                                                    // [Sq*B, D] heads concatenated (input of out_proj)
+  float* lse;                                                           // [B, H, Sq] row log-sum-exp of the scaled scores
+  const float* dO; int lddo;                                            // backward: gradient of O
+  float* dQ; float* dK; float* dV; int lddq, lddk, lddv;
+  float* delta;                                                         // [B, H, Sq] rowsum(dO * O)
+  int Sq, Sk, B, H, hd;
+  float scale;                                                          // 1 / sqrt(hd), applied to Q as PyTorch does
+};
+
+inline size_t attn_smem_bytes(int hd) { return (size_t)(2 * ATT_T * (hd + 1) + 2 * ATT_ROWS * hd + 2 * ATT_T) * sizeof(float); }
+
+// ---- forward ---------------------------------------------------------------------------------------------------
+template <int NDL>                    // ceil(hd / 32): head-dim elements per lane
+__global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const AttnArgs a) {
+  pdl_sync();
+  extern __shared__ float att_sm[];
+  const int hd = a.hd, ldt = hd + 1;
+  float* Ks = att_sm;                        // [T][hd+1]
+  float* Vs = Ks + ATT_T * ldt;              // [T][hd+1]
+  float* qs = Vs + ATT_T * ldt;              // [ROWS][hd], pre-scaled
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_ROWS;
+  const int col0 = h * hd;
+  for (int idx = threadIdx.x; idx < ATT_ROWS * hd; idx += ATT_WARPS * 32) {
+    const int r = idx / hd, d = idx - r * hd, i = q0 + r;
+    qs[idx] = i < a.Sq ? __ldg(a.Q + ((int64_t)i * a.B + b) * a.ldq + col0 + d) * a.scale : 0.f;
+  }
+  float m[ATT_R], l[ATT_R], o[ATT_R][NDL];
+#pragma unroll
+  for (int r = 0; r < ATT_R; ++r) {
+    m[r] = -INFINITY; l[r] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NDL; ++n) o[r][n] = 0.f;
+  }
+  for (int k0 = 0; k0 < a.Sk; k0 += ATT_T) {
+    __syncthreads();                         // previous tile fully consumed (first pass: qs visible)
+    for (int idx = threadIdx.x; idx < ATT_T * hd; idx += ATT_WARPS * 32) {
+      const int j = idx / hd, d = idx - j * hd, kk = k0 + j;
+      float kv = 0.f, vv = 0.f;
+      if (kk < a.Sk) {
+        kv = __ldg(a.K + ((int64_t)kk * a.B + b) * a.ldk + col0 + d);
+        vv = __ldg(a.V + ((int64_t)kk * a.B + b) * a.ldv + col0 + d);
+      }
+      Ks[j * ldt + d] = kv; Vs[j * ldt + d] = vv;
+    }
+    __syncthreads();
+    const int nk = min(ATT_T, a.Sk - k0);
+#pragma unroll
+    for (int r = 0; r < ATT_R; ++r) {
+      const int i = q0 + warp * ATT_R + r;
+      if (i >= a.Sq) break;                  // warp-uniform
+      const float* q = qs + (warp * ATT_R + r) * hd;
+      const float* kr = Ks + lane * ldt;
+      float s = 0.f;
+      for (int d = 0; d < hd; ++d) s = fmaf(q[d], kr[d], s);
+      if (lane >= nk) s = -INFINITY;
+      const float mn = fmaxf(m[r], warp_max(s));
+      const float p = lane < nk ? expf(s - mn) : 0.f;
+      const float corr = expf(m[r] - mn);    // exp(-inf) = 0 on the first tile
+      l[r] = l[r] * corr + warp_sum(p);
+      m[r] = mn;
+#pragma unroll
+      for (int n = 0; n < NDL; ++n) o[r][n] *= corr;
+      for (int jj = 0; jj < nk; ++jj) {
+        const float pj = __shfl_sync(0xffffffffu, p, jj);
+#pragma unroll
+        for (int n = 0; n < NDL; ++n) {
+          const int d = lane + 32 * n;
+          if (d < hd) o[r][n] = fmaf(pj, Vs[jj * ldt + d], o[r][n]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ATT_R; ++r) {
+    const int i = q0 + warp * ATT_R + r;
+    if (i >= a.Sq) break;
+    const float inv = 1.0f / l[r];
+#pragma unroll
+    for (int n = 0; n < NDL; ++n) {
+      const int d = lane + 32 * n;
+      if (d < hd) a.O[((int64_t)i * a.B + b) * a.ldo + col0 + d] = o[r][n] * inv;
+    }
+    if (lane == 0) a.lse[((int64_t)b * a.H + h) * a.Sq + i] = m[r] + logf(l[r]);
+  }
+}
+
+// ---- backward, pass 1: dQ and delta (one CTA per 16 queries) -----------------------------------------------------
+template <int NDL>
+__global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dq_kernel(const AttnArgs a) {
+  pdl_sync();
+  extern __shared__ float att_sm[];
+  const int hd = a.hd, ldt = hd + 1;
+  float* Ks = att_sm;                        // [T][hd+1]
+  float* Vs = Ks + ATT_T * ldt;              // [T][hd+1]
+  float* qs = Vs + ATT_T * ldt;              // [ROWS][hd], pre-scaled
+  float* dos = qs + ATT_ROWS * hd;           // [ROWS][hd]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_ROWS;
+  const int col0 = h * hd;
+  for (int idx = threadIdx.x; idx < ATT_ROWS * hd; idx += ATT_WARPS * 32) {
+    const int r = idx / hd, d = idx - r * hd, i = q0 + r;
+    float qv = 0.f, dv = 0.f;
+    if (i < a.Sq) {
+      qv = __ldg(a.Q + ((int64_t)i * a.B + b) * a.ldq + col0 + d) * a.scale;
+      dv = __ldg(a.dO + ((int64_t)i * a.B + b) * a.lddo + col0 + d);
+    }
+    qs[idx] = qv; dos[idx] = dv;
+  }
+  __syncthreads();
+  float lse[ATT_R], dl[ATT_R], dq[ATT_R][NDL];
+#pragma unroll
+  for (int r = 0; r < ATT_R; ++r) {
+    const int i = q0 + warp * ATT_R + r;
+    lse[r] = 0.f; dl[r] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NDL; ++n) dq[r][n] = 0.f;
+    if (i < a.Sq) {
+      float part = 0.f;
+#pragma unroll
+      for (int n = 0; n < NDL; ++n) {
+        const int d = lane + 32 * n;
+        if (d < hd) part = fmaf(dos[(warp * ATT_R + r) * hd + d], __ldg(a.O + ((int64_t)i * a.B + b) * a.ldo + col0 + d), part);
+      }
+      dl[r] = warp_sum(part);
+      lse[r] = __ldg(a.lse + ((int64_t)b * a.H + h) * a.Sq + i);
+      if (lane == 0) a.delta[((int64_t)b * a.H + h) * a.Sq + i] = dl[r];
+    }
+  }
+  for (int k0 = 0; k0 < a.Sk; k0 += ATT_T) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ATT_T * hd; idx += ATT_WARPS * 32) {
+      const int j = idx / hd, d = idx - j * hd, kk = k0 + j;
+      float kv = 0.f, vv = 0.f;
+      if (kk < a.Sk) {
+        kv = __ldg(a.K + ((int64_t)kk * a.B + b) * a.ldk + col0 + d);
+        vv = __ldg(a.V + ((int64_t)kk * a.B + b) * a.ldv + col0 + d);
+      }
+      Ks[j * ldt + d] = kv; Vs[j * ldt + d] = vv;
+    }
+    __syncthreads();
+    const int nk = min(ATT_T, a.Sk - k0);
+#pragma unroll
+    for (int r = 0; r < ATT_R; ++r) {
+      const int i = q0 + warp * ATT_R + r;
+      if (i >= a.Sq) break;
+      const float* q = qs + (warp * ATT_R + r) * hd;
+      const float* go = dos + (warp * ATT_R + r) * hd;
+      const float* kr = Ks + lane * ldt;
+      const float* vr = Vs + lane * ldt;
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < hd; ++d) { s = fmaf(q[d], kr[d], s); dp = fmaf(go[d], vr[d], dp); }
+      const float p = lane < nk ? expf(s - lse[r]) : 0.f;
+      // one key: P == 1 and dS == 0 EXACTLY (PyTorch: P * (dP - sum(dP * P)) = dP - dP), the fact behind the
+      // exact-zero W_q / W_k gradients of the reference's S = 1 calls; dp and delta sum in different orders here
+      const float ds = a.Sk == 1 ? 0.f : p * (dp - dl[r]);
+      for (int jj = 0; jj < nk; ++jj) {
+        const float dsj = __shfl_sync(0xffffffffu, ds, jj);
+#pragma unroll
+        for (int n = 0; n < NDL; ++n) {
+          const int d = lane + 32 * n;
+          if (d < hd) dq[r][n] = fmaf(dsj, Ks[jj * ldt + d], dq[r][n]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ATT_R; ++r) {
+    const int i = q0 + warp * ATT_R + r;
+    if (i >= a.Sq) break;
+#pragma unroll
+    for (int n = 0; n < NDL; ++n) {
+      const int d = lane + 32 * n;
+      if (d < hd) a.dQ[((int64_t)i * a.B + b) * a.lddq + col0 + d] = dq[r][n] * a.scale;
+    }
+  }
+}
+
+// ---- backward, pass 2: dK and dV (one CTA per 16 keys; queries stream through shared memory) --------------------
+template <int NDL>
+__global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dkv_kernel(const AttnArgs a) {
+  pdl_sync();
+  extern __shared__ float att_sm[];
+  const int hd = a.hd, ldt = hd + 1;
+  float* Qs = att_sm;                        // [T][hd+1], pre-scaled
+  float* dOs = Qs + ATT_T * ldt;             // [T][hd+1]
+  float* ks = dOs + ATT_T * ldt;             // [ROWS][hd]
+  float* vs = ks + ATT_ROWS * hd;            // [ROWS][hd]
+  float* lse_s = vs + ATT_ROWS * hd;         // [T]
+  float* dl_s = lse_s + ATT_T;               // [T]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * ATT_ROWS;
+  const int col0 = h * hd;
+  for (int idx = threadIdx.x; idx < ATT_ROWS * hd; idx += ATT_WARPS * 32) {
+    const int r = idx / hd, d = idx - r * hd, j = j0 + r;
+    float kv = 0.f, vv = 0.f;
+    if (j < a.Sk) {
+      kv = __ldg(a.K + ((int64_t)j * a.B + b) * a.ldk + col0 + d);
+      vv = __ldg(a.V + ((int64_t)j * a.B + b) * a.ldv + col0 + d);
+    }
+    ks[idx] = kv; vs[idx] = vv;
+  }
+  float dk[ATT_R][NDL], dv[ATT_R][NDL];
+#pragma unroll
+  for (int r = 0; r < ATT_R; ++r)
+#pragma unroll
+    for (int n = 0; n < NDL; ++n) { dk[r][n] = 0.f; dv[r][n] = 0.f; }
+  for (int i0 = 0; i0 < a.Sq; i0 += ATT_T) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ATT_T * hd; idx += ATT_WARPS * 32) {
+      const int t = idx / hd, d = idx - t * hd, i = i0 + t;
+      float qv = 0.f, gv = 0.f;
+      if (i < a.Sq) {
+        qv = __ldg(a.Q + ((int64_t)i * a.B + b) * a.ldq + col0 + d) * a.scale;
+        gv = __ldg(a.dO + ((int64_t)i * a.B + b) * a.lddo + col0 + d);
+      }
+      Qs[t * ldt + d] = qv; dOs[t * ldt + d] = gv;
+    }
+    if (threadIdx.x < ATT_T) {
+      const int i = i0 + threadIdx.x;
+      lse_s[threadIdx.x] = i < a.Sq ? __ldg(a.lse + ((int64_t)b * a.H + h) * a.Sq + i) : 0.f;
+      dl_s[threadIdx.x] = i < a.Sq ? __ldg(a.delta + ((int64_t)b * a.H + h) * a.Sq + i) : 0.f;
+    }
+    __syncthreads();
+    const int nq = min(ATT_T, a.Sq - i0);
+#pragma unroll
+    for (int r = 0; r < ATT_R; ++r) {
+      const int j = j0 + warp * ATT_R + r;
+      if (j >= a.Sk) break;
+      const float* kj = ks + (warp * ATT_R + r) * hd;
+      const float* vj = vs + (warp * ATT_R + r) * hd;
+      const float* qr = Qs + lane * ldt;
+      const float* gr = dOs + lane * ldt;
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < hd; ++d) { s = fmaf(qr[d], kj[d], s); dp = fmaf(gr[d], vj[d], dp); }
+      const float p = lane < nq ? expf(s - lse_s[lane]) : 0.f;
+      const float ds = a.Sk == 1 ? 0.f : p * (dp - dl_s[lane]);
+      for (int ii = 0; ii < nq; ++ii) {
+        const float pi = __shfl_sync(0xffffffffu, p, ii);
+        const float dsi = __shfl_sync(0xffffffffu, ds, ii);
+#pragma unroll
+        for (int n = 0; n < NDL; ++n) {
+          const int d = lane + 32 * n;
+          if (d < hd) {
+            dv[r][n] = fmaf(pi, dOs[ii * ldt + d], dv[r][n]);
+            dk[r][n] = fmaf(dsi, Qs[ii * ldt + d], dk[r][n]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ATT_R; ++r) {
+    const int j = j0 + warp * ATT_R + r;
+    if (j >= a.Sk) break;
+#pragma unroll
+    for (int n = 0; n < NDL; ++n) {
+      const int d = lane + 32 * n;
+      if (d < hd) {
+        a.dK[((int64_t)j * a.B + b) * a.lddk + col0 + d] = dk[r][n];
+        a.dV[((int64_t)j * a.B + b) * a.lddv + col0 + d] = dv[r][n];
+      }
+    }
+  }
+}
+
+// ---- launchers -----------------------------------------------------------------------------------------------
+#define FB200_ATT_DISPATCH(hd, CALL)                 \
+  do {                                               \
+    if ((hd) <= 32) { CALL(1); }                     \
+    else if ((hd) <= 64) { CALL(2); }                \
+    else if ((hd) <= 128) { CALL(4); }               \
+    else { CALL(8); }                                \
+  } while (0)
+
+template <typename K>
+inline cudaError_t attn_set_smem(K kern, size_t bytes) {
+  return bytes > 48 * 1024 ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) : cudaSuccess;
+}
+
+inline cudaError_t launch_attn_fwd(const AttnArgs& a, cudaStream_t st) {
+  if (a.hd < 1 || a.hd > 256) return cudaErrorInvalidValue;
+  const size_t smem = attn_smem_bytes(a.hd);
+  const dim3 grid((a.Sq + ATT_ROWS - 1) / ATT_ROWS, a.H, a.B);
+#define CALL(NDL) do { cudaError_t e = attn_set_smem(attn_fwd_kernel<NDL>, smem); if (e != cudaSuccess) return e; \
+                       pdl_launch(attn_fwd_kernel<NDL>, grid, ATT_WARPS * 32, smem, st, a); } while (0)
+  FB200_ATT_DISPATCH(a.hd, CALL);
+#undef CALL
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_attn_bwd(const AttnArgs& a, cudaStream_t st) {
+  if (a.hd < 1 || a.hd > 256) return cudaErrorInvalidValue;
+  const size_t smem = attn_smem_bytes(a.hd);
+  const dim3 gq((a.Sq + ATT_ROWS - 1) / ATT_ROWS, a.H, a.B), gk((a.Sk + ATT_ROWS - 1) / ATT_ROWS, a.H, a.B);
+#define CALL(NDL) do { cudaError_t e = attn_set_smem(attn_bwd_dq_kernel<NDL>, smem); if (e != cudaSuccess) return e;  \
+                       e = attn_set_smem(attn_bwd_dkv_kernel<NDL>, smem); if (e != cudaSuccess) return e;             \
+                       pdl_launch(attn_bwd_dq_kernel<NDL>, gq, ATT_WARPS * 32, smem, st, a);                          \
+                       pdl_launch(attn_bwd_dkv_kernel<NDL>, gk, ATT_WARPS * 32, smem, st, a); } while (0)
+  FB200_ATT_DISPATCH(a.hd, CALL);
+#undef CALL
+  return cudaGetLastError();
+}
+
+}  // namespace fb200

@@ -3,6 +3,7 @@
 #include "simt_gemm.cuh"
 #include "rowwise.cuh"
 #include "tc_gemm.cuh"
+#include "attention.cuh"
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -704,6 +705,111 @@ int fb200_gemm(int layout, int engine, int M, int N, int K, const float* A, int 
     return FB200_OK;
   }
   return tc_gemm_f32(layout, engine, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, accumulate, ws, ws_bytes, dev.num_sms, (cudaStream_t)stream);
+}
+
+// ---- multi-head attention on token sequences -------------------------------------------------------
+namespace {
+struct MhaLayout { size_t q, k, v, o, lse, delta, dO, dq, dk, dv, total; };
+MhaLayout mha_layout(const fb200_mha_desc& d) {
+  auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
+  const size_t nq = (size_t)d.Sq * d.B * d.D * sizeof(float), nk = (size_t)d.Skv * d.B * d.D * sizeof(float);
+  const size_t ns = (size_t)d.B * d.H * d.Sq * sizeof(float);
+  MhaLayout L; size_t c = 0;
+  L.q = c; c = al(c + nq); L.k = c; c = al(c + nk); L.v = c; c = al(c + nk); L.o = c; c = al(c + nq);
+  L.lse = c; c = al(c + ns); L.delta = c; c = al(c + ns);
+  L.dO = c; c = al(c + nq); L.dq = c; c = al(c + nq); L.dk = c; c = al(c + nk); L.dv = c; c = al(c + nk);
+  L.total = c + 256;
+  return L;
+}
+int mha_check(const fb200_mha_desc* d) {
+  if (!d || d->Sq < 1 || d->Skv < 1 || d->B < 1 || d->D < 4 || d->H < 1) return FB200_EBADARG;
+  if (d->D % d->H != 0) return FB200_EBADARG;                  // nn.MultiheadAttention asserts embed_dim % num_heads == 0
+  if (d->D % 4 != 0 || d->D / d->H > 256) return FB200_EUNSUPPORTED;
+  return FB200_OK;
+}
+// fp32 GEMM on the engine that fits: tcgen05 3xTF32 once the row dimension exceeds 128 and the strides are TMA-legal, else FFMA
+int gemm_auto(int layout, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+              const float* bias, int accumulate, void* stream) {
+  const int rows = layout == 2 ? K : M;
+  const bool aligned = !((((uintptr_t)A) | ((uintptr_t)B) | ((uintptr_t)C)) & 15) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0;
+  const int engine = (rows > 128 && aligned && tc_shape_ok(layout, M, N, K)) ? 1 : 0;
+  return fb200_gemm(layout, engine, M, N, K, A, lda, B, ldb, C, ldc, bias, 0, accumulate, nullptr, 0, stream);
+}
+int colsum_rows(const float* const* xs, float* const* dsts, int n, int rows, int N, int num_sms, cudaStream_t st) {
+  ColsumBatch cb{}; cb.B = rows; cb.nseg = n;
+  for (int i = 0; i < n; ++i) cb.seg[i] = ColsumSeg{make_ref((void*)xs[i], N, FMT_F32), N, dsts[i]};
+  int gx = (rows + 63) / 64; if (gx > 8 * num_sms / n + 1) gx = 8 * num_sms / n + 1; if (gx < 1) gx = 1;
+  pdl_launch(colsum_batch_kernel, dim3(gx, n), 256, 0, st, cb);
+  return cudaGetLastError() == cudaSuccess ? FB200_OK : FB200_ECUDA;
+}
+}  // namespace
+
+int fb200_mha_workspace_bytes(const fb200_mha_desc* d, size_t* bytes) {
+  int rc = mha_check(d); if (rc != FB200_OK) return rc;
+  if (!bytes) return FB200_EBADARG;
+  *bytes = mha_layout(*d).total;
+  return FB200_OK;
+}
+
+int fb200_mha_forward(const fb200_mha_desc* d, const float* query, const float* key, const float* value,
+                      const float* in_proj_weight, const float* in_proj_bias, const float* out_proj_weight, const float* out_proj_bias,
+                      float* out, void* ws, void* stream) {
+  int rc = mha_check(d); if (rc != FB200_OK) return rc;
+  if (!query || !key || !value || !in_proj_weight || !in_proj_bias || !out_proj_weight || !out_proj_bias || !out || !ws) return FB200_EBADARG;
+  if (!is_device_ptr(query) || !is_device_ptr(ws)) return FB200_EUNSUPPORTED;
+  if ((((uintptr_t)ws) & 255)) return FB200_EALIGN;
+  const MhaLayout L = mha_layout(*d);
+  char* w = (char*)ws;
+  const int D = d->D, Mq = d->Sq * d->B, Mk = d->Skv * d->B;
+  float* Qp = (float*)(w + L.q); float* Kp = (float*)(w + L.k); float* Vp = (float*)(w + L.v); float* Oc = (float*)(w + L.o);
+  // packed in_proj_weight = [W_q; W_k; W_v] (torch.nn.MultiheadAttention)
+  rc = gemm_auto(0, Mq, D, D, query, D, in_proj_weight, D, Qp, D, in_proj_bias, 0, stream); if (rc != FB200_OK) return rc;
+  rc = gemm_auto(0, Mk, D, D, key, D, in_proj_weight + (size_t)D * D, D, Kp, D, in_proj_bias + D, 0, stream); if (rc != FB200_OK) return rc;
+  rc = gemm_auto(0, Mk, D, D, value, D, in_proj_weight + (size_t)2 * D * D, D, Vp, D, in_proj_bias + 2 * D, 0, stream); if (rc != FB200_OK) return rc;
+  AttnArgs a{};
+  a.Q = Qp; a.K = Kp; a.V = Vp; a.ldq = a.ldk = a.ldv = D; a.O = Oc; a.ldo = D; a.lse = (float*)(w + L.lse);
+  a.Sq = d->Sq; a.Sk = d->Skv; a.B = d->B; a.H = d->H; a.hd = D / d->H; a.scale = 1.0f / sqrtf((float)a.hd);
+  CUDA_OK(launch_attn_fwd(a, (cudaStream_t)stream));
+  return gemm_auto(0, Mq, D, D, Oc, D, out_proj_weight, D, out, D, out_proj_bias, 0, stream);
+}
+
+int fb200_mha_backward(const fb200_mha_desc* d, const float* query, const float* key, const float* value,
+                       const float* in_proj_weight, const float* out_proj_weight, const float* dout,
+                       float* dquery, float* dkey, float* dvalue, float* d_in_proj_weight, float* d_in_proj_bias,
+                       float* d_out_proj_weight, float* d_out_proj_bias, void* ws, void* stream) {
+  int rc = mha_check(d); if (rc != FB200_OK) return rc;
+  if (!query || !key || !value || !in_proj_weight || !out_proj_weight || !dout || !d_in_proj_weight || !d_in_proj_bias ||
+      !d_out_proj_weight || !d_out_proj_bias || !ws) return FB200_EBADARG;
+  if (!is_device_ptr(dout) || !is_device_ptr(ws)) return FB200_EUNSUPPORTED;
+  DeviceInfo dev; rc = get_device_info(dev); if (rc != FB200_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const MhaLayout L = mha_layout(*d);
+  char* w = (char*)ws;
+  const int D = d->D, Mq = d->Sq * d->B, Mk = d->Skv * d->B;
+  float* Qp = (float*)(w + L.q); float* Kp = (float*)(w + L.k); float* Vp = (float*)(w + L.v); float* Oc = (float*)(w + L.o);
+  float* dOc = (float*)(w + L.dO); float* dQp = (float*)(w + L.dq); float* dKp = (float*)(w + L.dk); float* dVp = (float*)(w + L.dv);
+  // out_proj: dW_o = dout^T O, db_o = colsum(dout), dO = dout W_o
+  rc = gemm_auto(2, D, D, Mq, dout, D, Oc, D, d_out_proj_weight, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
+  rc = gemm_auto(1, Mq, D, D, dout, D, out_proj_weight, D, dOc, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
+  AttnArgs a{};
+  a.Q = Qp; a.K = Kp; a.V = Vp; a.ldq = a.ldk = a.ldv = D; a.O = Oc; a.ldo = D; a.lse = (float*)(w + L.lse); a.delta = (float*)(w + L.delta);
+  a.dO = dOc; a.lddo = D; a.dQ = dQp; a.dK = dKp; a.dV = dVp; a.lddq = a.lddk = a.lddv = D;
+  a.Sq = d->Sq; a.Sk = d->Skv; a.B = d->B; a.H = d->H; a.hd = D / d->H; a.scale = 1.0f / sqrtf((float)a.hd);
+  CUDA_OK(launch_attn_bwd(a, st));
+  // in_proj: dW = [dQ^T query; dK^T key; dV^T value], db = column sums, and the input gradients
+  rc = gemm_auto(2, D, D, Mq, dQp, D, query, D, d_in_proj_weight, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
+  rc = gemm_auto(2, D, D, Mk, dKp, D, key, D, d_in_proj_weight + (size_t)D * D, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
+  rc = gemm_auto(2, D, D, Mk, dVp, D, value, D, d_in_proj_weight + (size_t)2 * D * D, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
+  CUDA_OK(cudaMemsetAsync(d_in_proj_bias, 0, (size_t)3 * D * sizeof(float), st));
+  CUDA_OK(cudaMemsetAsync(d_out_proj_bias, 0, (size_t)D * sizeof(float), st));
+  { const float* xs[2] = {dout, dQp}; float* ds[2] = {d_out_proj_bias, d_in_proj_bias};
+    rc = colsum_rows(xs, ds, 2, Mq, D, dev.num_sms, st); if (rc != FB200_OK) return rc; }
+  { const float* xs[2] = {dKp, dVp}; float* ds[2] = {d_in_proj_bias + D, d_in_proj_bias + 2 * D};
+    rc = colsum_rows(xs, ds, 2, Mk, D, dev.num_sms, st); if (rc != FB200_OK) return rc; }
+  if (dquery) { rc = gemm_auto(1, Mq, D, D, dQp, D, in_proj_weight, D, dquery, D, nullptr, 0, stream); if (rc != FB200_OK) return rc; }
+  if (dkey) { rc = gemm_auto(1, Mk, D, D, dKp, D, in_proj_weight + (size_t)D * D, D, dkey, D, nullptr, 0, stream); if (rc != FB200_OK) return rc; }
+  if (dvalue) { rc = gemm_auto(1, Mk, D, D, dVp, D, in_proj_weight + (size_t)2 * D * D, D, dvalue, D, nullptr, 0, stream); if (rc != FB200_OK) return rc; }
+  return FB200_OK;
 }
 
 int fb200_ln_relu_dropout_fwd(const float* x, const float* gamma, const float* beta, const uint8_t* mask, float p, int train,

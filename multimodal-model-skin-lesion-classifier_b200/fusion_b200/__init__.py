@@ -11,7 +11,8 @@ from . import _lib, dp
 from ._lib import Fb200Error
 from .head import (FusedCrossEntropyLoss, FusedFocalLoss, FusedHeadFunction, FusedSoftTargetCrossEntropy, cross_entropy,
                    make_desc, softmax_argmax)
+from .attention import FusedMHAFunction, MultiheadAttention
 from .model import GraphedTrainStep, MultimodalModel
 from .optim import FusedAdam
 
-__all__ = ["MultimodalModel", "GraphedTrainStep", "FusedAdam", "FusedCrossEntropyLoss", "FusedFocalLoss", "FusedSoftTargetCrossEntropy", "softmax_argmax", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]
+__all__ = ["MultimodalModel", "MultiheadAttention", "FusedMHAFunction", "GraphedTrainStep", "FusedAdam", "FusedCrossEntropyLoss", "FusedFocalLoss", "FusedSoftTargetCrossEntropy", "softmax_argmax", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]

@@ -25,6 +25,11 @@ class Desc(C.Structure):
         "mechanism", "B", "F", "V", "T", "D", "H", "C", "n", "text_mode", "dtype", "train", "flags", "reserved")]
 
 
+class MhaDesc(C.Structure):
+    """struct fb200_mha_desc (include/fb200.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("Sq", "Skv", "B", "D", "H", "flags")]
+
+
 class Fb200Error(RuntimeError):
     """Non-zero status from libfb200 (kept a RuntimeError so the reference's
     ``try/except ... continue`` around each experiment keeps working: train_pad_20.py:486-488)."""
@@ -78,6 +83,10 @@ def lib():
     sig("fb200_debug_gemm_replay", i32, dp, pp, vp, vp, vp, vp, vp, vp)
     sig("fb200_debug_tc_trace", i32, vp)
     sig("fb200_debug_set_pdl", i32, i32)
+    mp = C.POINTER(MhaDesc)
+    sig("fb200_mha_workspace_bytes", i32, mp, C.POINTER(sz))
+    sig("fb200_mha_forward", i32, mp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
+    sig("fb200_mha_backward", i32, mp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     sig("fb200_list_gemms", i32, dp, C.POINTER(C.c_int32), i32)
     sig("fb200_head_backward", i32, dp, pp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp)
     sig("fb200_cross_entropy", i32, vp, vp, vp, vp, i32, i32, vp, vp, vp)
