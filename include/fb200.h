@@ -70,6 +70,9 @@ enum fb200_mechanism {
 #define FB200_FLAG_NEED_DTEXT  2   /* backward also produces d(text_in) (trainable encoder)  */
 #define FB200_FLAG_FORCE_SIMT  4   /* never use the tcgen05 GEMM (exact-fp32 FFMA everywhere) */
 #define FB200_FLAG_FORCE_TC    8   /* use the tcgen05 GEMM wherever its shape rules allow     */
+#define FB200_FLAG_ONE_STREAM 16   /* launch everything on the caller's stream (default: the metadata chain of large
+                                      batches runs on an internal side stream, forked from and joined back into the
+                                      caller's stream inside the call - graph-capturable, invisible to the caller) */
 
 /* dropout sites, reference call order (nn.Dropout modules reached by forward) */
 enum fb200_dropout_site {

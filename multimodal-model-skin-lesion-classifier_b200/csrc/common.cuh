@@ -135,10 +135,9 @@ __device__ __forceinline__ float4 drop_mult4(const DropSpec& d, int64_t row, int
 // third kernel start while the first is still running; measured on B200: a reader two launches downstream then
 // occasionally saw stale data.  With wait-then-release at most two kernels overlap.)
 // FB200_PDL=0 launches without the attribute (A/B measurements).
-__device__ __forceinline__ void pdl_sync() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_release(); }
 inline int& pdl_flag() { static int v = -1; return v; }
 inline bool pdl_enabled() {
   int& v = pdl_flag();

@@ -51,6 +51,8 @@ struct Ctx {
   cudaStream_t st;
   DeviceInfo dev;
   bool gemm_only = false;     // debug replay: launch only the GEMM kernels of the step (bench.py times them with CUDA events)
+  // two-lane execution (Plan::two_lanes): lane 0 = the caller's stream, lane 1 = a side stream for the metadata chain
+  cudaStream_t lane_st[2] = {nullptr, nullptr};
 
   TRef value(const View& v) const {
     const Act& a = p.acts[v.buf];
@@ -95,6 +97,63 @@ static TcOperand tc_operand(const TRef& r, int inner, int outer) {
   TcOperand o; o.base = r.p; o.plane_elems = r.plane; o.ld = r.ld; o.inner = inner; o.outer = outer; return o;
 }
 
+// ------------------------------------------------------------------------------- lanes
+// Side stream and event pool of the calling host thread (forward runs on the main thread, backward on autograd's
+// worker).  Events only order work between the two lanes INSIDE one call: every call forks the side stream from the
+// caller's stream and joins it back before returning, so callers (and CUDA-graph capture) see one stream.
+struct LaneRes {
+  cudaStream_t side[64] = {};
+  std::vector<cudaEvent_t> pool[64];
+};
+static thread_local LaneRes t_lanes;
+struct LaneSync {
+  bool on = false; int dev = 0; size_t next = 0;
+  cudaStream_t st[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev[2];        // per buffer: last event recorded on each lane (nullptr: none)
+  int begin(Ctx& c, size_t nbuf) {
+    on = false;
+    c.lane_st[0] = c.lane_st[1] = c.st;
+    if (!c.p.two_lanes) return FB200_OK;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return FB200_ECUDA;
+    if (!t_lanes.side[dev]) CUDA_OK(cudaStreamCreateWithFlags(&t_lanes.side[dev], cudaStreamNonBlocking));
+    st[0] = c.st; st[1] = t_lanes.side[dev];
+    ev[0].assign(nbuf, nullptr); ev[1].assign(nbuf, nullptr);
+    next = 0; on = true;
+    cudaEvent_t e; int rc = record(0, e); if (rc != FB200_OK) return rc;      // fork: the side stream starts after everything queued so far
+    CUDA_OK(cudaStreamWaitEvent(st[1], e, 0));
+    c.lane_st[1] = st[1];
+    return FB200_OK;
+  }
+  int record(int lane, cudaEvent_t& e) {
+    auto& pool = t_lanes.pool[dev];
+    if (next == pool.size()) { cudaEvent_t n; CUDA_OK(cudaEventCreateWithFlags(&n, cudaEventDisableTiming)); pool.push_back(n); }
+    e = pool[next++];
+    CUDA_OK(cudaEventRecord(e, st[lane]));
+    return FB200_OK;
+  }
+  // before an op on `lane` touches buffer b: wait for the other lane's last op on it
+  int wait_for(int lane, int b) {
+    if (!on || b < 0) return FB200_OK;
+    cudaEvent_t e = ev[1 - lane][b];
+    if (e) CUDA_OK(cudaStreamWaitEvent(st[lane], e, 0));
+    return FB200_OK;
+  }
+  // after an op on `lane` touched the buffers bs
+  int touched(int lane, std::initializer_list<int> bs) {
+    if (!on) return FB200_OK;
+    cudaEvent_t e; int rc = record(lane, e); if (rc != FB200_OK) return rc;
+    for (int b : bs) if (b >= 0) ev[lane][b] = e;
+    return FB200_OK;
+  }
+  int join(Ctx& c) {
+    if (!on) return FB200_OK;
+    cudaEvent_t e; int rc = record(1, e); if (rc != FB200_OK) return rc;
+    CUDA_OK(cudaStreamWaitEvent(st[0], e, 0));
+    on = false; c.st = st[0];
+    return FB200_OK;
+  }
+};
+
 // ------------------------------------------------------------------------------- forward
 // The [N,K] weight operand of a tcgen05 Linear: the bf16 copy in the workspace, or the fp32 master itself.
 static TRef weight_operand(const Ctx& c, const Op& o) {
@@ -115,7 +174,11 @@ static int run_forward(Ctx& c) {
     if (!c.gemm_only) pdl_launch(wprep_kernel, dim3(64, a.nseg), 256, 0, c.st, a);
     CUDA_OK(cudaGetLastError());
   }
+  LaneSync ls; const cudaStream_t main_st = c.st;
+  { int rc = ls.begin(c, p.acts.size()); if (rc != FB200_OK) return rc; }
   for (const Op& o : p.ops) {
+    c.st = c.lane_st[o.lane];
+    for (int b : {o.in0.buf, o.in1.buf, o.in2.buf}) { int rc = ls.wait_for(o.lane, b); if (rc != FB200_OK) return rc; }
     switch (o.kind) {
       case OP_CAST: {
         const TRef src = c.value(o.in0);
@@ -184,8 +247,10 @@ static int run_forward(Ctx& c) {
       default: return FB200_EBADARG;
     }
     CUDA_OK(cudaGetLastError());
+    { int rc = ls.touched(o.lane, {o.out.buf}); if (rc != FB200_OK) return rc; }
   }
-  return FB200_OK;
+  c.st = main_st;
+  return ls.join(c);
 }
 
 // ------------------------------------------------------------------------------- backward
@@ -214,11 +279,16 @@ static int run_backward(Ctx& c) {
   std::vector<ColsumSeg> colsums;
   std::vector<std::vector<TcGroupProblem>> dw_round;   // [k]: k-th application of a weight (k > 0 accumulates, in launch order)
   std::vector<int> tc_uses(NUM_SLOTS, 0);
+  LaneSync ls; const cudaStream_t main_st = c.st;
+  { int rc = ls.begin(c, p.acts.size()); if (rc != FB200_OK) return rc; }      // after the zero fill of the gradient buffer
   for (int oi = (int)p.ops.size() - 1; oi >= 0; --oi) {
     const Op& o = p.ops[oi];
     // the gradient of a view that lives inside a fully written buffer counts as written
     if (o.kind == OP_CAST) continue;                  // format copy of an input: its gradient goes straight to the input (dx_view)
     if (!is_written(o.out)) return FB200_EBADARG;
+    c.st = c.lane_st[o.lane];
+    // gradient buffers this op reads (out) or writes / accumulates into (its inputs): order after the other lane's last touch
+    for (int b : {o.out.buf, o.in0.buf, o.in1.buf, o.in2.buf, o.dx_view.buf}) { int rc = ls.wait_for(o.lane, b); if (rc != FB200_OK) return rc; }
     switch (o.kind) {
       case OP_CAST: break;
       case OP_LINEAR: {
@@ -341,7 +411,10 @@ static int run_backward(Ctx& c) {
       default: return FB200_EBADARG;
     }
     CUDA_OK(cudaGetLastError());
+    { int rc = ls.touched(o.lane, {o.out.buf, o.in0.buf, o.in1.buf, o.in2.buf, o.dx_view.buf}); if (rc != FB200_OK) return rc; }
   }
+  c.st = main_st;
+  { int rc = ls.join(c); if (rc != FB200_OK) return rc; }
   // weight gradients of all tcgen05 Linears, grouped (round 1 only exists for weights applied twice)
   for (size_t round = 0; round < dw_round.size(); ++round) {
     for (size_t base = 0; base < dw_round[round].size(); base += TC_MAX_GROUP) {

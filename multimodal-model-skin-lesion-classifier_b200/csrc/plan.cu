@@ -1,6 +1,7 @@
 // plan.cu - lowers a fb200_desc to the op program (host only).
 #include "plan.h"
 #include <cstring>
+#include <cstdlib>
 
 namespace fb200 {
 
@@ -315,6 +316,26 @@ int build_plan(const fb200_desc& d, Plan& p) {
     } break;
     default:
       p.error = "mechanism not implemented"; return FB200_EUNSUPPORTED;
+  }
+
+  // ---- lanes: the image chain and the metadata chain of a fusion string are independent until the concatenation
+  //      (or the first op that reads both).  Ops whose inputs derive from the metadata input alone get lane 1; the
+  //      executor launches them on a side stream so that the two chains of 128-CTA GEMMs fill each other's idle SMs,
+  //      prologues and epilogues.  Only where it pays: tcgen05 path, batches of at least 512 rows.
+  {
+    std::vector<int> color(p.acts.size(), 0);          // bit 0: image input, bit 1: metadata input
+    color[X] = 1; color[TIN] = 2;
+    int n1 = 0;
+    for (auto& o : p.ops) {
+      int c = 0;
+      for (const View* v : {&o.in0, &o.in1, &o.in2}) if (v->buf >= 0) c |= color[v->buf];
+      o.lane = (c == 2) ? 1 : 0;
+      n1 += o.lane;
+      color[o.out.buf] |= c;
+    }
+    static const bool env_off = [] { const char* e = getenv("FB200_LANES"); return e && e[0] == '0'; }();   // A/B measurements
+    p.two_lanes = p.use_tc && d.B >= 512 && n1 > 0 && n1 < (int)p.ops.size() && !(d.flags & FB200_FLAG_ONE_STREAM) && !env_off;
+    if (!p.two_lanes) for (auto& o : p.ops) o.lane = 0;
   }
 
   // ---- validate slots exist, lay out the flat gradient buffer (slot order)

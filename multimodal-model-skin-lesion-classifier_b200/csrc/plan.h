@@ -65,6 +65,7 @@ struct Op {
   int engine = 0;                                   // LINEAR: 0 SIMT, 1 tcgen05
   View dx_view;                                     // LINEAR: where dX goes (the fp32 external input when in0 is its operand-format copy)
   int wprep = -1;                                   // LINEAR on tcgen05: index into Plan::wprep (operand-format copy of W)
+  int lane = 0;                                     // 1: depends on the metadata input only -> may run on the side stream
 };
 
 struct WPrep { int slot, row0, rows, cols; size_t off; };   // operand-format weight copy living in the workspace
@@ -72,6 +73,7 @@ struct WPrep { int slot, row0, rows, cols; size_t off; };   // operand-format we
 struct Plan {
   fb200_desc d;
   bool use_tc = false;               // tcgen05 GEMMs enabled for this call
+  bool two_lanes = false;            // image chain and metadata chain are launched on two streams (exec.cu)
   std::vector<WPrep> wprep;
   int fmt = FMT_F32;                 // GEMM operand format of workspace activations (F32 / PAIR / BF16)
   std::vector<Act> acts;

@@ -219,7 +219,8 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
   // previous kernel in the stream; wait until every kernel this one depends on has completed and flushed before the
-  // first global-memory access, then let the next kernel start ITS prologue.
+  // first global-memory access, then let the next kernel start ITS prologue.  (Releasing later - once the tile's
+  // last MMA is issued - measured 1 % slower, with one stream and with two.)
   pdl_sync();
   if (tr && threadIdx.x == 0) tr[13] = clock64();                                    // trace: setup done
 

@@ -72,3 +72,26 @@ def test_fused_adam_bitwise_with_and_without_pdl():
     finally:
         L.fb200_debug_set_pdl(prev)
     assert all(torch.equal(a, b) for a, b in zip(res[0], res[1]))
+
+
+@pytest.mark.parametrize("mech", ["crossattention", "gfcam", "metablock", "att-intramodal+residual+cross-attention-metadados",
+                                  "att-intramodal+residual+cross-attention-metadados+att-intramodal+residual", "rg-att"])
+def test_two_lane_execution_equals_one_stream(mech):
+    """Batches of >= 512 rows launch the metadata chain on an internal side stream (plan.cu: lanes, exec.cu: LaneSync).
+    Repeated steps must reproduce the single-stream result (FB200_FLAG_ONE_STREAM) - a missing cross-lane
+    dependency shows up as a stale or half-written operand now and then."""
+    dims = dict(F=512, V=85, C=6)
+    case = dict(cfg=dict(dims, mechanism=mech), B=640, seed=11, train=False, full_grads=False)
+    cfg, one = build_model(case, "fp32", flags=_lib.FLAG_ONE_STREAM)
+    _, two = build_model(case, "fp32")
+    x, tin, y, cw, _ = case_inputs(cfg, case)
+    one.eval(); two.eval()
+    l_ref, g_ref = _grads_once(one, x, tin, y, cw, True)
+    for fused in (True, False):
+        for _ in range(15):
+            l, g = _grads_once(two, x, tin, y, cw, fused)
+            assert abs(float(l) - float(l_ref)) < 2e-6 * abs(float(l_ref))
+            assert g.keys() == g_ref.keys()
+            for k in g_ref:
+                dev = float((g[k] - g_ref[k]).abs().max() / g_ref[k].abs().max().clamp_min(1e-30))
+                assert dev < 1e-5, (k, dev)
