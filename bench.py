@@ -350,16 +350,25 @@ def main():
         cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
                "sample": f"{r['steps']} train steps of batch {B} on the reference torch.nn CPU path (median), {r['ms_per_step']:.1f} ms/step"}
 
+    # ---- the token-sequence attention kernel, timed alone: image tokens attending to metadata tokens
+    extras = None
+    if rank == 0:
+        try:
+            extras = {"mha_tokens": time_token_attention(torch, fb, dev)}
+        except Exception as exc:                                    # never lose the headline line to an extra
+            extras = {"mha_tokens": {"error": repr(exc)}}
+
     if rank == 0:
         line = {
             "metric": "fusion-head train samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if dtype == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "mechanism": mech, "per_gpu_batch": B, "global_batch": B * world,
-                       "F": F, "V": V, "C": Cn, "D": 512, "heads": 8, "parallelism": f"dp{world}", "launch": "eager" if args.no_graph else "one CUDA graph per train step",
+                       "F": F, "V": V, "C": Cn, "D": 512, "heads": 8, "parallelism": f"dp{world}", "launch": ("eager" if args.no_graph else "one CUDA graph per train step") + "; every kernel launched with programmatic dependent launch; metadata chain on an internal side stream",
                        "l2": f"inputs rotate over a pool of {nb} batches = {nb * in_bytes / 1e6:.0f} MB (> 126 MB L2 when >= 127); weights ({plive * 4 / 1e6:.1f} MB) stay L2-resident by design"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss": last_loss, "sweep": sweep or None,
+            "extras": extras,
         }
         emit(line)
     if world > 1:
@@ -455,6 +464,29 @@ def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype, model):
             "hbm_gbs": hbm, "step_peak_tflops": peak, "gemm_ms_per_step": tot_ms, "gemm_launches_per_step": sum(shapes.values()),
             "how": "all GEMM launches of one train step replayed alone (fb200_debug_gemm_replay), CUDA events on the launch stream, eager launches",
             "top_shapes_single_launch": per[:6]}
+
+
+def time_token_attention(torch, fb, dev, Sq=197, Skv=85, B=32, D=512, H=8, reps=20):
+    """fb200_mha_forward + fb200_mha_backward through the MultiheadAttention drop-in on ViT-sized image tokens (197)
+    attending to 85 metadata tokens, batch 32, COMMON_DIM 512, 8 heads; CUDA events, median of `reps`."""
+    m = fb.MultiheadAttention(D, H).to(dev)
+    q = torch.randn(Sq, B, D, device=dev, requires_grad=True)
+    kv = torch.randn(Skv, B, D, device=dev, requires_grad=True)
+    dy = torch.randn(Sq, B, D, device=dev)
+    tf, tb = [], []
+    for i in range(reps + 3):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        q.grad = kv.grad = None; m.zero_grad(set_to_none=True)
+        e0.record(); out, _ = m(q, kv, kv); e1.record(); out.backward(dy); e2.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            tf.append(e0.elapsed_time(e1)); tb.append(e1.elapsed_time(e2))
+    hd = D // H
+    core = 4.0 * B * H * Sq * Skv * hd                      # QK^T and PV, forward
+    proj = 2.0 * D * D * B * (2 * Sq + 2 * Skv)             # q, k, v, out projections
+    fwd_ms, bwd_ms = statistics.median(tf), statistics.median(tb)
+    return {"shape": {"Sq": Sq, "Skv": Skv, "B": B, "D": D, "H": H}, "fwd_us": fwd_ms * 1e3, "bwd_us": bwd_ms * 1e3,
+            "fwd_tflops": (core + proj) / (fwd_ms * 1e-3) / 1e12, "note": "eager launches through autograd (host overhead included); fp32, probabilities never stored"}
 
 
 def measure_tf32_peak(torch, dev, n=8192):

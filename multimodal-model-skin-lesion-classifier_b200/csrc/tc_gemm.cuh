@@ -36,6 +36,7 @@ struct TcEpilogue {
   int accumulate;         // C += result
   int atomic;             // split-K: fp32 atomic add into C (FMT_F32 only)
   float* colsum;          // optional: colsum[n] += sum_m result(m,n)  (unused by the head; reserved)
+  int dbg;                // debug (timing experiments only, results are wrong): 1 skip B split, 2 skip A split, 4 one MMA per k-slice, 8 two MMAs
   long long* trace;       // debug: per-k-block clock64 stamps of CTA (0,0,0): [i*8 + {issue, full, mma_issued, empty_seen, split_done}]
 };
 
@@ -282,8 +283,8 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
           const uint32_t first = (chunk_first && j == 0) ? 0u : 1u;
           if (ATM) {
             umma_ts_tf32(d_tmem, a_tm + j * Cfg::UMMA_K, db, idesc, first);
-            umma_ts_tf32(d_tmem, a_tm + Cfg::BK + j * Cfg::UMMA_K, db, idesc, 1u);
-            umma_ts_tf32(d_tmem, a_tm + j * Cfg::UMMA_K, db + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);
+            if (!(ep.dbg & 4)) umma_ts_tf32(d_tmem, a_tm + Cfg::BK + j * Cfg::UMMA_K, db, idesc, 1u);
+            if (!(ep.dbg & 12)) umma_ts_tf32(d_tmem, a_tm + j * Cfg::UMMA_K, db + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);
           } else {
             umma<KIND>(d_tmem, da, db, idesc, first);
             if (KIND == 1) {
@@ -342,7 +343,10 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         if (ATM) {
           // A: thread = output row m (TMEM lane 32q + lane); gather its KH values of K, split, store hi | lo to TMEM.
           uint32_t hi[KH], lo[KH];
-          if (A_MN) {
+          if (ep.dbg & 2) {
+#pragma unroll
+            for (int rr = 0; rr < KH; ++rr) { hi[rr] = 0x3f800000u; lo[rr] = 0u; }
+          } else if (A_MN) {
             // MN-major tile (dW: A = dY^T): chunk q holds m in [32q, 32q+32); K row r is 128 B with its four
             // 32-byte groups XOR-swizzled by (r & 3).  One 4-byte load per K value, conflict-free across the warp.
             const uint32_t base = st + q * (Cfg::BK * 128) + (lane & 7) * 4;
@@ -373,12 +377,14 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
           // B: the raw tile stays where TMA put it (= hi); the lo plane goes to the second buffer at the same swizzled
           // offsets (elementwise, swizzle-oblivious); explicit ld/st.shared.  Issued between the TMEM stores and
           // their wait so that the store latency is covered.
+          if (!(ep.dbg & 1)) {
 #pragma unroll 4
           for (int v = tw; v < Cfg::B_BYTES / 16; v += 32 * TC_WORKERS) {
             const uint32_t hi_a = st + Cfg::B_OFF + v * 16, lo_a = hi_a + Cfg::B_BYTES;
             float4 x;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(low(x.x)), "f"(low(x.y)), "f"(low(x.z)), "f"(low(x.w)) : "memory");
+          }
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
@@ -519,7 +525,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_grouped_tn_kernel(const
   const int tiles_n = (g.N[p] + BN - 1) / BN;
   TcEpilogue ep;
   ep.C = make_ref(g.C[p], g.ldc[p], FMT_F32); ep.bias = nullptr; ep.relu = 0; ep.mask_src.p = nullptr; ep.accumulate = g.accumulate[p];
-  ep.atomic = 0; ep.colsum = nullptr; ep.trace = nullptr;
+  ep.atomic = 0; ep.colsum = nullptr; ep.trace = nullptr; ep.dbg = 0;
   tc_gemm_tile<KIND, 1, 1, BN>(&g.maps[2 * p], &g.maps[2 * p + 1], ep, g.M[p], g.N[p], (t / tiles_n) * TC_BM, (t % tiles_n) * BN, 0,
                                (g.K + Cfg::BK - 1) / Cfg::BK, nullptr);
 }
@@ -598,6 +604,7 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   split = (total_kb + kb_per - 1) / kb_per;                       // no empty slices
   ep.atomic = split > 1 ? 1 : 0;
   ep.trace = tc_trace_buffer();
+  { static const int dbg = [] { const char* e = getenv("FB200_TC_DBG"); return e ? atoi(e) : 0; }(); ep.dbg = dbg; }
   dim3 grid(tiles_n, tiles_m, split);
   if (pdl_launch(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, ma, mb, ep, g.M, g.N, g.K, kb_per) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
   return FB200_OK;
