@@ -12,8 +12,8 @@
 //                 forward (X W^T), dX (dY W) and dW (dY^T X) all read the SAME row-major
 //                 tensors straight from HBM through TMA - nothing is ever transposed in memory.
 //
-// CTA = 320 threads: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
-// single-thread MMA issuer, warps 2..9 = workers (operand split, chunk promotion, epilogue:
+// CTA = 576 threads: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..17 = workers (operand split, chunk promotion, epilogue:
 // TMEM -> registers -> smem -> global, fused bias / ReLU / ReLU-mask / accumulate / split-K reduction).  One 128 x BLOCK_N output tile per CTA,
 // STAGES-deep smem ring of 128-byte-swizzled tiles guarded by full/empty mbarriers.
 #pragma once
@@ -24,8 +24,10 @@
 namespace fb200 {
 
 constexpr int TC_BM = 128;
-constexpr int TC_NH = 2;                          // worker warps per TMEM lane quarter: each owns 1/TC_NH of the columns
+constexpr int TC_NH = 4;                          // worker warps per TMEM lane quarter: each owns 1/TC_NH of the columns
 constexpr int TC_WORKERS = 4 * TC_NH;             // split + promote + epilogue warps
+constexpr int TC_GROUPS = 2;                      // fp32-strict: the workers split k-blocks in turn (group g takes i = g mod TC_GROUPS)
+constexpr int TC_GWARPS = TC_WORKERS / TC_GROUPS; // warps of one group: all four lane quarters x TC_NH / TC_GROUPS column parts
 constexpr int TC_THREADS = 64 + 32 * TC_WORKERS;  // + TMA producer warp + MMA warp
 
 struct TcEpilogue {
@@ -36,7 +38,7 @@ struct TcEpilogue {
   int accumulate;         // C += result
   int atomic;             // split-K: fp32 atomic add into C (FMT_F32 only)
   float* colsum;          // optional: colsum[n] += sum_m result(m,n)  (unused by the head; reserved)
-  int dbg;                // debug (timing experiments only, results are wrong): 1 skip B split, 2 skip A split, 4 one MMA per k-slice, 8 two MMAs
+  int dbg;                // debug (timing experiments only, results are wrong): 1 skip B split, 2 skip A split, 16 no tcgen05.st, 32 no A TMA, 64 no B TMA
   long long* trace;       // debug: per-k-block clock64 stamps of CTA (0,0,0): [i*8 + {issue, full, mma_issued, empty_seen, split_done}]
 };
 
@@ -59,11 +61,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU.
+// SPIN = true only for the single MMA-issuing thread.  Everybody else backs off with nanosleep between polls: ten warps
+// polling flat out (try_wait returns at once on this hardware) compete with the MMA warp for issue slots on their
+// schedulers - measured, the MMA thread needed ~800 cycles to issue the four k-slices of a k-block.
+template <bool SPIN = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { __trap(); }
+  for (uint32_t n = 1;; ++n) {
+    if (!SPIN) __nanosleep(32);
+    if (mbar_try_wait(bar, parity)) return;
+    if ((n & 1023u) == 0 && clock64() - t0 > 4000000000LL) { __trap(); }
   }
 }
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
@@ -73,6 +81,12 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// exactly one lane of the (converged) warp gets true
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -120,6 +134,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+template <int N> __device__ __forceinline__ void tmem_stN(uint32_t taddr, const uint32_t (&r)[N]);
+template <> __device__ __forceinline__ void tmem_stN<16>(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
+template <> __device__ __forceinline__ void tmem_stN<8>(uint32_t taddr, const uint32_t (&r)[8]) { tmem_st8(taddr, r); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -161,17 +183,23 @@ struct TcCfg {
   static constexpr int PLANES = KIND == 0 ? 1 : 2;       // smem planes per operand tile (tf32x3: raw/hi + lo)
   static constexpr int A_BYTES = TC_BM * 128;            // one plane of the A tile
   static constexpr int B_BYTES = BN * 128;
-  // ATM (fp32-strict, K-major A): the split A tile goes to TENSOR MEMORY (tcgen05.st) instead of back to
-  // shared memory, and the MMAs read A from TMEM - shared memory then only carries the raw A tile once and
-  // the B planes, which is what keeps the 128-byte/clk smem port from starving the tensor pipe.
+  // ATM (fp32-strict): the split A tile goes to TENSOR MEMORY (tcgen05.st) instead of back to shared memory, and
+  // the MMAs read A from TMEM - shared memory then only carries the raw A tile once and the B planes.
+  // The raw A tiles and the B planes live in TWO rings: an A slot is free again as soon as the workers have read it
+  // into registers, a B slot only when the MMAs that read it have retired.  Measured on B200, the mainloop was bound
+  // by bytes in flight (TMA issue -> landed ~3400 cycles under load, over 4 coupled stages = 1080 cycles per k-block
+  // with NO split work and one MMA instead of three); 4 A slots + 5 B slots use the same 224 KB better.
   static constexpr int A_PLANES = ATM ? 1 : PLANES;      // smem planes of A
-  static constexpr int B_OFF = A_PLANES * A_BYTES;       // B tile offset inside a stage
-  static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + PLANES * B_BYTES;
-  static constexpr int TMA_BYTES = A_BYTES + B_BYTES;    // bytes TMA delivers per stage (one plane of each)
-  static constexpr int STAGES = (KIND == 0) ? (BN <= 128 ? 6 : 4) : (ATM ? 4 : (BN <= 128 ? 3 : 2));
+  static constexpr int STAGES = (KIND == 0) ? (BN <= 128 ? 6 : 4) : (ATM ? 5 : (BN <= 128 ? 3 : 2));   // ring of B (ATM) / of A+B stages
+  static constexpr int A_STAGES = ATM ? 4 : STAGES;      // ATM: ring of raw A tiles in smem = ring of split A tiles in TMEM
+  static constexpr int A_RING_BYTES = ATM ? A_STAGES * A_BYTES : 0;                 // ATM: A ring first, then the B ring
+  static constexpr int B_OFF = ATM ? 0 : A_PLANES * A_BYTES;                         // B tile offset inside a stage
+  static constexpr int STAGE_BYTES = (ATM ? 0 : A_PLANES * A_BYTES) + PLANES * B_BYTES;
+  static constexpr int TMA_BYTES = A_BYTES + B_BYTES;    // bytes TMA delivers per k-block (one plane of each)
+  static constexpr int RING_BYTES = A_RING_BYTES + STAGES * STAGE_BYTES;
   static constexpr int A_TMEM_COLS = 2 * (128 / ESIZE);  // hi + lo columns of one A stage in TMEM (ATM)
   static constexpr int EPC = 128 / ESIZE;                // elements per 128-byte chunk along MN (MN-major operands)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   // The tensor-core accumulator truncates on every accumulate, a bias that grows linearly with the number
   // of MMAs chained into one TMEM accumulator (measured: 3e-5 relative at K = 4096 in 3xTF32).  The
   // fp32-strict kind therefore accumulates at most CHUNK_KB k-blocks (K = 128) in TMEM, and the epilogue
@@ -180,7 +208,7 @@ struct TcCfg {
   static constexpr int CHUNK_KB = KIND == 1 ? 4 : (1 << 30);
   static constexpr int ACC_BUFS = KIND == 1 ? 2 : 1;
   static constexpr int ACC_COLS = ACC_BUFS * BN;
-  static constexpr int TMEM_NEED = ACC_COLS + (ATM ? STAGES * A_TMEM_COLS : 0);
+  static constexpr int TMEM_NEED = ACC_COLS + (ATM ? A_STAGES * A_TMEM_COLS : 0);
   static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
   static_assert(TMEM_NEED <= 512, "tensor memory has 512 columns");
 };
@@ -194,12 +222,16 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
   using Cfg = TcCfg<KIND, BN, ATM>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);      // 128B swizzle needs 1024-byte alignment
-  uint64_t* full_bar = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint8_t* ring_b = smem + Cfg::A_RING_BYTES;               // stages of B planes (ATM) / of A+B tiles
+  uint64_t* full_bar = (uint64_t*)(smem + Cfg::RING_BYTES); // [STAGES] TMA landed (ATM: the B tile)
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;             // [STAGES] the MMAs that read the stage have retired
   uint64_t* split_bar = empty_bar + Cfg::STAGES;            // [STAGES] tf32x3: tile split into hi/lo, ready for the MMA thread
   uint64_t* tmem_full = split_bar + Cfg::STAGES;            // [2]
   uint64_t* tmem_empty = tmem_full + 2;                     // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint64_t* a_full = tmem_empty + 2;                        // [A_STAGES] ATM: raw A tile landed
+  uint64_t* a_empty = a_full + Cfg::A_STAGES;               // [A_STAGES] ATM: every worker warp has read the raw A tile
+  uint32_t* tmem_slot = (uint32_t*)(a_empty + Cfg::A_STAGES);
+  static_assert((3 * Cfg::STAGES + 4 + 2 * Cfg::A_STAGES) * 8 + 4 <= 512, "barrier block");
   const CUtensorMap& map_a = *pmap_a;
   const CUtensorMap& map_b = *pmap_b;
 
@@ -208,7 +240,8 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], TC_WORKERS); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], KIND == 1 ? TC_GWARPS : TC_WORKERS); }
+    for (int a = 0; a < Cfg::A_STAGES; ++a) { mbar_init(&a_full[a], 1); mbar_init(&a_empty[a], TC_GWARPS); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], TC_WORKERS); mbar_init(&tmem_empty[1], TC_WORKERS);   // one arrive per worker warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,20 +261,22 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
+      auto load_b = [&](int i) {
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (tr) tr[i * 8 + 3] = clock64();
-        mbar_expect_tx(&full_bar[s], Cfg::TMA_BYTES);
-        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        if (ATM && (ep.dbg & 64)) { mbar_expect_tx(&full_bar[s], 0); return; }
+        mbar_expect_tx(&full_bar[s], ATM ? Cfg::B_BYTES : Cfg::TMA_BYTES);
+        uint8_t* st = ring_b + s * Cfg::STAGE_BYTES;
         const int k0 = (kb_begin + i) * Cfg::BK;
-        uint8_t* a_dst = st;
         uint8_t* b_dst = st + Cfg::B_OFF;
-        if (A_MN) {
+        if (!ATM) {
+          if (A_MN) {
 #pragma unroll
-          for (int c = 0; c < TC_BM / Cfg::EPC; ++c) tma_load_3d(&map_a, &full_bar[s], a_dst + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, k0, 0);
-        } else {
-          tma_load_3d(&map_a, &full_bar[s], a_dst, k0, m0, 0);
+            for (int c = 0; c < TC_BM / Cfg::EPC; ++c) tma_load_3d(&map_a, &full_bar[s], st + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, k0, 0);
+          } else {
+            tma_load_3d(&map_a, &full_bar[s], st, k0, m0, 0);
+          }
         }
         if (B_MN) {
 #pragma unroll
@@ -250,11 +285,37 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
           tma_load_3d(&map_b, &full_bar[s], b_dst, k0, n0, 0);
         }
         if (tr) tr[i * 8 + 0] = clock64();
+      };
+      auto load_a = [&](int i) {                       // ATM only: the raw A tile of k-block i into its own ring
+        const int sa = i % Cfg::A_STAGES; const uint32_t ph = (i / Cfg::A_STAGES) & 1;
+        mbar_wait(&a_empty[sa], ph ^ 1);
+        if (ep.dbg & 32) { mbar_expect_tx(&a_full[sa], 0); return; }
+        mbar_expect_tx(&a_full[sa], Cfg::A_BYTES);
+        uint8_t* a_dst = smem + sa * Cfg::A_BYTES;
+        const int k0 = (kb_begin + i) * Cfg::BK;
+        if (A_MN) {
+#pragma unroll
+          for (int c = 0; c < TC_BM / Cfg::EPC; ++c) tma_load_3d(&map_a, &a_full[sa], a_dst + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, k0, 0);
+        } else {
+          tma_load_3d(&map_a, &a_full[sa], a_dst, k0, m0, 0);
+        }
+      };
+      // A runs one k-block ahead of B in issue order: the B ring is the tight one (its slots wait for the MMAs), and an
+      // A tile must never queue behind a B slot that is not free yet
+      if (ATM) load_a(0);
+      for (int i = 0; i < num_kb; ++i) {
+        load_b(i);
+        if (ATM && i + 1 < num_kb) load_a(i + 1);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the WHOLE warp walks the k-blocks in lock step, one ELECTED lane issues.  Uniform control flow keeps
+    //       the descriptor arithmetic on the uniform datapath; under a plain `if (lane == 0)` the compiler wraps every
+    //       tcgen05.mma in an elect / branch "waterfall" loop over the active lanes (~200 cycles per k-slice whatever the
+    //       number of MMAs).  Issued back to back, the twelve TS-mode tf32 MMAs of a k-block take ~1170 cycles of tensor
+    //       pipe (~97 each): that is the mainloop's bound now - a second issuing warp taking every other k-block (token
+    //       passed through named barriers) hid the ~400-cycle handshake but did not shorten the period. =====
+    {
       constexpr uint32_t idesc = make_idesc(KIND, ATM ? 0 : A_MN, B_MN, TC_BM, BN);
       constexpr uint32_t a_lt = (A_MN && KIND == 1) ? 1 : 2, b_lt = (B_MN && KIND == 1) ? 1 : 2;   // smem layout types
       constexpr uint32_t a_lbo = A_MN ? Cfg::BK * 128 : 16, a_sbo = (A_MN && KIND == 1) ? 512 : 1024;
@@ -266,43 +327,45 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
         const int chunk = i / Cfg::CHUNK_KB, ab = chunk & (Cfg::ACC_BUFS - 1);
         const bool chunk_first = (i % Cfg::CHUNK_KB) == 0;
-        if (chunk_first) { mbar_wait(&tmem_empty[ab], ((chunk / Cfg::ACC_BUFS) & 1) ^ 1); tc_fence_after(); }
-        mbar_wait(KIND == 1 ? &split_bar[s] : &full_bar[s], ph);
+        if (tr && lane == 0) tr[i * 8 + 7] = clock64();
+        if (chunk_first) { mbar_wait<true>(&tmem_empty[ab], ((chunk / Cfg::ACC_BUFS) & 1) ^ 1); }
+        mbar_wait<true>(KIND == 1 ? &split_bar[s] : &full_bar[s], ph);
+        if (tr && lane == 0) tr[i * 8 + 6] = clock64();
         tc_fence_after();
-        if (tr) tr[i * 8 + 1] = clock64();
+        if (tr && lane == 0) tr[i * 8 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
-        const uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t a_hi = smem_u32(ring_b + s * Cfg::STAGE_BYTES);                  // (A in smem: the non-ATM kinds)
         const uint32_t b_hi = a_hi + Cfg::B_OFF;
         // descriptors differ only in the 14-bit start-address field (>> 4): add to the low word
         const uint64_t da0 = a_desc_base + (uint64_t)(a_hi >> 4), db0 = b_desc_base + (uint64_t)(b_hi >> 4);
-        const uint32_t a_tm = tmem_base + (uint32_t)(Cfg::ACC_COLS + s * Cfg::A_TMEM_COLS);      // ATM: hi columns, lo = +BK
+        const uint32_t a_tm = tmem_base + (uint32_t)(Cfg::ACC_COLS + (i % Cfg::A_STAGES) * Cfg::A_TMEM_COLS);      // ATM: hi columns, lo = +BK
+        const bool last_of_chunk = (i % Cfg::CHUNK_KB) == Cfg::CHUNK_KB - 1 || i == num_kb - 1;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int j = 0; j < Cfg::BK / Cfg::UMMA_K; ++j) {
-          const uint64_t da = da0 + (uint64_t)((j * a_kstep) >> 4);
-          const uint64_t db = db0 + (uint64_t)((j * b_kstep) >> 4);
-          const uint32_t first = (chunk_first && j == 0) ? 0u : 1u;
-          if (ATM) {
-            umma_ts_tf32(d_tmem, a_tm + j * Cfg::UMMA_K, db, idesc, first);
-            if (!(ep.dbg & 4)) umma_ts_tf32(d_tmem, a_tm + Cfg::BK + j * Cfg::UMMA_K, db, idesc, 1u);
-            if (!(ep.dbg & 12)) umma_ts_tf32(d_tmem, a_tm + j * Cfg::UMMA_K, db + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);
-          } else {
-            umma<KIND>(d_tmem, da, db, idesc, first);
-            if (KIND == 1) {
-              umma<KIND>(d_tmem, da + (uint64_t)(Cfg::A_BYTES >> 4), db, idesc, 1u);
-              umma<KIND>(d_tmem, da, db + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);
+          for (int j = 0; j < Cfg::BK / Cfg::UMMA_K; ++j) {
+            const uint64_t da = da0 + (uint64_t)((j * a_kstep) >> 4);
+            const uint64_t db = db0 + (uint64_t)((j * b_kstep) >> 4);
+            const uint32_t first = (chunk_first && j == 0) ? 0u : 1u;
+            if (ATM) {
+              umma_ts_tf32(d_tmem, a_tm + j * Cfg::UMMA_K, db, idesc, first);
+              umma_ts_tf32(d_tmem, a_tm + Cfg::BK + j * Cfg::UMMA_K, db, idesc, 1u);
+              umma_ts_tf32(d_tmem, a_tm + j * Cfg::UMMA_K, db + (uint64_t)(Cfg::B_BYTES >> 4), idesc, 1u);
+            } else {
+              umma<KIND>(d_tmem, da, db, idesc, first);
             }
           }
+          umma_commit(&empty_bar[s]);                                               // frees the smem slot once these MMAs retire
+          if (last_of_chunk) umma_commit(&tmem_full[ab]);                           // chunk accumulator complete
         }
-        umma_commit(&empty_bar[s]);                                                 // frees the smem slot once these MMAs retire
-        if (tr) tr[i * 8 + 2] = clock64();
-        if ((i % Cfg::CHUNK_KB) == Cfg::CHUNK_KB - 1 || i == num_kb - 1) umma_commit(&tmem_full[ab]);   // chunk accumulator complete
+        __syncwarp();
+        if (tr && lane == 0) tr[i * 8 + 2] = clock64();
       }
     }
   } else {
-    // ===== workers: warps 2..9.  A warp may only touch TMEM lanes [32 (warp % 4), +32); the TC_NH warps that share a
-    //       lane quarter split the columns between them (h = which part).  Two warps per scheduler: the operand split is
-    //       issue/latency bound, one warp per scheduler left the tensor pipe waiting for it (1275 cycles per k-block
-    //       against 817 of MMA work). =====
+    // ===== workers: warps 2..17.  A warp may only touch TMEM lanes [32 (warp % 4), +32); the TC_NH warps that share a
+    //       lane quarter split the columns between them (h = which part).  Four warps per scheduler: the operand split is
+    //       issue / latency bound - its slowest warp, not the tensor pipe, set the pace with one (1275 cycles per k-block)
+    //       and with two warps per scheduler (1316; the twelve MMAs of a k-block issue in ~700). =====
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
     constexpr int HN = BN / TC_NH;                                                   // accumulator columns per thread
@@ -328,87 +391,89 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
     };
     int next_promote = 0;
     if constexpr (KIND == 1) {
-      const int tw = threadIdx.x - 64;                                              // 0 .. 32 * TC_WORKERS - 1
-      constexpr int KH = Cfg::BK / TC_NH;                                           // K values of the A tile this thread splits
-      for (int i = 0; i < num_kb; ++i) {
+      // Two groups of eight warps take the k-blocks in turn: the split of one k-block is a chain of dependent
+      // latencies (LDS -> ALU -> tcgen05.st / STS -> wait::st -> proxy fence -> arrive, ~1300 cycles under load whether 8 or
+      // 16 warps share it), so each group gets two k-block periods for it and the tensor pipe sees one every period.
+      constexpr int NHG = TC_NH / TC_GROUPS;                                        // column parts per lane quarter inside a group
+      const int grp = h / NHG, hh = h % NHG;
+      const int tw = (threadIdx.x - 64) - grp * (32 * TC_GWARPS);                   // 0 .. 32 * TC_GWARPS - 1 inside the group
+      constexpr int KH = Cfg::BK / NHG;                                             // K values of the A tile this thread splits
+      static_assert(ATM, "fp32-strict always stages A through tensor memory");
+      for (int i = grp; i < num_kb; i += TC_GROUPS) {
         const int s = i % Cfg::STAGES; const uint32_t ph = (i / Cfg::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const int sa = i % Cfg::A_STAGES; const uint32_t pha = (i / Cfg::A_STAGES) & 1;
         // The tensor core TRUNCATES the low 13 mantissa bits of a tf32 operand.  So the raw fp32 value IS the hi
         // operand (hi = trunc(x), no ALU work and no smem rewrite), lo = x - trunc(x) is exact in fp32, and only lo
         // is rounded to nearest (ties away) on the bit pattern: a truncated lo would be a one-sided error that does
         // not average out over K.  x = hi + lo to 2^-22 |x|, unbiased.
         auto rnd = [](float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); };
         auto low = [&rnd](float x) { return rnd(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); };
-        if (ATM) {
-          // A: thread = output row m (TMEM lane 32q + lane); gather its KH values of K, split, store hi | lo to TMEM.
-          uint32_t hi[KH], lo[KH];
-          if (ep.dbg & 2) {
+        // A: thread = output row m (TMEM lane 32q + lane); gather its KH values of K from the raw tile, split, store
+        // hi | lo to tensor memory.
+        mbar_wait(&a_full[sa], pha);
+        const uint32_t sta = smem_u32(smem + sa * Cfg::A_BYTES);
+        uint32_t hi[KH], lo[KH];
+        if (ep.dbg & 2) {
 #pragma unroll
-            for (int rr = 0; rr < KH; ++rr) { hi[rr] = 0x3f800000u; lo[rr] = 0u; }
-          } else if (A_MN) {
-            // MN-major tile (dW: A = dY^T): chunk q holds m in [32q, 32q+32); K row r is 128 B with its four
-            // 32-byte groups XOR-swizzled by (r & 3).  One 4-byte load per K value, conflict-free across the warp.
-            const uint32_t base = st + q * (Cfg::BK * 128) + (lane & 7) * 4;
-            const int gsel = lane >> 3;
+          for (int rr = 0; rr < KH; ++rr) { hi[rr] = 0x3f800000u; lo[rr] = 0u; }
+        } else if (A_MN) {
+          // MN-major tile (dW: A = dY^T): chunk q holds m in [32q, 32q+32); K row r is 128 B with its four
+          // 32-byte groups XOR-swizzled by (r & 3).  One 4-byte load per K value, conflict-free across the warp.
+          const uint32_t base = sta + q * (Cfg::BK * 128) + (lane & 7) * 4;
+          const int gsel = lane >> 3;
 #pragma unroll
-            for (int rr = 0; rr < KH; ++rr) {
-              const int r = h * KH + rr;
-              float x;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(base + r * 128 + ((gsel ^ (r & 3)) << 5)));
-              hi[rr] = __float_as_uint(x); lo[rr] = __float_as_uint(low(x));
-            }
-          } else {
-            // K-major tile: row m at m*128 B with its eight 16-byte chunks XOR-swizzled by (m & 7)
-            const int r = q * 32 + lane;
-#pragma unroll
-            for (int jj = 0; jj < KH / 4; ++jj) {
-              const int j = h * (KH / 4) + jj;
-              float4 x;
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(st + r * 128 + ((j ^ (r & 7)) << 4)));
-              hi[4 * jj] = __float_as_uint(x.x); hi[4 * jj + 1] = __float_as_uint(x.y); hi[4 * jj + 2] = __float_as_uint(x.z); hi[4 * jj + 3] = __float_as_uint(x.w);
-              lo[4 * jj] = __float_as_uint(low(x.x)); lo[4 * jj + 1] = __float_as_uint(low(x.y)); lo[4 * jj + 2] = __float_as_uint(low(x.z)); lo[4 * jj + 3] = __float_as_uint(low(x.w));
-            }
+          for (int rr = 0; rr < KH; ++rr) {
+            const int r = hh * KH + rr;
+            float x;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(base + r * 128 + ((gsel ^ (r & 3)) << 5)));
+            hi[rr] = __float_as_uint(x); lo[rr] = __float_as_uint(low(x));
           }
-          const uint32_t a_tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ACC_COLS + s * Cfg::A_TMEM_COLS + h * KH);
-          static_assert(KH == 16, "tcgen05.st shape below is x16");
-          tmem_st16(a_tm, hi);
-          tmem_st16(a_tm + Cfg::BK, lo);
-          // B: the raw tile stays where TMA put it (= hi); the lo plane goes to the second buffer at the same swizzled
-          // offsets (elementwise, swizzle-oblivious); explicit ld/st.shared.  Issued between the TMEM stores and
-          // their wait so that the store latency is covered.
-          if (!(ep.dbg & 1)) {
+        } else {
+          // K-major tile: row m at m*128 B with its eight 16-byte chunks XOR-swizzled by (m & 7)
+          const int r = q * 32 + lane;
+#pragma unroll
+          for (int jj = 0; jj < KH / 4; ++jj) {
+            const int j = hh * (KH / 4) + jj;
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(sta + r * 128 + ((j ^ (r & 7)) << 4)));
+            hi[4 * jj] = __float_as_uint(x.x); hi[4 * jj + 1] = __float_as_uint(x.y); hi[4 * jj + 2] = __float_as_uint(x.z); hi[4 * jj + 3] = __float_as_uint(x.w);
+            lo[4 * jj] = __float_as_uint(low(x.x)); lo[4 * jj + 1] = __float_as_uint(low(x.y)); lo[4 * jj + 2] = __float_as_uint(low(x.z)); lo[4 * jj + 3] = __float_as_uint(low(x.w));
+          }
+        }
+        // tensor-memory slot sa was last read by the MMAs of k-block i - A_STAGES: they must have retired
+        if (i >= Cfg::A_STAGES) { const int j = i - Cfg::A_STAGES; mbar_wait(&empty_bar[j % Cfg::STAGES], (j / Cfg::STAGES) & 1); tc_fence_after(); }
+        const uint32_t a_tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(Cfg::ACC_COLS + sa * Cfg::A_TMEM_COLS + hh * KH);
+        static_assert(KH == 16 || KH == 8, "tcgen05.st shapes x16 / x8");
+        if (!(ep.dbg & 16)) {
+          tmem_stN<KH>(a_tm, hi);
+          tmem_stN<KH>(a_tm + Cfg::BK, lo);
+        }
+        // the raw A tile is in registers / on its way to tensor memory: hand its smem slot back to the producer
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_empty[sa])) : "memory");
+        // B: the raw tile stays where TMA put it (= hi); the lo plane goes to the second buffer at the same swizzled
+        // offsets (elementwise, swizzle-oblivious); explicit ld/st.shared.  Issued between the TMEM stores and
+        // their wait so that the store latency is covered.
+        mbar_wait(&full_bar[s], ph);
+        const uint32_t st = smem_u32(ring_b + s * Cfg::STAGE_BYTES);
+        if (!(ep.dbg & 1)) {
 #pragma unroll 4
-          for (int v = tw; v < Cfg::B_BYTES / 16; v += 32 * TC_WORKERS) {
+          for (int v = tw; v < Cfg::B_BYTES / 16; v += 32 * TC_GWARPS) {
             const uint32_t hi_a = st + Cfg::B_OFF + v * 16, lo_a = hi_a + Cfg::B_BYTES;
             float4 x;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(low(x.x)), "f"(low(x.y)), "f"(low(x.z)), "f"(low(x.w)) : "memory");
           }
-          }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-        } else {
-          // elementwise and position preserving, hence oblivious to the swizzle / major of the tile;
-          // explicit ld/st.shared (a generic pointer would go through the slow generic-address path)
-#pragma unroll 4
-          for (int v = tw; v < Cfg::TMA_BYTES / 16; v += 32 * TC_WORKERS) {
-            const int off = v * 16;
-            const uint32_t hi_a = off < Cfg::A_BYTES ? st + off : st + Cfg::A_BYTES + off;                // B tile starts after both A planes
-            const uint32_t lo_a = hi_a + (off < Cfg::A_BYTES ? Cfg::A_BYTES : Cfg::B_BYTES);
-            float4 x;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi_a));
-            const float4 hv = make_float4(rnd(x.x), rnd(x.y), rnd(x.z), rnd(x.w));
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi_a), "f"(hv.x), "f"(hv.y), "f"(hv.z), "f"(hv.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo_a), "f"(rnd(x.x - hv.x)), "f"(rnd(x.y - hv.y)), "f"(rnd(x.z - hv.z)), "f"(rnd(x.w - hv.w)) : "memory");
-          }
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");               // generic-proxy writes -> visible to tcgen05 (async proxy)
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_bar[s])) : "memory");
         if (tr && tw == 0) tr[i * 8 + 4] = clock64();
-        // promote one chunk behind the split front so the MMA thread never starves
-        if ((i % Cfg::CHUNK_KB) == Cfg::CHUNK_KB - 1 && i / Cfg::CHUNK_KB >= 1) { promote(next_promote); ++next_promote; }
+        // promote one chunk behind the split front so the MMA thread never starves (every warp of both groups takes part:
+        // group g reaches the end of a chunk at its last k-block of that chunk)
+        if ((i % Cfg::CHUNK_KB) >= Cfg::CHUNK_KB - TC_GROUPS && i / Cfg::CHUNK_KB >= 1) { promote(next_promote); ++next_promote; }
       }
     }
     for (; next_promote < num_chunks; ++next_promote) promote(next_promote);
@@ -419,7 +484,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
     // instruction covers 512 contiguous bytes of ONE row, with bias / ReLU / mask / accumulate applied on the way.
     {
       constexpr int LDS_ROW = BN + 4;                                                // floats; +4 keeps the 128-bit accesses conflict free
-      static_assert(4 * 32 * LDS_ROW * 4 <= Cfg::STAGES * Cfg::STAGE_BYTES, "epilogue staging must fit in the operand ring");
+      static_assert(4 * 32 * LDS_ROW * 4 <= Cfg::RING_BYTES, "epilogue staging must fit in the operand rings");
       const uint32_t wbase = smem_u32(smem) + (uint32_t)(q * 32 * LDS_ROW * 4);
 #pragma unroll
       for (int g = 0; g < HN / 4; ++g)
