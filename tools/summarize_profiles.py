@@ -53,6 +53,27 @@ def full():
               open(os.path.join(P, f"{tag}_dominant_kernel_traffic.json"), "w"), indent=1)
     return recs
 
+def attention():
+    rep = os.path.join(G, f"prof_{tag}_attn.ncu-rep")
+    if not os.path.exists(rep):
+        return []
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines())); hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
+    recs = [{w: (r[idx[w]] + " " + units[idx[w]]).strip() for w in want if w in idx} for r in rows[2:]]
+    json.dump({"command": "ncu --set full --clock-control none --import-source on -k regex:attn_ -c 3 python tools/attn_once.py",
+               "shape": "Sq=197 image tokens, Skv=85 metadata tokens, B=32, D=512, H=8 (hd=64), fp32", "kernels": recs},
+              open(os.path.join(P, f"{tag}_attention_ncu_summary.json"), "w"), indent=1)
+    return recs
+
+
 if __name__ == "__main__":
     tot, agg = launch_list(); print("launch list total", tot)
+    for r in attention(): print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum")})
     for r in full(): print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed")})
