@@ -13,8 +13,9 @@
 // one CTA per 16 keys produces dK and dV.
 //
 // Work split inside a CTA (4 warps, 4 rows each): score-like dot products run lanes-over-keys (each lane owns one
-// key of the tile and walks the head dimension; the tile rows are padded to hd + 1 words so the 32 lanes hit 32
-// banks), accumulations into a head-dim vector run lanes-over-d with the probability broadcast by shuffle.
+// key of the tile and walks the head dimension with 128-bit loads; the tile rows are padded so that the lanes spread
+// over all banks) for the warp's four rows at once - every tile element is loaded once and used four times;
+// accumulations into a head-dim vector run lanes-over-d with the probabilities broadcast by shuffle.
 // Everything is fp32 with expf/logf: the parity bar is 1e-5 against the float64 oracle.
 #pragma once
 #include "common.cuh"
@@ -37,16 +38,42 @@ struct AttnArgs {
   float scale;                                                          // 1 / sqrt(hd), applied to Q as PyTorch does
 };
 
-inline size_t attn_smem_bytes(int hd) { return (size_t)(2 * ATT_T * (hd + 1) + 2 * ATT_ROWS * hd + 2 * ATT_T) * sizeof(float); }
+// Row stride (words) of the streamed tiles.  Lanes-over-keys dot products read one tile row per lane: with hd a
+// multiple of 4 the rows are padded to hd + 4 words, so that 128-bit loads of eight consecutive lanes cover the 32
+// banks exactly once; otherwise hd + 1 and scalar loads.
+__host__ __device__ inline int attn_ldt(int hd) { return (hd % 4 == 0) ? hd + 4 : hd + 1; }
+inline size_t attn_smem_bytes(int hd) { return (size_t)(2 * ATT_T * attn_ldt(hd) + 2 * ATT_ROWS * hd + 2 * ATT_T) * sizeof(float); }
+
+// acc[r] += <rows[r], mine> for the warp's ATT_R rows at once: `mine` (this lane's tile row) is loaded ONCE per element
+// and used for all four rows; rows[] are warp-wide broadcasts.  Before this blocking every row re-read the tile and the
+// kernels were shared-memory bound (ncu r01: 66-77 % l1tex, 26 % FMA pipe).
+__device__ __forceinline__ void attn_dot_rows(const float* __restrict__ rows, int row_stride, const float* __restrict__ mine, int hd, float (&acc)[ATT_R]) {
+  if ((hd & 3) == 0) {
+    for (int d = 0; d < hd; d += 4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(mine + d);
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r) {
+        const float4 q4 = *reinterpret_cast<const float4*>(rows + r * row_stride + d);
+        acc[r] = fmaf(q4.x, k4.x, fmaf(q4.y, k4.y, fmaf(q4.z, k4.z, fmaf(q4.w, k4.w, acc[r]))));
+      }
+    }
+  } else {
+    for (int d = 0; d < hd; ++d) {
+      const float k = mine[d];
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r) acc[r] = fmaf(rows[r * row_stride + d], k, acc[r]);
+    }
+  }
+}
 
 // ---- forward ---------------------------------------------------------------------------------------------------
 template <int NDL>                    // ceil(hd / 32): head-dim elements per lane
 __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const AttnArgs a) {
   pdl_sync();
-  extern __shared__ float att_sm[];
-  const int hd = a.hd, ldt = hd + 1;
-  float* Ks = att_sm;                        // [T][hd+1]
-  float* Vs = Ks + ATT_T * ldt;              // [T][hd+1]
+  extern __shared__ __align__(16) float att_sm[];
+  const int hd = a.hd, ldt = attn_ldt(hd);
+  float* Ks = att_sm;                        // [T][ldt]
+  float* Vs = Ks + ATT_T * ldt;              // [T][ldt]
   float* qs = Vs + ATT_T * ldt;              // [ROWS][hd], pre-scaled
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_ROWS;
@@ -62,6 +89,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const AttnArgs
 #pragma unroll
     for (int n = 0; n < NDL; ++n) o[r][n] = 0.f;
   }
+  const float* qw = qs + warp * ATT_R * hd;  // this warp's ATT_R query rows (rows past Sq are zeros: computed, never stored)
   for (int k0 = 0; k0 < a.Sk; k0 += ATT_T) {
     __syncthreads();                         // previous tile fully consumed (first pass: qs visible)
     for (int idx = threadIdx.x; idx < ATT_T * hd; idx += ATT_WARPS * 32) {
@@ -75,29 +103,30 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const AttnArgs
     }
     __syncthreads();
     const int nk = min(ATT_T, a.Sk - k0);
+    float s[ATT_R], p[ATT_R];
+#pragma unroll
+    for (int r = 0; r < ATT_R; ++r) s[r] = 0.f;
+    attn_dot_rows(qw, hd, Ks + lane * ldt, hd, s);
 #pragma unroll
     for (int r = 0; r < ATT_R; ++r) {
-      const int i = q0 + warp * ATT_R + r;
-      if (i >= a.Sq) break;                  // warp-uniform
-      const float* q = qs + (warp * ATT_R + r) * hd;
-      const float* kr = Ks + lane * ldt;
-      float s = 0.f;
-      for (int d = 0; d < hd; ++d) s = fmaf(q[d], kr[d], s);
-      if (lane >= nk) s = -INFINITY;
-      const float mn = fmaxf(m[r], warp_max(s));
-      const float p = lane < nk ? expf(s - mn) : 0.f;
+      if (lane >= nk) s[r] = -INFINITY;
+      const float mn = fmaxf(m[r], warp_max(s[r]));
+      p[r] = lane < nk ? expf(s[r] - mn) : 0.f;
       const float corr = expf(m[r] - mn);    // exp(-inf) = 0 on the first tile
-      l[r] = l[r] * corr + warp_sum(p);
+      l[r] = l[r] * corr + warp_sum(p[r]);
       m[r] = mn;
 #pragma unroll
       for (int n = 0; n < NDL; ++n) o[r][n] *= corr;
-      for (int jj = 0; jj < nk; ++jj) {
-        const float pj = __shfl_sync(0xffffffffu, p, jj);
+    }
+    for (int jj = 0; jj < nk; ++jj) {
+      float v[NDL];
 #pragma unroll
-        for (int n = 0; n < NDL; ++n) {
-          const int d = lane + 32 * n;
-          if (d < hd) o[r][n] = fmaf(pj, Vs[jj * ldt + d], o[r][n]);
-        }
+      for (int n = 0; n < NDL; ++n) { const int d = lane + 32 * n; v[n] = d < hd ? Vs[jj * ldt + d] : 0.f; }
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r) {
+        const float pj = __shfl_sync(0xffffffffu, p[r], jj);
+#pragma unroll
+        for (int n = 0; n < NDL; ++n) o[r][n] = fmaf(pj, v[n], o[r][n]);
       }
     }
   }
@@ -119,10 +148,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const AttnArgs
 template <int NDL>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dq_kernel(const AttnArgs a) {
   pdl_sync();
-  extern __shared__ float att_sm[];
-  const int hd = a.hd, ldt = hd + 1;
-  float* Ks = att_sm;                        // [T][hd+1]
-  float* Vs = Ks + ATT_T * ldt;              // [T][hd+1]
+  extern __shared__ __align__(16) float att_sm[];
+  const int hd = a.hd, ldt = attn_ldt(hd);
+  float* Ks = att_sm;                        // [T][ldt]
+  float* Vs = Ks + ATT_T * ldt;              // [T][ldt]
   float* qs = Vs + ATT_T * ldt;              // [ROWS][hd], pre-scaled
   float* dos = qs + ATT_ROWS * hd;           // [ROWS][hd]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,6 +186,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dq_kernel(const AttnA
       if (lane == 0) a.delta[((int64_t)b * a.H + h) * a.Sq + i] = dl[r];
     }
   }
+  const float* qw = qs + warp * ATT_R * hd;
+  const float* gw = dos + warp * ATT_R * hd;
   for (int k0 = 0; k0 < a.Sk; k0 += ATT_T) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < ATT_T * hd; idx += ATT_WARPS * 32) {
@@ -170,27 +201,27 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dq_kernel(const AttnA
     }
     __syncthreads();
     const int nk = min(ATT_T, a.Sk - k0);
+    float s[ATT_R], dp[ATT_R], ds[ATT_R];
+#pragma unroll
+    for (int r = 0; r < ATT_R; ++r) { s[r] = 0.f; dp[r] = 0.f; }
+    attn_dot_rows(qw, hd, Ks + lane * ldt, hd, s);
+    attn_dot_rows(gw, hd, Vs + lane * ldt, hd, dp);
 #pragma unroll
     for (int r = 0; r < ATT_R; ++r) {
-      const int i = q0 + warp * ATT_R + r;
-      if (i >= a.Sq) break;
-      const float* q = qs + (warp * ATT_R + r) * hd;
-      const float* go = dos + (warp * ATT_R + r) * hd;
-      const float* kr = Ks + lane * ldt;
-      const float* vr = Vs + lane * ldt;
-      float s = 0.f, dp = 0.f;
-      for (int d = 0; d < hd; ++d) { s = fmaf(q[d], kr[d], s); dp = fmaf(go[d], vr[d], dp); }
-      const float p = lane < nk ? expf(s - lse[r]) : 0.f;
+      const float p = lane < nk ? expf(s[r] - lse[r]) : 0.f;
       // one key: P == 1 and dS == 0 EXACTLY (PyTorch: P * (dP - sum(dP * P)) = dP - dP), the fact behind the
       // exact-zero W_q / W_k gradients of the reference's S = 1 calls; dp and delta sum in different orders here
-      const float ds = a.Sk == 1 ? 0.f : p * (dp - dl[r]);
-      for (int jj = 0; jj < nk; ++jj) {
-        const float dsj = __shfl_sync(0xffffffffu, ds, jj);
+      ds[r] = a.Sk == 1 ? 0.f : p * (dp[r] - dl[r]);
+    }
+    for (int jj = 0; jj < nk; ++jj) {
+      float kk[NDL];
 #pragma unroll
-        for (int n = 0; n < NDL; ++n) {
-          const int d = lane + 32 * n;
-          if (d < hd) dq[r][n] = fmaf(dsj, Ks[jj * ldt + d], dq[r][n]);
-        }
+      for (int n = 0; n < NDL; ++n) { const int d = lane + 32 * n; kk[n] = d < hd ? Ks[jj * ldt + d] : 0.f; }
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r) {
+        const float dsj = __shfl_sync(0xffffffffu, ds[r], jj);
+#pragma unroll
+        for (int n = 0; n < NDL; ++n) dq[r][n] = fmaf(dsj, kk[n], dq[r][n]);
       }
     }
   }
@@ -210,10 +241,10 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dq_kernel(const AttnA
 template <int NDL>
 __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dkv_kernel(const AttnArgs a) {
   pdl_sync();
-  extern __shared__ float att_sm[];
-  const int hd = a.hd, ldt = hd + 1;
-  float* Qs = att_sm;                        // [T][hd+1], pre-scaled
-  float* dOs = Qs + ATT_T * ldt;             // [T][hd+1]
+  extern __shared__ __align__(16) float att_sm[];
+  const int hd = a.hd, ldt = attn_ldt(hd);
+  float* Qs = att_sm;                        // [T][ldt], pre-scaled
+  float* dOs = Qs + ATT_T * ldt;             // [T][ldt]
   float* ks = dOs + ATT_T * ldt;             // [ROWS][hd]
   float* vs = ks + ATT_ROWS * hd;            // [ROWS][hd]
   float* lse_s = vs + ATT_ROWS * hd;         // [T]
@@ -235,6 +266,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dkv_kernel(const Attn
   for (int r = 0; r < ATT_R; ++r)
 #pragma unroll
     for (int n = 0; n < NDL; ++n) { dk[r][n] = 0.f; dv[r][n] = 0.f; }
+  const float* kw = ks + warp * ATT_R * hd;  // this warp's ATT_R key rows (rows past Sk are zeros: computed, never stored)
+  const float* vw = vs + warp * ATT_R * hd;
   for (int i0 = 0; i0 < a.Sq; i0 += ATT_T) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < ATT_T * hd; idx += ATT_WARPS * 32) {
@@ -253,29 +286,29 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dkv_kernel(const Attn
     }
     __syncthreads();
     const int nq = min(ATT_T, a.Sq - i0);
+    float s[ATT_R], dp[ATT_R], p[ATT_R], ds[ATT_R];
+#pragma unroll
+    for (int r = 0; r < ATT_R; ++r) { s[r] = 0.f; dp[r] = 0.f; }
+    attn_dot_rows(kw, hd, Qs + lane * ldt, hd, s);        // lanes over queries
+    attn_dot_rows(vw, hd, dOs + lane * ldt, hd, dp);
 #pragma unroll
     for (int r = 0; r < ATT_R; ++r) {
-      const int j = j0 + warp * ATT_R + r;
-      if (j >= a.Sk) break;
-      const float* kj = ks + (warp * ATT_R + r) * hd;
-      const float* vj = vs + (warp * ATT_R + r) * hd;
-      const float* qr = Qs + lane * ldt;
-      const float* gr = dOs + lane * ldt;
-      float s = 0.f, dp = 0.f;
-      for (int d = 0; d < hd; ++d) { s = fmaf(qr[d], kj[d], s); dp = fmaf(gr[d], vj[d], dp); }
-      const float p = lane < nq ? expf(s - lse_s[lane]) : 0.f;
-      const float ds = a.Sk == 1 ? 0.f : p * (dp - dl_s[lane]);
-      for (int ii = 0; ii < nq; ++ii) {
-        const float pi = __shfl_sync(0xffffffffu, p, ii);
-        const float dsi = __shfl_sync(0xffffffffu, ds, ii);
+      p[r] = lane < nq ? expf(s[r] - lse_s[lane]) : 0.f;
+      ds[r] = a.Sk == 1 ? 0.f : p[r] * (dp[r] - dl_s[lane]);
+    }
+    for (int ii = 0; ii < nq; ++ii) {
+      float qi[NDL], gi[NDL];
 #pragma unroll
-        for (int n = 0; n < NDL; ++n) {
-          const int d = lane + 32 * n;
-          if (d < hd) {
-            dv[r][n] = fmaf(pi, dOs[ii * ldt + d], dv[r][n]);
-            dk[r][n] = fmaf(dsi, Qs[ii * ldt + d], dk[r][n]);
-          }
-        }
+      for (int n = 0; n < NDL; ++n) {
+        const int d = lane + 32 * n;
+        qi[n] = d < hd ? Qs[ii * ldt + d] : 0.f; gi[n] = d < hd ? dOs[ii * ldt + d] : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < ATT_R; ++r) {
+        const float pi = __shfl_sync(0xffffffffu, p[r], ii);
+        const float dsi = __shfl_sync(0xffffffffu, ds[r], ii);
+#pragma unroll
+        for (int n = 0; n < NDL; ++n) { dv[r][n] = fmaf(pi, gi[n], dv[r][n]); dk[r][n] = fmaf(dsi, qi[n], dk[r][n]); }
       }
     }
   }

@@ -70,9 +70,12 @@ struct Ctx {
   }
   const float* param(int slot, int64_t elem_off = 0) const { return (const float*)params[slot] + elem_off; }
   float* pgrad(int slot, int64_t elem_off = 0) const { return grads + p.goff[slot] + elem_off; }
-  void enable_fixup(GemmArgs& g) const {       // small-batch FFMA GEMMs: split K across CTAs, last slice fixes up
+  void enable_fixup(GemmArgs& g, int lane = 0) const {       // small-batch FFMA GEMMs: split K across CTAs, last slice fixes up
     if (p.splitk_bytes == 0 || g.M > 128) return;
-    g.partial = (float*)(ws + p.splitk_off); g.partial_bytes = p.splitk_bytes; g.counters = (unsigned*)(ws + p.counters_off);
+    // each lane owns half of the scratch and of the arrival counters: GEMMs of the two lanes run concurrently
+    const size_t half = p.splitk_bytes / 2;
+    g.partial = (float*)(ws + p.splitk_off + (size_t)lane * half); g.partial_bytes = half;
+    g.counters = (unsigned*)(ws + p.counters_off) + lane * 2048;
   }
   DropSpec drop(const Op& o) const {
     DropSpec s; s.mask = nullptr; s.seed = seed; s.offset = offset; s.state = rng_state; s.p = o.p; s.site = o.site; s.active = 0;
@@ -208,7 +211,7 @@ static int run_forward(Ctx& c) {
         g.A = c.value(o.in0); g.B = make_ref((void*)c.param(o.w_slot, (int64_t)o.w_row0 * o.in0.cols), o.in0.cols, FMT_F32);
         g.C = c.value(o.out); g.M = B; g.N = o.out.cols; g.K = o.in0.cols; g.a_kc = 1; g.b_kc = 1;
         g.bias = c.param(o.b_slot, o.w_row0); g.relu = o.relu; g.mask_src.p = nullptr; g.accumulate = 0; g.split_k = 1; g.colsum_a = nullptr;
-        c.enable_fixup(g);
+        c.enable_fixup(g, o.lane);
         CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
       } break;
       case OP_LNRD: {
@@ -353,7 +356,7 @@ static int run_backward(Ctx& c) {
           h.mask_src.p = nullptr;
           if (p.acts[o.in0.buf].relu_out) h.mask_src = c.value(o.in0);
           h.accumulate = is_written(o.dx_view); h.split_k = 1; h.colsum_a = nullptr;
-          c.enable_fixup(h);
+          c.enable_fixup(h, o.lane);
           CUDA_OK(launch_simt_gemm(h, c.dev.num_sms, c.st));
           set_written(o.dx_view);
         }

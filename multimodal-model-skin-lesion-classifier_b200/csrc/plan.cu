@@ -320,8 +320,8 @@ int build_plan(const fb200_desc& d, Plan& p) {
 
   // ---- lanes: the image chain and the metadata chain of a fusion string are independent until the concatenation
   //      (or the first op that reads both).  Ops whose inputs derive from the metadata input alone get lane 1; the
-  //      executor launches them on a side stream so that the two chains of 128-CTA GEMMs fill each other's idle SMs,
-  //      prologues and epilogues.  Only where it pays: tcgen05 path, batches of at least 512 rows.
+  //      executor launches them on a side stream: at large batches the two chains of 128-CTA GEMMs fill each other's
+  //      idle SMs and launch gaps, at small batches (launch-latency-bound kernels of a few CTAs) they simply run side by side.
   {
     std::vector<int> color(p.acts.size(), 0);          // bit 0: image input, bit 1: metadata input
     color[X] = 1; color[TIN] = 2;
@@ -334,7 +334,7 @@ int build_plan(const fb200_desc& d, Plan& p) {
       color[o.out.buf] |= c;
     }
     static const bool env_off = [] { const char* e = getenv("FB200_LANES"); return e && e[0] == '0'; }();   // A/B measurements
-    p.two_lanes = p.use_tc && d.B >= 512 && n1 > 0 && n1 < (int)p.ops.size() && !(d.flags & FB200_FLAG_ONE_STREAM) && !env_off;
+    p.two_lanes = n1 > 0 && n1 < (int)p.ops.size() && !(d.flags & FB200_FLAG_ONE_STREAM) && !env_off;
     if (!p.two_lanes) for (auto& o : p.ops) o.lane = 0;
   }
 
@@ -376,7 +376,7 @@ int build_plan(const fb200_desc& d, Plan& p) {
     if (o.kind == OP_META) { o.stats_off = cur; cur = align(cur + (size_t)d.B * 4 * sizeof(float)); }
   }
   // small batches on the FFMA path: split-K fix-up scratch (partial tiles) + per-tile arrival counters
-  if (!p.use_tc || d.B <= 128) { p.splitk_off = cur; p.splitk_bytes = (size_t)8 << 20; cur = align(cur + p.splitk_bytes); p.counters_off = cur; cur = align(cur + 4096 * sizeof(unsigned)); }
+  if (!p.use_tc || d.B <= 128) { p.splitk_off = cur; p.splitk_bytes = (size_t)16 << 20; cur = align(cur + p.splitk_bytes); p.counters_off = cur; cur = align(cur + 4096 * sizeof(unsigned)); }
   // tail: dlogits of the fused train step (exec.cu addresses it from the end)
   cur = align(cur + (size_t)d.B * d.C * sizeof(float));
   p.ws_bytes = cur + 256;

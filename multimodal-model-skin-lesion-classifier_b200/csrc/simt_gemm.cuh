@@ -309,7 +309,7 @@ inline cudaError_t launch_simt_gemm(GemmArgs g, int num_sms, cudaStream_t st) {
   int bm = big ? 128 : 64, bn = big ? 128 : 64;
   int tiles = ((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn);
   int split = 1;
-  if (g.partial && g.counters && tiles <= 4096) {
+  if (g.partial && g.counters && tiles <= 2048) {       // 2048 arrival counters per lane (exec.cu)
     // fix-up split-K (any epilogue): fill ~2 waves, keep >= 2 k-steps of 16 per slice
     int want = (2 * num_sms + tiles - 1) / tiles;
     int maxs = g.K / 32; if (maxs < 1) maxs = 1;

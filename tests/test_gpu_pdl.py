@@ -76,12 +76,14 @@ def test_fused_adam_bitwise_with_and_without_pdl():
 
 @pytest.mark.parametrize("mech", ["crossattention", "gfcam", "metablock", "att-intramodal+residual+cross-attention-metadados",
                                   "att-intramodal+residual+cross-attention-metadados+att-intramodal+residual", "rg-att"])
-def test_two_lane_execution_equals_one_stream(mech):
-    """Batches of >= 512 rows launch the metadata chain on an internal side stream (plan.cu: lanes, exec.cu: LaneSync).
+@pytest.mark.parametrize("B", [32, 640])
+def test_two_lane_execution_equals_one_stream(mech, B):
+    """The metadata chain is launched on an internal side stream (plan.cu: lanes, exec.cu: LaneSync) - FFMA path with
+    per-lane split-K scratch at B = 32, tcgen05 path at B = 640.
     Repeated steps must reproduce the single-stream result (FB200_FLAG_ONE_STREAM) - a missing cross-lane
     dependency shows up as a stale or half-written operand now and then."""
     dims = dict(F=512, V=85, C=6)
-    case = dict(cfg=dict(dims, mechanism=mech), B=640, seed=11, train=False, full_grads=False)
+    case = dict(cfg=dict(dims, mechanism=mech), B=B, seed=11, train=False, full_grads=False)
     cfg, one = build_model(case, "fp32", flags=_lib.FLAG_ONE_STREAM)
     _, two = build_model(case, "fp32")
     x, tin, y, cw, _ = case_inputs(cfg, case)
