@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--dtype", default=None, choices=[None, "fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"], help="GEMM engine policy (auto: tcgen05 from B > 128 in fp32, always in bf16)")
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"], help="GEMM engine policy (auto: tcgen05 from B > 32 in fp32, always in bf16)")
     ap.add_argument("--sweep", default="", help="comma-separated extra per-GPU batch sizes reported under 'sweep'")
     return ap.parse_args()
 

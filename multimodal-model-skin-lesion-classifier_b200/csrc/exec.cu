@@ -803,12 +803,12 @@ int mha_check(const fb200_mha_desc* d) {
   if (d->D % 4 != 0 || d->D / d->H > 256) return FB200_EUNSUPPORTED;
   return FB200_OK;
 }
-// fp32 GEMM on the engine that fits: tcgen05 3xTF32 once the row dimension exceeds 128 and the strides are TMA-legal, else FFMA
+// fp32 GEMM on the engine that fits: tcgen05 3xTF32 once the row dimension exceeds 32 and the strides are TMA-legal, else FFMA
 int gemm_auto(int layout, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
               const float* bias, int accumulate, void* stream) {
   const int rows = layout == 2 ? K : M;
   const bool aligned = !((((uintptr_t)A) | ((uintptr_t)B) | ((uintptr_t)C)) & 15) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0;
-  const int engine = (rows > 128 && aligned && tc_shape_ok(layout, M, N, K)) ? 1 : 0;
+  const int engine = (rows > 32 && aligned && tc_shape_ok(layout, M, N, K)) ? 1 : 0;
   return fb200_gemm(layout, engine, M, N, K, A, lda, B, ldb, C, ldc, bias, 0, accumulate, nullptr, 0, stream);
 }
 int colsum_rows(const float* const* xs, float* const* dsts, int n, int rows, int N, int num_sms, cudaStream_t st) {

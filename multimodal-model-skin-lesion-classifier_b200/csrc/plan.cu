@@ -192,9 +192,10 @@ int build_plan(const fb200_desc& d, Plan& p) {
       d.mechanism != FB200_RGATT2FUSEFEATURES && d.mechanism != FB200_RGATT_FULL_RGATT2FUSE && d.mechanism != FB200_RGATT_FULL_METABLOCK && d.n != 2) {
     p.error = "fusion strings that concatenate two modalities need n = 2"; return FB200_EBADARG;
   }
-  // engine policy: bf16 always rides the tensor cores; fp32 switches to the 3xTF32 tensor path once the
-  // batch exceeds 128 rows (measured crossover; below that the exact FFMA kernel with split-K fix-up wins)
-  p.use_tc = !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B > 128);
+  // engine policy: bf16 always rides the tensor cores; fp32 switches to the 3xTF32 tensor path above 32 rows (measured
+  // with the r01 kernels: 0.365 vs 0.371 ms per step at B=32, 0.374 vs 0.402 at 64, 0.391 vs 0.494 at 128; up to 32 rows
+  // the exact FFMA kernel with split-K fix-up costs the same and is bit-faithful fp32)
+  p.use_tc = !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B > 32);
   p.fmt = d.dtype == FB200_BF16 ? FMT_BF16 : FMT_F32;    // fp32-strict keeps everything fp32 in memory (hi/lo split happens in smem)
 
   Builder b(p);

@@ -33,7 +33,7 @@ def test_fp32_matches_reference_golden(name):
 
 @pytest.mark.parametrize("name", [n for n in sorted(CASES) if n.startswith("cfg") or n in ("small14_train", "small16_train", "small17_train", "edge_cross_B33")])
 def test_fp32_tensor_core_path_matches_reference_golden(name):
-    """Same fixtures through the tcgen05 3xTF32 GEMMs (FB200_FLAG_FORCE_TC; normally enabled from B > 128)."""
+    """Same fixtures through the tcgen05 3xTF32 GEMMs (FB200_FLAG_FORCE_TC; normally enabled from B > 32)."""
     case = CASES[name]
     cfg, model = build_model(case, "fp32", flags=_lib.FLAG_FORCE_TC)
     logits, loss, grads, dx = run_autograd(model, cfg, case)
