@@ -418,6 +418,18 @@ static int run_backward(Ctx& c) {
   }
   c.st = main_st;
   { int rc = ls.join(c); if (rc != FB200_OK) return rc; }
+  // Every dY is written now.  The bias gradients (HBM-bound column sums over all dY buffers) go to the side stream and run
+  // next to the grouped weight-gradient launch (tensor-bound) instead of after it.
+  { int rc = ls.begin(c, 0); if (rc != FB200_OK) return rc; }
+  c.st = c.lane_st[1];
+  for (size_t base = 0; base < colsums.size(); base += 24) {
+    ColsumBatch cb{}; cb.B = B; cb.nseg = 0;
+    for (size_t i = base; i < colsums.size() && cb.nseg < 24; ++i) cb.seg[cb.nseg++] = colsums[i];
+    int gx = (B + 63) / 64; if (gx > 8 * c.dev.num_sms / cb.nseg + 1) gx = 8 * c.dev.num_sms / cb.nseg + 1; if (gx < 1) gx = 1;   // ~64 rows per CTA
+    if (!c.gemm_only) pdl_launch(colsum_batch_kernel, dim3(gx, cb.nseg), 256, 0, c.st, cb);
+    CUDA_OK(cudaGetLastError());
+  }
+  c.st = main_st;
   // weight gradients of all tcgen05 Linears, grouped (round 1 only exists for weights applied twice)
   for (size_t round = 0; round < dw_round.size(); ++round) {
     for (size_t base = 0; base < dw_round[round].size(); base += TC_MAX_GROUP) {
@@ -426,14 +438,7 @@ static int run_backward(Ctx& c) {
       if (rc != FB200_OK) return rc;
     }
   }
-  // bias gradients of all tcgen05 Linears: the dY buffers are still intact in the workspace
-  for (size_t base = 0; base < colsums.size(); base += 24) {
-    ColsumBatch cb{}; cb.B = B; cb.nseg = 0;
-    for (size_t i = base; i < colsums.size() && cb.nseg < 24; ++i) cb.seg[cb.nseg++] = colsums[i];
-    int gx = (B + 63) / 64; if (gx > 8 * c.dev.num_sms / cb.nseg + 1) gx = 8 * c.dev.num_sms / cb.nseg + 1; if (gx < 1) gx = 1;   // ~64 rows per CTA
-    if (!c.gemm_only) pdl_launch(colsum_batch_kernel, dim3(gx, cb.nseg), 256, 0, c.st, cb);
-    CUDA_OK(cudaGetLastError());
-  }
+  { int rc = ls.join(c); if (rc != FB200_OK) return rc; }
   // inputs nobody differentiated through still owe the caller a defined gradient
   if (c.d_img && !gwritten[0]) CUDA_OK(cudaMemsetAsync(c.d_img, 0, (size_t)B * p.d.F * sizeof(float), c.st));
   if (c.d_txt && !gwritten[1]) CUDA_OK(cudaMemsetAsync(c.d_txt, 0, (size_t)B * p.acts[1].cols * sizeof(float), c.st));
