@@ -529,25 +529,38 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
             v.x = fmaxf(v.x + bv.x, floor_v); v.y = fmaxf(v.y + bv.y, floor_v); v.z = fmaxf(v.z + bv.z, floor_v); v.w = fmaxf(v.w + bv.w, floor_v);
             *(float4*)(cp + (int64_t)r * ep.C.ld) = v;
           }
-        } else {
-#pragma unroll 2
+        } else if (ep.atomic) {
           for (int r = r_begin; r < r_end; ++r) {
-            const int64_t row = row_base + r;
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rbase + (uint32_t)(r * LDS_ROW * 4)));
-            if (ep.atomic) {
-              float* c = (float*)ep.C.p + row * ep.C.ld + n;
-              atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
-              continue;
+            float* c = (float*)ep.C.p + (row_base + r) * ep.C.ld + n;
+            atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
+          }
+        } else {
+          // any output format, ReLU-backward mask, accumulate-into-gradient: four rows per trip, every global load of the
+          // trip issued before the first use (the flags are warp-uniform: predicated, no divergence)
+          const float floor_v = ep.relu ? 0.f : -INFINITY;
+          const bool has_mask = ep.mask_src.p != nullptr, acc_c = ep.accumulate != 0;
+          for (int r = r_begin; r < r_end; r += 4) {
+            float4 v[4], mk[4], o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const bool ok = r + u < r_end;
+              const int64_t row = row_base + (ok ? r + u : r);
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(rbase + (uint32_t)((ok ? r + u : r) * LDS_ROW * 4)));
+              mk[u] = has_mask ? ld4(ep.mask_src, row, n) : make_float4(1.f, 1.f, 1.f, 1.f);
+              o[u] = acc_c ? ld4(ep.C, row, n) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (ep.mask_src.p) {
-              const float4 mk = ld4(ep.mask_src, row, n);
-              v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (r + u >= r_end) break;
+              float4 w;
+              w.x = fmaxf(v[u].x + bv.x, floor_v); w.y = fmaxf(v[u].y + bv.y, floor_v);
+              w.z = fmaxf(v[u].z + bv.z, floor_v); w.w = fmaxf(v[u].w + bv.w, floor_v);
+              w.x = (mk[u].x > 0.f ? w.x : 0.f) + o[u].x; w.y = (mk[u].y > 0.f ? w.y : 0.f) + o[u].y;
+              w.z = (mk[u].z > 0.f ? w.z : 0.f) + o[u].z; w.w = (mk[u].w > 0.f ? w.w : 0.f) + o[u].w;
+              st4(ep.C, row_base + r + u, n, w);
             }
-            if (ep.accumulate) { const float4 o = ld4(ep.C, row, n); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            st4(ep.C, row, n, v);
           }
         }
       }
