@@ -206,10 +206,25 @@ def main():
         denoms = [None] * nb
         if world > 1:                                            # global weighted-CE denominator, static buffers
             denoms = [torch.zeros(1, device=dev) for _ in range(nb)]
+        # data parallel: the gradient all-reduce (optionally in two buckets, the first one under the second half of the
+        # weight-gradient launch: fb200_head_train_step_dp records `mids[j]` when the first bucket is final)
+        mids = [None] * nb
+        bar = None
+        if world > 1:
+            # Overlapping bucket 1 with the second half of the weight gradients (fb200_head_train_step_dp) measured SLOWER
+            # here (2 GPUs: 0.905 vs 0.871 ms per step): NCCL's CTAs push the 136-tile launch into a second wave.
+            # Default: one in-place all-reduce of the gradient span behind the step; FB200_DP_OVERLAP=1 for the overlapped path.
+            if os.environ.get("FB200_DP_OVERLAP", "0") == "1":
+                mids = [torch.cuda.Event() for _ in range(nb)]
+                for ev in mids:
+                    ev.record()
+            bar = fb.dp.BucketedAllReduce(dev)
+        split = _lib.dp_bucket_split(fb.make_desc(mech, Bsz, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype, train=True,
+                                                  flags={"auto": 0, "simt": 4, "tc": 8}[args.engine])) if world > 1 else 0
         graphs = []
         if use_graph:
             for j in range(nb):
-                graphs.append(fb.GraphedTrainStep(model, xs[j], ts[j], ys[j], cw, denom=denoms[j]))
+                graphs.append(fb.GraphedTrainStep(model, xs[j], ts[j], ys[j], cw, denom=denoms[j], mid_event=mids[j]))
 
         # The global weighted-CE denominator of a batch only needs its labels, which the loader has one step ahead:
         # it is all-reduced on a side stream while the previous step computes (dp.DenominatorPrefetcher).
@@ -221,17 +236,18 @@ def main():
                 if i == 0:
                     pref.issue(j, ys[j], cw, denoms[j])
                 pref.wait(j)
+                jn = (i + 1) % nb
+                pref.issue(jn, ys[jn], cw, denoms[jn])              # next batch's denominator: its tiny all-reduce rides under this step
             if use_graph:
                 loss = graphs[j].run()
                 flat = graphs[j].flat_grad
             else:
-                loss, _ = model.forward_loss(xs[j], ts[j], ys[j], cw, denom=denoms[j])
+                loss, _ = model.forward_loss(xs[j], ts[j], ys[j], cw, denom=denoms[j], mid_event=mids[j])
                 flat = model.flat_grad
             if world > 1:
+                bar.start(flat, live_ranges, split, mids[j])       # bucket 1 on the communication stream, under the tail of the step
                 pref.mark_consumed(j)
-                jn = (i + 1) % nb
-                pref.issue(jn, ys[jn], cw, denoms[jn])
-                fb.dp.allreduce_gradients(flat, ranges=live_ranges)   # SUM: the global denominator already averages; only live slices travel
+                bar.finish(flat)                                    # bucket 2 (SUM: the global denominator already averages; only live slices travel)
             return loss
 
         for i in range(warm):
@@ -283,9 +299,15 @@ def main():
 
         use_graph = not args.no_graph
         live_ranges2 = _lib.grad_live_ranges(fb.make_desc(mech, Bsz, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype))
+        bar2 = fb.dp.BucketedAllReduce(dev) if world > 1 else None
+        split2 = _lib.dp_bucket_split(fb.make_desc(mech, Bsz, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype, train=True,
+                                                   flags={"auto": 0, "simt": 4, "tc": 8}[args.engine])) if world > 1 else 0
         for s in slots:
             s["denom"] = torch.zeros(1, device=dev) if world > 1 else None
-            s["graph"] = fb.GraphedTrainStep(m2, s["x"], s["t"], s["y"], cw, denom=s["denom"]) if use_graph else None
+            s["mid"] = None
+            if world > 1:
+                s["mid"] = torch.cuda.Event(); s["mid"].record()
+            s["graph"] = fb.GraphedTrainStep(m2, s["x"], s["t"], s["y"], cw, denom=s["denom"], mid_event=s["mid"]) if use_graph else None
 
         def run(n, base):
             cur = torch.cuda.current_stream()
@@ -300,9 +322,10 @@ def main():
                 if use_graph:
                     loss = s["graph"].run(); flat = s["graph"].flat_grad
                 else:
-                    loss, _ = m2.forward_loss(s["x"], s["t"], s["y"], cw, denom=s["denom"]); flat = m2.flat_grad
+                    loss, _ = m2.forward_loss(s["x"], s["t"], s["y"], cw, denom=s["denom"], mid_event=s["mid"]); flat = m2.flat_grad
                 if world > 1:
-                    fb.dp.allreduce_gradients(flat, ranges=live_ranges2)
+                    bar2.start(flat, live_ranges2, split2, s["mid"])
+                    bar2.finish(flat)
                 host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)       # D2H read of the step's result
                 s["free"].record(cur)
         for s in slots:

@@ -197,6 +197,20 @@ int fb200_head_train_step(const fb200_desc* d, const void* const* params,
                           void* logits, float* loss_out, void* grads,
                           void* d_img_feat, void* d_text_in, void* ws, void* stream);
 
+/* Data-parallel variant of fb200_head_train_step (the head's gradients are all-reduced after every step).
+ * Every gradient whose offset in the flat buffer is below fb200_dp_bucket_split(d) is final when `mid_event`
+ * (a cudaEvent_t; recorded on `stream`, as an external event-record node when the stream is being captured) fires;
+ * the tcgen05 weight gradients above the split are launched after it.  The caller waits for the event on its
+ * communication stream and all-reduces the first bucket while the second half of the weight gradients is computed.
+ * mid_event = NULL: identical to fb200_head_train_step.  fb200_dp_bucket_split: 0 when the configuration has nothing to
+ * split (FFMA path, weights applied twice) - the event then fires at the end of the step. */
+int fb200_head_train_step_dp(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
+                             const int64_t* labels, const float* class_w, const float* denom,
+                             const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
+                             void* logits, float* loss_out, void* grads, void* d_img_feat, void* d_text_in, void* ws, void* stream,
+                             void* mid_event);
+int64_t fb200_dp_bucket_split(const fb200_desc* d);
+
 /* The other losses the reference's loops use, forward + dlogits in one launch, mean reduction folded in:
  * kind 1 = FocalLoss(alpha, gamma) (models/focalLoss.py:6-26; targets = int64 labels [B], weight = alpha [C] or NULL)
  * kind 2 = SoftTargetCrossEntropy(weight) (models/softtargetsCrossEntropy.py:5-22; targets = fp32 soft labels [B,C]).

@@ -53,6 +53,7 @@ struct Ctx {
   bool gemm_only = false;     // debug replay: launch only the GEMM kernels of the step (bench.py times them with CUDA events)
   // two-lane execution (Plan::two_lanes): lane 0 = the caller's stream, lane 1 = a side stream for the metadata chain
   cudaStream_t lane_st[2] = {nullptr, nullptr};
+  void* mid_event = nullptr;  // fb200_head_train_step_dp: recorded once every gradient below Plan::dp_split is final
 
   TRef value(const View& v) const {
     const Act& a = p.acts[v.buf];
@@ -430,15 +431,37 @@ static int run_backward(Ctx& c) {
     CUDA_OK(cudaGetLastError());
   }
   c.st = main_st;
-  // weight gradients of all tcgen05 Linears, grouped (round 1 only exists for weights applied twice)
-  for (size_t round = 0; round < dw_round.size(); ++round) {
-    for (size_t base = 0; base < dw_round[round].size(); base += TC_MAX_GROUP) {
-      const int n = (int)std::min<size_t>(TC_MAX_GROUP, dw_round[round].size() - base);
-      int rc = launch_tc_grouped_tn(p.fmt == FMT_BF16 ? 0 : 1, dw_round[round].data() + base, n, B, c.st);
+  // weight gradients of all tcgen05 Linears, grouped (round 1 only exists for weights applied twice).  With a data-parallel
+  // caller's event: first the problems below Plan::dp_split, then the event (every gradient below the split is final: the
+  // row kernels and the column sums are done), then the rest - the caller all-reduces the first bucket under the second half.
+  auto launch_dw = [&](const std::vector<TcGroupProblem>& v) -> int {
+    for (size_t base = 0; base < v.size(); base += TC_MAX_GROUP) {
+      const int n = (int)std::min<size_t>(TC_MAX_GROUP, v.size() - base);
+      int rc = launch_tc_grouped_tn(p.fmt == FMT_BF16 ? 0 : 1, v.data() + base, n, B, c.st);
       if (rc != FB200_OK) return rc;
     }
+    return FB200_OK;
+  };
+  auto record_mid = [&]() -> int {
+    if (!c.mid_event) return FB200_OK;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_OK(cudaStreamIsCapturing(c.st, &cap));
+    CUDA_OK(cudaEventRecordWithFlags((cudaEvent_t)c.mid_event, c.st, cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    return FB200_OK;
+  };
+  const bool split = c.mid_event && p.dp_split > 0 && dw_round.size() == 1;
+  if (split) {
+    std::vector<TcGroupProblem> first, second;
+    for (auto& gp : dw_round[0]) ((gp.C - c.grads) < p.dp_split ? first : second).push_back(gp);
+    { int rc = launch_dw(first); if (rc != FB200_OK) return rc; }
+    { int rc = ls.join(c); if (rc != FB200_OK) return rc; }
+    { int rc = record_mid(); if (rc != FB200_OK) return rc; }
+    { int rc = launch_dw(second); if (rc != FB200_OK) return rc; }
+  } else {
+    for (size_t round = 0; round < dw_round.size(); ++round) { int rc = launch_dw(dw_round[round]); if (rc != FB200_OK) return rc; }
+    { int rc = ls.join(c); if (rc != FB200_OK) return rc; }
+    { int rc = record_mid(); if (rc != FB200_OK) return rc; }
   }
-  { int rc = ls.join(c); if (rc != FB200_OK) return rc; }
   // inputs nobody differentiated through still owe the caller a defined gradient
   if (c.d_img && !gwritten[0]) CUDA_OK(cudaMemsetAsync(c.d_img, 0, (size_t)B * p.d.F * sizeof(float), c.st));
   if (c.d_txt && !gwritten[1]) CUDA_OK(cudaMemsetAsync(c.d_txt, 0, (size_t)B * p.acts[1].cols * sizeof(float), c.st));
@@ -738,6 +761,21 @@ int fb200_head_train_step(const fb200_desc* d, const void* const* params, const 
                           const int64_t* labels, const float* class_w, const float* denom,
                           const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
                           void* logits, float* loss_out, void* grads, void* d_img_feat, void* d_text_in, void* ws, void* stream) {
+  return fb200_head_train_step_dp(d, params, img_feat, text_in, labels, class_w, denom, masks, seed, offset, rng_state,
+                                  logits, loss_out, grads, d_img_feat, d_text_in, ws, stream, nullptr);
+}
+
+int64_t fb200_dp_bucket_split(const fb200_desc* d) {
+  if (!d) return -1;
+  Plan p; if (build_plan(*d, p) != FB200_OK) return -1;
+  return p.dp_split;
+}
+
+int fb200_head_train_step_dp(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
+                             const int64_t* labels, const float* class_w, const float* denom,
+                             const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
+                             void* logits, float* loss_out, void* grads, void* d_img_feat, void* d_text_in, void* ws, void* stream,
+                             void* mid_event) {
   Plan plan; DeviceInfo dev;
   int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
   if (rc != FB200_OK) return rc;
@@ -750,6 +788,7 @@ int fb200_head_train_step(const fb200_desc* d, const void* const* params, const 
   Ctx c{plan, params, img_feat, text_in, logits, dlog,
         (d->flags & FB200_FLAG_NEED_DIMG) ? d_img_feat : nullptr, (d->flags & FB200_FLAG_NEED_DTEXT) ? d_text_in : nullptr,
         (float*)grads, masks, seed, offset, (const uint64_t*)rng_state, w, (cudaStream_t)stream, dev};
+  c.mid_event = mid_event;
   rc = run_forward(c);
   if (rc != FB200_OK) return rc;
   rc = ce_launch(logits, labels, class_w, denom, d->B, d->C, loss_out, dlog, c.st);

@@ -2,6 +2,7 @@
 #include "plan.h"
 #include <cstring>
 #include <cstdlib>
+#include <algorithm>
 
 namespace fb200 {
 
@@ -351,6 +352,30 @@ int build_plan(const fb200_desc& d, Plan& p) {
     off += (n + 3) & ~int64_t(3);                      // keep every gradient 16-byte aligned
   }
   p.grad_elems = off;
+
+  // ---- data-parallel bucket split (fb200_head_train_step_dp): the weight gradients of the tcgen05 Linears are all produced by
+  //      the grouped launch that ends the backward pass.  Split them by offset into two halves of about equal tile count:
+  //      the caller all-reduces everything below dp_split while the second half is still being computed.
+  {
+    struct W { int64_t off; int tiles; };
+    std::vector<W> ws;
+    bool twice = false;
+    for (auto& o : p.ops) if (o.kind == OP_LINEAR && o.engine == 1) {
+      const int64_t off = p.goff[o.w_slot] + (int64_t)o.w_row0 * o.in0.cols;
+      for (auto& w : ws) if (w.off == off) twice = true;
+      ws.push_back(W{off, ((o.out.cols + 127) / 128) * ((o.in0.cols + 127) / 128)});
+    }
+    p.dp_split = 0;
+    if (!twice && ws.size() >= 2) {
+      std::sort(ws.begin(), ws.end(), [](const W& a, const W& b) { return a.off < b.off; });
+      int total = 0; for (auto& w : ws) total += w.tiles;
+      int acc = 0;
+      for (size_t i = 0; i + 1 < ws.size(); ++i) {
+        acc += ws[i].tiles;
+        if (2 * acc >= total) { p.dp_split = ws[i + 1].off; break; }
+      }
+    }
+  }
 
   // ---- per-buffer storage format: only GEMM operands pay for the operand format (bf16 / tf32 pair);
   //      everything the row kernels exchange among themselves stays fp32

@@ -82,6 +82,8 @@ struct Plan {
   bool live[NUM_SLOTS] = {};
   int64_t goff[NUM_SLOTS];           // element offset in the flat gradient buffer, -1 if not live
   int64_t grad_elems = 0;
+  int64_t dp_split = 0;              // element offset in the flat gradient buffer: tcgen05 weight gradients below it are launched
+                                     // first (then fb200_head_train_step_dp records its event), the others after; 0 = no split
   size_t ws_bytes = 0;
   size_t splitk_off = 0, splitk_bytes = 0, counters_off = 0;   // FFMA split-K fix-up scratch (small batches)
   float drop_p[FB200_NUM_DROPOUT_SITES] = {};

@@ -91,6 +91,8 @@ def lib():
     sig("fb200_head_backward", i32, dp, pp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp)
     sig("fb200_cross_entropy", i32, vp, vp, vp, vp, i32, i32, vp, vp, vp)
     sig("fb200_head_train_step", i32, dp, pp, vp, vp, vp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp)
+    sig("fb200_head_train_step_dp", i32, dp, pp, vp, vp, vp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp)
+    sig("fb200_dp_bucket_split", i64, dp)
     f32 = C.c_float
     sig("fb200_gemm", i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, vp, sz, vp)
     sig("fb200_gemm_workspace_bytes", i32, i32, i32, i32, i32, i32, C.POINTER(sz))
@@ -194,6 +196,15 @@ def dropout_sites(desc: Desc):
 
 
 _ranges_cache = {}
+
+
+def dp_bucket_split(desc: Desc):
+    """Element offset in the flat gradient buffer below which every gradient is final when the mid-step event of
+    fb200_head_train_step_dp fires (0: nothing to split)."""
+    v = lib().fb200_dp_bucket_split(C.byref(desc))
+    if v < 0:
+        raise Fb200Error(-1, "fb200_dp_bucket_split")
+    return int(v)
 
 
 def grad_live_ranges(desc: Desc):

@@ -146,13 +146,16 @@ class MultimodalModel(nn.Module):
                                        *self._params_in_slot_order())
 
     # ------------------------------------------------------------------ fused train step (opt-in)
-    def forward_loss(self, image, text_metadata, label, class_weights=None, denom=None, zero_grad=True):
+    def forward_loss(self, image, text_metadata, label, class_weights=None, denom=None, zero_grad=True, mid_event=None):
         """forward + weighted CE + backward of the head in ONE library call.
 
         Writes ``.grad`` of every live head parameter (views of one flat buffer, summed into
         existing grads unless ``zero_grad``), back-propagates into the backbone when it has
         trainable parameters, and returns (loss, logits) as device tensors without syncing.
-        ``denom``: device scalar with the global sum of class weights (data parallel runs)."""
+        ``denom``: device scalar with the global sum of class weights (data parallel runs).
+        ``mid_event``: a recorded-once ``torch.cuda.Event``; the library records it as soon as every gradient below
+        ``_lib.dp_bucket_split(desc)`` in ``flat_grad`` is final (fb200_head_train_step_dp) - dp.BucketedAllReduce
+        all-reduces that bucket while the remaining weight gradients are still being computed."""
         L = _lib.lib()
         img_feat, text_in = self._encode(image, text_metadata)
         train = bool(self.training)
@@ -183,9 +186,10 @@ class MultimodalModel(nn.Module):
             # Philox key lives on the device so that a captured CUDA graph draws new masks on every replay
             self._rng_state = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 1], dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(L.fb200_head_train_step(C.byref(desc), table.arr, _ptr(x), _ptr(t), _ptr(y), _ptr(w), _ptr(denom), marr,
-                                               0, 0, _ptr(self._rng_state),
-                                               _ptr(logits), _ptr(loss_out), _ptr(flat), _ptr(d_img), _ptr(d_txt), _ptr(ws), _stream()),
+            ev = C.c_void_p(mid_event.cuda_event) if mid_event is not None else C.c_void_p(0)
+            _lib.check(L.fb200_head_train_step_dp(C.byref(desc), table.arr, _ptr(x), _ptr(t), _ptr(y), _ptr(w), _ptr(denom), marr,
+                                                  0, 0, _ptr(self._rng_state),
+                                                  _ptr(logits), _ptr(loss_out), _ptr(flat), _ptr(d_img), _ptr(d_txt), _ptr(ws), _stream(), ev),
                        "fb200_head_train_step")
             if train:
                 _lib.check(L.fb200_rng_advance(_ptr(self._rng_state), 1, _stream()), "fb200_rng_advance")
@@ -198,6 +202,7 @@ class MultimodalModel(nn.Module):
             else:
                 p.grad = p.grad + g
         self.flat_grad = flat                # one contiguous bucket for the DP all-reduce
+        self.last_desc = desc
         if need_dimg:
             img_feat.backward(d_img)
         if need_dtxt:
@@ -216,10 +221,11 @@ class GraphedTrainStep:
         x.copy_(next_x); ...; step.run(); optimizer.step()
     """
 
-    def __init__(self, model, image, text_metadata, label, class_weights=None, denom=None, warmup=2):
+    def __init__(self, model, image, text_metadata, label, class_weights=None, denom=None, warmup=2, mid_event=None):
         if any(p.requires_grad for p in model.image_encoder.parameters()):
             raise ValueError("GraphedTrainStep captures the head only: use a frozen backbone (or feed features)")
-        self.model, self.args = model, (image, text_metadata, label, class_weights, denom)
+        self.model, self.args = model, (image, text_metadata, label, class_weights, denom, True, mid_event)
+        self.mid_event = mid_event
         side = torch.cuda.Stream(device=image.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -230,6 +236,7 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss, self.logits = model.forward_loss(*self.args)
         self.flat_grad = model.flat_grad
+        self.desc = model.last_desc
 
     def run(self):
         self.graph.replay()

@@ -83,3 +83,13 @@ def test_shard_rows_cover_the_batch():
             spans = [dp.shard_rows(B, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == B
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_bucket_split_of_live_ranges():
+    from fusion_b200.dp import BucketedAllReduce
+    ranges = [(0, 100), (150, 300), (300, 420)]
+    lo, hi = BucketedAllReduce.split_ranges(ranges, 200)
+    assert lo == [(0, 100), (150, 200)] and hi == [(200, 300), (300, 420)]
+    lo, hi = BucketedAllReduce.split_ranges(ranges, 150)
+    assert lo == [(0, 100)] and hi == [(150, 300), (300, 420)]
+    assert sum(e - b for b, e in lo) + sum(e - b for b, e in hi) == sum(e - b for b, e in ranges)

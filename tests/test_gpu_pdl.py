@@ -97,3 +97,38 @@ def test_two_lane_execution_equals_one_stream(mech, B):
             for k in g_ref:
                 dev = float((g[k] - g_ref[k]).abs().max() / g_ref[k].abs().max().clamp_min(1e-30))
                 assert dev < 1e-5, (k, dev)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_dp_mid_event_marks_first_bucket_final(graph):
+    """fb200_head_train_step_dp: when the mid-step event fires, every gradient below the bucket split already has its final
+    value (a communication stream that waits for the event alone may all-reduce it), and the step as a whole is unchanged."""
+    dims = dict(F=2048, V=85, C=6)
+    case = dict(cfg=dict(dims, mechanism="crossattention"), B=1024, seed=3, train=False, full_grads=False)
+    cfg, model = build_model(case, "fp32")
+    x, tin, y, cw, _ = case_inputs(cfg, case)
+    model.eval()
+    l_ref, _ = model.forward_loss(x, tin, y, cw)
+    ref = model.flat_grad.clone()
+    split = _lib.dp_bucket_split(model.last_desc)
+    total = ref.numel()
+    assert 0 < split < total
+    lo, hi = fb.dp.BucketedAllReduce.split_ranges(_lib.grad_live_ranges(model.last_desc), split)
+    assert lo and hi and all(e <= split for _, e in lo) and all(b >= split for b, _ in hi)
+    mid = torch.cuda.Event(); mid.record()
+    side = torch.cuda.Stream()
+    snap = torch.empty(split, device="cuda")
+    for _ in range(5):
+        if graph:
+            step = fb.GraphedTrainStep(model, x, tin, y, cw, warmup=1, mid_event=mid)
+            step.flat_grad.zero_()
+            step.run(); flat = step.flat_grad
+        else:
+            model.forward_loss(x, tin, y, cw, mid_event=mid); flat = model.flat_grad
+        side.wait_event(mid)                                  # NOT the end of the step
+        with torch.cuda.stream(side):
+            snap.copy_(flat[:split])
+        torch.cuda.synchronize()
+        dev = float((snap - ref[:split]).abs().max() / ref[:split].abs().max())
+        assert dev < 1e-5, dev
+        assert float((flat - ref).abs().max() / ref.abs().max()) < 1e-5
