@@ -66,6 +66,29 @@ __device__ __forceinline__ void attn_dot_rows(const float* __restrict__ rows, in
   }
 }
 
+
+// Cooperative load of up to `nrows` rows (row index s0 + j < S, else zeros) of head h into shared memory, row stride `lds`
+// words, optionally scaled: 128-bit global loads and shared stores when hd is a multiple of 4 (the views are 16-byte
+// aligned: D % 4 == 0, hd % 4 == 0), scalar otherwise.
+__device__ __forceinline__ void attn_load_rows(float* __restrict__ dst, int lds, const float* __restrict__ src, int ld, int B, int b, int col0,
+                                               int s0, int S, int nrows, int hd, float scale) {
+  if ((hd & 3) == 0 && (ld & 3) == 0 && (lds & 3) == 0) {
+    const int g = hd >> 2;
+    for (int idx = threadIdx.x; idx < nrows * g; idx += ATT_WARPS * 32) {
+      const int j = idx / g, d = (idx - j * g) << 2, sidx = s0 + j;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sidx < S) v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)sidx * B + b) * ld + col0 + d));
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+      *reinterpret_cast<float4*>(dst + j * lds + d) = v;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < nrows * hd; idx += ATT_WARPS * 32) {
+      const int j = idx / hd, d = idx - j * hd, sidx = s0 + j;
+      dst[j * lds + d] = sidx < S ? __ldg(src + ((int64_t)sidx * B + b) * ld + col0 + d) * scale : 0.f;
+    }
+  }
+}
+
 // ---- forward ---------------------------------------------------------------------------------------------------
 template <int NDL>                    // ceil(hd / 32): head-dim elements per lane
 __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const AttnArgs a) {
@@ -78,10 +101,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const AttnArgs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_ROWS;
   const int col0 = h * hd;
-  for (int idx = threadIdx.x; idx < ATT_ROWS * hd; idx += ATT_WARPS * 32) {
-    const int r = idx / hd, d = idx - r * hd, i = q0 + r;
-    qs[idx] = i < a.Sq ? __ldg(a.Q + ((int64_t)i * a.B + b) * a.ldq + col0 + d) * a.scale : 0.f;
-  }
+  attn_load_rows(qs, hd, a.Q, a.ldq, a.B, b, col0, q0, a.Sq, ATT_ROWS, hd, a.scale);
   float m[ATT_R], l[ATT_R], o[ATT_R][NDL];
 #pragma unroll
   for (int r = 0; r < ATT_R; ++r) {
@@ -92,15 +112,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_fwd_kernel(const AttnArgs
   const float* qw = qs + warp * ATT_R * hd;  // this warp's ATT_R query rows (rows past Sq are zeros: computed, never stored)
   for (int k0 = 0; k0 < a.Sk; k0 += ATT_T) {
     __syncthreads();                         // previous tile fully consumed (first pass: qs visible)
-    for (int idx = threadIdx.x; idx < ATT_T * hd; idx += ATT_WARPS * 32) {
-      const int j = idx / hd, d = idx - j * hd, kk = k0 + j;
-      float kv = 0.f, vv = 0.f;
-      if (kk < a.Sk) {
-        kv = __ldg(a.K + ((int64_t)kk * a.B + b) * a.ldk + col0 + d);
-        vv = __ldg(a.V + ((int64_t)kk * a.B + b) * a.ldv + col0 + d);
-      }
-      Ks[j * ldt + d] = kv; Vs[j * ldt + d] = vv;
-    }
+    attn_load_rows(Ks, ldt, a.K, a.ldk, a.B, b, col0, k0, a.Sk, ATT_T, hd, 1.f);
+    attn_load_rows(Vs, ldt, a.V, a.ldv, a.B, b, col0, k0, a.Sk, ATT_T, hd, 1.f);
     __syncthreads();
     const int nk = min(ATT_T, a.Sk - k0);
     float s[ATT_R], p[ATT_R];
@@ -157,15 +170,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dq_kernel(const AttnA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_ROWS;
   const int col0 = h * hd;
-  for (int idx = threadIdx.x; idx < ATT_ROWS * hd; idx += ATT_WARPS * 32) {
-    const int r = idx / hd, d = idx - r * hd, i = q0 + r;
-    float qv = 0.f, dv = 0.f;
-    if (i < a.Sq) {
-      qv = __ldg(a.Q + ((int64_t)i * a.B + b) * a.ldq + col0 + d) * a.scale;
-      dv = __ldg(a.dO + ((int64_t)i * a.B + b) * a.lddo + col0 + d);
-    }
-    qs[idx] = qv; dos[idx] = dv;
-  }
+  attn_load_rows(qs, hd, a.Q, a.ldq, a.B, b, col0, q0, a.Sq, ATT_ROWS, hd, a.scale);
+  attn_load_rows(dos, hd, a.dO, a.lddo, a.B, b, col0, q0, a.Sq, ATT_ROWS, hd, 1.f);
   __syncthreads();
   float lse[ATT_R], dl[ATT_R], dq[ATT_R][NDL];
 #pragma unroll
@@ -190,15 +196,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dq_kernel(const AttnA
   const float* gw = dos + warp * ATT_R * hd;
   for (int k0 = 0; k0 < a.Sk; k0 += ATT_T) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < ATT_T * hd; idx += ATT_WARPS * 32) {
-      const int j = idx / hd, d = idx - j * hd, kk = k0 + j;
-      float kv = 0.f, vv = 0.f;
-      if (kk < a.Sk) {
-        kv = __ldg(a.K + ((int64_t)kk * a.B + b) * a.ldk + col0 + d);
-        vv = __ldg(a.V + ((int64_t)kk * a.B + b) * a.ldv + col0 + d);
-      }
-      Ks[j * ldt + d] = kv; Vs[j * ldt + d] = vv;
-    }
+    attn_load_rows(Ks, ldt, a.K, a.ldk, a.B, b, col0, k0, a.Sk, ATT_T, hd, 1.f);
+    attn_load_rows(Vs, ldt, a.V, a.ldv, a.B, b, col0, k0, a.Sk, ATT_T, hd, 1.f);
     __syncthreads();
     const int nk = min(ATT_T, a.Sk - k0);
     float s[ATT_R], dp[ATT_R], ds[ATT_R];
@@ -252,15 +251,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dkv_kernel(const Attn
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * ATT_ROWS;
   const int col0 = h * hd;
-  for (int idx = threadIdx.x; idx < ATT_ROWS * hd; idx += ATT_WARPS * 32) {
-    const int r = idx / hd, d = idx - r * hd, j = j0 + r;
-    float kv = 0.f, vv = 0.f;
-    if (j < a.Sk) {
-      kv = __ldg(a.K + ((int64_t)j * a.B + b) * a.ldk + col0 + d);
-      vv = __ldg(a.V + ((int64_t)j * a.B + b) * a.ldv + col0 + d);
-    }
-    ks[idx] = kv; vs[idx] = vv;
-  }
+  attn_load_rows(ks, hd, a.K, a.ldk, a.B, b, col0, j0, a.Sk, ATT_ROWS, hd, 1.f);
+  attn_load_rows(vs, hd, a.V, a.ldv, a.B, b, col0, j0, a.Sk, ATT_ROWS, hd, 1.f);
   float dk[ATT_R][NDL], dv[ATT_R][NDL];
 #pragma unroll
   for (int r = 0; r < ATT_R; ++r)
@@ -270,15 +262,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_bwd_dkv_kernel(const Attn
   const float* vw = vs + warp * ATT_R * hd;
   for (int i0 = 0; i0 < a.Sq; i0 += ATT_T) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < ATT_T * hd; idx += ATT_WARPS * 32) {
-      const int t = idx / hd, d = idx - t * hd, i = i0 + t;
-      float qv = 0.f, gv = 0.f;
-      if (i < a.Sq) {
-        qv = __ldg(a.Q + ((int64_t)i * a.B + b) * a.ldq + col0 + d) * a.scale;
-        gv = __ldg(a.dO + ((int64_t)i * a.B + b) * a.lddo + col0 + d);
-      }
-      Qs[t * ldt + d] = qv; dOs[t * ldt + d] = gv;
-    }
+    attn_load_rows(Qs, ldt, a.Q, a.ldq, a.B, b, col0, i0, a.Sq, ATT_T, hd, a.scale);
+    attn_load_rows(dOs, ldt, a.dO, a.lddo, a.B, b, col0, i0, a.Sq, ATT_T, hd, 1.f);
     if (threadIdx.x < ATT_T) {
       const int i = i0 + threadIdx.x;
       lse_s[threadIdx.x] = i < a.Sq ? __ldg(a.lse + ((int64_t)b * a.H + h) * a.Sq + i) : 0.f;
