@@ -115,3 +115,59 @@ def test_dropout_sites():
     d = make_desc("metablock", 16, 1664, 13, 512, 512, 8, 8, train=True)
     s = _lib.dropout_sites(d)
     assert set(s) == {4, 5} and abs(s[4][0] - 0.3) < 1e-7
+
+
+def test_dp_bucket_split_is_a_balanced_weight_boundary():
+    """fb200_dp_bucket_split (host-only): 0 where nothing can be split (FFMA path), otherwise the offset of a weight
+    gradient that cuts the tcgen05 weight-gradient tiles into two halves of equal wave count for the headline config."""
+    L = _lib.lib()
+    small = make_desc("crossattention", 32, 2048, 85, 512, 512, 8, 6, train=True)
+    assert _lib.dp_bucket_split(small) == 0
+    d = make_desc("crossattention", 4096, 2048, 85, 512, 512, 8, 6, train=True)
+    split = _lib.dp_bucket_split(d)
+    total, offs = _lib.grad_layout(d)
+    assert 0 < split < total
+    names = _lib.param_names()
+    # the split is the start of a weight (or of the V third of an in_proj_weight): never inside a bias / LayerNorm vector
+    starts = set()
+    for i, k in enumerate(names):
+        if i in offs and k.endswith("weight"):
+            shp = _lib.param_shape(d, i)
+            starts.add(offs[i])
+            if len(shp) == 2 and k.endswith("in_proj_weight"):
+                starts.add(offs[i] + 2 * shp[0] // 3 * shp[1])
+    assert split in starts
+    # tiles (128 x 128) of the tcgen05 weight gradients on either side: 136 | 136 for this configuration = one wave each on 148 SMs
+    lo = hi = 0
+    for i, k in enumerate(names):
+        if i not in offs or not k.endswith("weight"):
+            continue
+        shp = _lib.param_shape(d, i)
+        if len(shp) != 2:
+            continue                                      # LayerNorm weight vectors
+        r, c = shp
+        if c % 8 or c < 32 or r < 32:
+            continue                                      # K = 85 (FFMA), the 6-class head
+        if k.endswith("in_proj_weight"):
+            r, off = r // 3, offs[i] + 2 * (r // 3) * c   # only the V third is computed
+        else:
+            off = offs[i]
+        tiles = -(-r // 128) * -(-c // 128)
+        if off < split:
+            lo += tiles
+        else:
+            hi += tiles
+    assert (lo, hi) == (136, 136)
+
+
+def test_mha_workspace_and_argument_checks_on_host():
+    L = _lib.lib()
+    d = _lib.MhaDesc(Sq=197, Skv=85, B=32, D=512, H=8, flags=0)
+    n = ctypes.c_size_t(0)
+    assert L.fb200_mha_workspace_bytes(ctypes.byref(d), ctypes.byref(n)) == 0
+    floats = 6 * 197 * 32 * 512 + 4 * 85 * 32 * 512 + 2 * 32 * 8 * 197        # Q, O, dO, dQ | K, V, dK, dV | lse, delta ... (+ alignment)
+    assert n.value >= 4 * (4 * 197 * 32 * 512 + 4 * 85 * 32 * 512 + 2 * 32 * 8 * 197) and n.value < 4 * floats
+    bad = _lib.MhaDesc(Sq=4, Skv=4, B=1, D=512, H=7, flags=0)                   # embed_dim % num_heads != 0
+    assert L.fb200_mha_workspace_bytes(ctypes.byref(bad), ctypes.byref(n)) == -1
+    wide = _lib.MhaDesc(Sq=4, Skv=4, B=1, D=1024, H=2, flags=0)                 # head dim 512 > 256
+    assert L.fb200_mha_workspace_bytes(ctypes.byref(wide), ctypes.byref(n)) == -2
