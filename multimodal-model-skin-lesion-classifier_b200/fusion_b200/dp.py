@@ -54,7 +54,8 @@ class BucketedAllReduce:
     all-reduces bucket 2 behind the step and joins the communication stream back."""
 
     def __init__(self, device, group=None):
-        self.stream = torch.cuda.Stream(device=device)
+        device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None     # None: host tensors (gloo tests)
         self.group = group
 
     @staticmethod
@@ -72,9 +73,12 @@ class BucketedAllReduce:
             return
         b0, e1 = min(b for b, _ in ranges), max(e for _, e in ranges)
         self._hi = (b0, e1)
-        if mid_event is None or not split or not (b0 < split < e1):
+        if not split or not (b0 < split < e1) or (mid_event is None and self.stream is not None):
             return
         self._hi = (split, e1)
+        if self.stream is None:                      # host tensors: same two buckets, nothing to overlap
+            dist.all_reduce(flat_grad[b0:split], op=dist.ReduceOp.SUM, group=self.group)
+            return
         self.stream.wait_event(mid_event)
         with torch.cuda.stream(self.stream):
             dist.all_reduce(flat_grad[b0:split], op=dist.ReduceOp.SUM, group=self.group)
@@ -83,7 +87,8 @@ class BucketedAllReduce:
     def finish(self, flat_grad):
         if self._hi is not None:
             dist.all_reduce(flat_grad[self._hi[0]:self._hi[1]], op=dist.ReduceOp.SUM, group=self.group)
-            torch.cuda.current_stream().wait_stream(self.stream)
+            if self.stream is not None:
+                torch.cuda.current_stream().wait_stream(self.stream)
 
 
 class DenominatorPrefetcher:

@@ -48,7 +48,16 @@ def _worker(rank, world, port, mech, q):
     for b, e in ranges:
         covered[b:e] = True
     assert float(flat[~covered].abs().max()) == 0.0 if (~covered).any() else True     # what is not shipped is structurally zero
+    local = flat.clone()
     dp.allreduce_gradients(flat, ranges=ranges)
+    # what bench.py runs at N > 1: one in-place all-reduce of the live span, or two buckets around a split
+    b0, e1 = ranges[0][0], ranges[-1][1]
+    for split in (0, (b0 + e1) // 2 // 4 * 4):
+        f2 = local.clone()
+        bar = dp.BucketedAllReduce("cpu")
+        bar.start(f2, ranges, split, None)
+        bar.finish(f2)
+        assert torch.equal(f2, flat), split
     num = torch.tensor([o["num"]]); dist.all_reduce(num)
     if rank == 0:
         full = ho.head_forward_backward(cfg, params, x, tin, labels, cw, masks)
