@@ -13,9 +13,16 @@
  * host pointer or a missing GPU is FB200_EUNSUPPORTED / FB200_ECUDA.
  *
  * Threading: the library keeps no mutable global state besides a per-device cache of
- * immutable kernel attributes; calls are re-entrant, launch only on the stream handed in
- * (forward is called on the Python main thread, backward on autograd's device thread) and
- * are CUDA-graph capturable.
+ * immutable kernel attributes and, per host thread and device, one internal side stream with
+ * a pool of timing-disabled events.  Calls are re-entrant (forward is called on the Python
+ * main thread, backward on autograd's device thread).  All work is ordered on the stream
+ * handed in: the head entry points may fork part of it onto the side stream, but join it back
+ * before they return (FB200_FLAG_ONE_STREAM disables the fork), so they are CUDA-graph
+ * capturable and callers see one stream.  Every kernel is launched with the
+ * programmatic-stream-serialization attribute and waits (griddepcontrol.wait) before its first
+ * global-memory access.  Environment switches for A/B measurements, read once: FB200_PDL=0
+ * (plain launches), FB200_LANES=0 (one stream), FB200_TC_DBG=<bits> (timing-only GEMM
+ * ablations; results are wrong by construction).
  */
 #ifndef FB200_H
 #define FB200_H
