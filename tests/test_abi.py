@@ -171,3 +171,36 @@ def test_mha_workspace_and_argument_checks_on_host():
     assert L.fb200_mha_workspace_bytes(ctypes.byref(bad), ctypes.byref(n)) == -1
     wide = _lib.MhaDesc(Sq=4, Skv=4, B=1, D=1024, H=2, flags=0)                 # head dim 512 > 256
     assert L.fb200_mha_workspace_bytes(ctypes.byref(wide), ctypes.byref(n)) == -2
+
+
+def test_engine_policy_and_launch_counts_on_host():
+    """Host-side plan introspection: fp32 uses the exact FFMA kernels up to 32 rows and the tcgen05 3xTF32 path above
+    (bf16 always tcgen05); widths that TMA cannot take (V = 85) and the class head stay off the tensor path; the step of the
+    headline configuration is 40 kernel launches (27 tcgen05 GEMMs + ONE grouped weight-gradient launch + 12 others)."""
+    L = _lib.lib()
+
+    def gemms(B, dtype="fp32", flags=0):
+        d = make_desc("crossattention", B, 2048, 85, 512, 512, 8, 6, dtype=dtype, train=True, flags=flags)
+        arr = (ctypes.c_int32 * (5 * 256))()
+        L.fb200_list_gemms.restype = ctypes.c_int
+        L.fb200_list_gemms.argtypes = [ctypes.POINTER(_lib.Desc), ctypes.POINTER(ctypes.c_int32), ctypes.c_int]
+        n = L.fb200_list_gemms(ctypes.byref(d), arr, 256)
+        return [tuple(arr[5 * i + j] for j in range(5)) for i in range(n)], d      # (layout, engine, M, N, K)
+
+    g32, _ = gemms(32)
+    assert {e for _, e, *_ in g32} == {0}                                          # FFMA everywhere
+    g64, _ = gemms(64)
+    assert {e for _, e, *_ in g64} == {0, 1}
+    assert all(e == 0 for lay, e, M, N, K in g64 if 85 in (N, K))                  # text_fc.0: K = 85 is not TMA-legal
+    assert all(e == 1 for lay, e, M, N, K in g64 if 85 not in (N, K))
+    gb, _ = gemms(32, dtype="bf16")
+    assert 2 in {e for _, e, *_ in gb}                                             # bf16 rides tcgen05 at any batch
+    gs, _ = gemms(4096, flags=_lib.FLAG_FORCE_SIMT)
+    assert {e for _, e, *_ in gs} == {0}
+    g, d = gemms(4096)
+    fwd, bwd = ctypes.c_int(0), ctypes.c_int(0)
+    assert L.fb200_launch_count(ctypes.byref(d), ctypes.byref(fwd), ctypes.byref(bwd)) == 0
+    assert (fwd.value, bwd.value) == (18, 19)              # + CE pass 1 / 2 + the Philox advance = the 40 launches of profiles/r01_launch_list
+    # forward NT, weight-gradient TN for every Linear; input-gradient NN only where something upstream needs it
+    nt = [x for x in g if x[0] == 0]; tn = [x for x in g if x[0] == 2]; nn = [x for x in g if x[0] == 1]
+    assert len(nt) == len(tn) == 15 and len(nn) == 13      # image_projector and text_fc.0 have no dX (inputs need no gradient)
