@@ -56,7 +56,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"], help="GEMM engine policy (auto: tcgen05 from B > 32 in fp32, always in bf16)")
-    ap.add_argument("--sweep", default="", help="comma-separated extra per-GPU batch sizes reported under 'sweep'")
+    ap.add_argument("--sweep", default="32,256,1024", help="comma-separated extra per-GPU batch sizes reported under 'sweep' ('' disables)")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the GPU-eager reference (torch.nn on cuda) and the eager drop-in route")
     return ap.parse_args()
 
 
@@ -102,6 +103,18 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def physical_cores():
+    """Physical cores of the box (SURVEY 8d asks for physical, not logical, cores in `cpu_baseline.cores`)."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
 # ----------------------------------------------------------------------------- reference arm
 def reference_arm(args, wl):
     """The reference's own CPU implementation of the path (torch.nn on the host cores)."""
@@ -111,7 +124,7 @@ def reference_arm(args, wl):
     import torch
     from oracle.torch_port import time_cpu_train_step
     mech, F, V, Cn, T, tm, dtype = wl
-    threads = os.cpu_count() or 1
+    threads = physical_cores()
     B = args.batch
     r = time_cpu_train_step(mech, F, V, Cn, B, T=T, one_hot=(tm == 0), steps=max(args.steps, 2), warmup=max(min(args.warmup, 3), 1),
                             threads=threads, budget_s=150.0)
@@ -367,13 +380,34 @@ def main():
 
     sweep = {}
     for bs in [int(v) for v in args.sweep.split(",") if v]:
-        _, ms_b, _, _, _ = run_config(bs, max(10, K // 2), W)
-        sweep[str(bs)] = {"ms_per_step": ms_b, "samples_per_s": bs * world / (ms_b * 1e-3)}
+        if bs == B:
+            continue
+        _, ms_b, _, _, _ = run_config(bs, max(20, K), W)
+        d_b = fb.make_desc(mech, bs, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype, train=True, flags={"auto": 0, "simt": 4, "tc": 8}[args.engine])
+        fl_b, by_b, _ = _lib.algorithmic_work(d_b)
+        t_roof_b = max(fl_b / (roof["step_peak_tflops"] * 1e12), by_b / (roof["hbm_gbs"] * 1e9)) * 1e3
+        sweep[str(bs)] = {"ms_per_step": ms_b, "samples_per_s": bs * world / (ms_b * 1e-3), "t_roof_ms": t_roof_b, "roofline_frac": t_roof_b / ms_b}
+
+    # ---- the incumbent on the same box: the reference torch.nn module on device='cuda' (stock ATen / cuBLAS
+    #      kernels, fp32, TF32 off like the reference), eager and as one CUDA graph; and this repo's eager DROP-IN route
+    #      model(x, meta) -> criterion -> loss.backward() (no graph, no fused step) - the call shape of train_pad_20.py:110-112
+    incumbent = None
+    if rank == 0 and not args.no_incumbent:
+        incumbent = {}
+        for bs in sorted({32, B}):
+            try:
+                incumbent[str(bs)] = time_incumbents(torch, fb, dev, wl, bs, build)
+            except Exception as exc:
+                incumbent[str(bs)] = {"error": repr(exc)}
+
+    dp_check = None
+    if world > 1:
+        dp_check = run_dp_check(torch, dist, fb, _lib, dev, wl, build, rank, world)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.torch_port import time_cpu_train_step
-        r = time_cpu_train_step(mech, F, V, Cn, B, T=T, one_hot=(tm == 0), steps=6, warmup=2, threads=os.cpu_count(), budget_s=25.0)
+        r = time_cpu_train_step(mech, F, V, Cn, B, T=T, one_hot=(tm == 0), steps=6, warmup=2, threads=physical_cores(), budget_s=25.0)
         cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["threads"], "kind": "port",
                "sample": f"{r['steps']} train steps of batch {B} on the reference torch.nn CPU path (median), {r['ms_per_step']:.1f} ms/step"}
 
@@ -395,7 +429,7 @@ def main():
                        "l2": f"inputs rotate over a pool of {nb} batches = {nb * in_bytes / 1e6:.0f} MB (> 126 MB L2 when >= 127); weights ({plive * 4 / 1e6:.1f} MB) stay L2-resident by design"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss": last_loss, "sweep": sweep or None,
-            "extras": extras,
+            "incumbent": incumbent, "dp_check": dp_check, "extras": extras,
         }
         emit(line)
     if world > 1:
@@ -491,6 +525,107 @@ def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype, model):
             "hbm_gbs": hbm, "step_peak_tflops": peak, "gemm_ms_per_step": tot_ms, "gemm_launches_per_step": sum(shapes.values()),
             "how": "all GEMM launches of one train step replayed alone (fb200_debug_gemm_replay), CUDA events on the launch stream, eager launches",
             "top_shapes_single_launch": per[:6]}
+
+
+def time_incumbents(torch, fb, dev, wl, Bsz, build, steps=30, warm=5):
+    """ms per train step (zero_grad + forward + weighted CE + backward) at batch `Bsz`, inputs resident, CUDA events:
+    gpu_eager / gpu_eager_graph = the reference torch.nn module (oracle/torch_port.py, bit-identical to the reference) on cuda,
+    eager_dropin = this repo's model through the reference call shape, one library call per pass, no CUDA graph."""
+    from oracle.torch_port import ReferencePort
+    mech, F, V, Cn, T, tm, dtype = wl
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(Bsz, F, generator=g).to(dev); t = torch.randn(Bsz, V if tm == 0 else T, generator=g).to(dev)
+    y = torch.randint(0, Cn, (Bsz,), generator=g).to(dev)
+    cw = torch.ones(Cn, device=dev)
+    out = {}
+
+    def timed(fn):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False          # the reference runs fp32 with PyTorch's defaults
+    try:
+        torch.manual_seed(1234)
+        ref = ReferencePort(mech, F, Cn, V=V if V else 85, T=T, one_hot=(tm == 0)).to(dev).train()
+        crit = torch.nn.CrossEntropyLoss(weight=cw)
+
+        def ref_step():
+            ref.zero_grad(set_to_none=True)
+            crit(ref(x, t), y).backward()
+        out["gpu_eager_ms"] = timed(ref_step)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    ref_step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            ref.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                crit(ref(x, t), y).backward()
+            out["gpu_eager_graph_ms"] = timed(graph.replay)
+            del graph
+        except Exception as exc:
+            out["gpu_eager_graph_ms"] = None
+            out["gpu_eager_graph_error"] = repr(exc)
+        del ref
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+    model = build(Bsz)
+    crit2 = fb.FusedCrossEntropyLoss(weight=cw)
+
+    def dropin_step():
+        model.zero_grad(set_to_none=True)
+        crit2(model(x, t), y).backward()
+    out["eager_dropin_ms"] = timed(dropin_step)
+
+    def fused_step():
+        model.forward_loss(x, t, y, cw)
+    out["eager_fused_step_ms"] = timed(fused_step)
+    out["note"] = ("gpu_eager*: reference torch.nn module on cuda (fp32, TF32 off), eager launches / one CUDA graph; eager_dropin: "
+                   "fusion_b200 model(x, meta) -> FusedCrossEntropyLoss -> backward(), no graph; eager_fused_step: forward_loss, no graph")
+    return out
+
+
+def run_dp_check(torch, dist, fb, _lib, dev, wl, build, rank, world, rows_per_rank=192):
+    """N ranks + NCCL + global denominator against ONE process at the global batch, on the hardware: every rank draws the same
+    global batch, runs its shard through forward_loss with the global weighted-CE denominator and SUM-all-reduces the flat
+    gradient; the result must equal forward_loss on the whole batch (eval mode: dropout draws depend on the local row index)."""
+    mech, F, V, Cn, T, tm, dtype = wl
+    Bg = rows_per_rank * world
+    g = torch.Generator().manual_seed(777)
+    x = torch.randn(Bg, F, generator=g).to(dev); t = torch.randn(Bg, V if tm == 0 else T, generator=g).to(dev)
+    y = torch.randint(0, Cn, (Bg,), generator=g).to(dev)
+    counts = torch.bincount(y.cpu(), minlength=Cn).clamp_min(1).float()
+    cw = (Bg / (Cn * counts)).to(dev)
+    model = build(Bg)
+    model.eval()
+    lo, hi = fb.dp.shard_rows(Bg, rank, world)
+    denom = fb.dp.global_denominator(y[lo:hi], cw)
+    loss_s, _ = model.forward_loss(x[lo:hi], t[lo:hi], y[lo:hi], cw, denom=denom)
+    flat_s = model.flat_grad.clone()
+    fb.dp.allreduce_gradients(flat_s)
+    loss_s = loss_s.clone(); dist.all_reduce(loss_s)
+    loss_g, _ = model.forward_loss(x, t, y, cw)
+    flat_g = model.flat_grad
+    torch.cuda.synchronize()
+    err = ((flat_s - flat_g).abs().max() / flat_g.abs().max()).item()
+    l2 = ((flat_s - flat_g).norm() / flat_g.norm()).item()
+    worst = torch.tensor([err, l2, abs(loss_s.item() - loss_g.item()) / abs(loss_g.item())], device=dev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    return {"max_rel_err": worst[0].item(), "rel_l2": worst[1].item(), "loss_rel_err": worst[2].item(), "global_batch": Bg,
+            "how": f"{world} ranks x {rows_per_rank} rows, global denominator, NCCL SUM all-reduce of the flat gradient vs one process on {Bg} rows (eval mode)"}
 
 
 def time_token_attention(torch, fb, dev, Sq=197, Skv=85, B=32, D=512, H=8, reps=20):

@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <unordered_set>
+#include <unordered_map>
 #include <algorithm>
 #include <cmath>
 
@@ -34,6 +36,22 @@ static bool is_device_ptr(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// cudaPointerGetAttributes costs about a microsecond; parameters, class weights and masks are the same allocations call after
+// call, so pointers that passed once are remembered (a freed-and-reused address is still a device address or the
+// allocator would not have handed it out to a CUDA tensor - the check guards against HOST pointers, not lifetimes).
+static bool is_device_ptr_cached(const void* p) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> seen;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (seen.count(p)) return true;
+  }
+  if (!is_device_ptr(p)) return false;
+  std::lock_guard<std::mutex> g(mu);
+  if (seen.size() < (size_t)1 << 16) seen.insert(p);
+  return true;
 }
 
 #define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; } } while (0)
@@ -284,7 +302,10 @@ static int run_backward(Ctx& c) {
   std::vector<std::vector<TcGroupProblem>> dw_round;   // [k]: k-th application of a weight (k > 0 accumulates, in launch order)
   std::vector<int> tc_uses(NUM_SLOTS, 0);
   LaneSync ls; const cudaStream_t main_st = c.st;
-  { int rc = ls.begin(c, p.acts.size()); if (rc != FB200_OK) return rc; }      // after the zero fill of the gradient buffer
+  // event slots: one per activation buffer, then one per parameter slot (FFMA weight gradients are non-atomic
+  // read-modify-writes of the parameter's gradient slice: a weight applied on both lanes must be ordered too)
+  const int nbuf = (int)p.acts.size();
+  { int rc = ls.begin(c, p.acts.size() + NUM_SLOTS); if (rc != FB200_OK) return rc; }      // after the zero fill of the gradient buffer
   for (int oi = (int)p.ops.size() - 1; oi >= 0; --oi) {
     const Op& o = p.ops[oi];
     // the gradient of a view that lives inside a fully written buffer counts as written
@@ -292,7 +313,8 @@ static int run_backward(Ctx& c) {
     if (!is_written(o.out)) return FB200_EBADARG;
     c.st = c.lane_st[o.lane];
     // gradient buffers this op reads (out) or writes / accumulates into (its inputs): order after the other lane's last touch
-    for (int b : {o.out.buf, o.in0.buf, o.in1.buf, o.in2.buf, o.dx_view.buf}) { int rc = ls.wait_for(o.lane, b); if (rc != FB200_OK) return rc; }
+    const int wslot_ev = (o.kind == OP_LINEAR && o.engine == 0 && o.w_slot >= 0) ? nbuf + o.w_slot : -1;
+    for (int b : {o.out.buf, o.in0.buf, o.in1.buf, o.in2.buf, o.dx_view.buf, wslot_ev}) { int rc = ls.wait_for(o.lane, b); if (rc != FB200_OK) return rc; }
     switch (o.kind) {
       case OP_CAST: break;
       case OP_LINEAR: {
@@ -415,7 +437,7 @@ static int run_backward(Ctx& c) {
       default: return FB200_EBADARG;
     }
     CUDA_OK(cudaGetLastError());
-    { int rc = ls.touched(o.lane, {o.out.buf, o.in0.buf, o.in1.buf, o.in2.buf, o.dx_view.buf}); if (rc != FB200_OK) return rc; }
+    { int rc = ls.touched(o.lane, {o.out.buf, o.in0.buf, o.in1.buf, o.in2.buf, o.dx_view.buf, wslot_ev}); if (rc != FB200_OK) return rc; }
   }
   c.st = main_st;
   { int rc = ls.join(c); if (rc != FB200_OK) return rc; }
@@ -475,13 +497,26 @@ static int check_common(const fb200_desc* d, const void* const* params, const vo
   rc = get_device_info(dev);
   if (rc != FB200_OK) return rc;
   if (dev.cc_major < 10) return FB200_EUNSUPPORTED;          // sm_100a only: no other architecture is built
-  if (!is_device_ptr(img) || !is_device_ptr(ws)) return FB200_EUNSUPPORTED;   // no CPU path
+  if (!is_device_ptr(img) || !is_device_ptr(txt) || !is_device_ptr(ws)) return FB200_EUNSUPPORTED;   // no CPU path
   for (int s = 0; s < NUM_SLOTS; ++s) {
     if (!plan.live[s]) continue;
     if (!params[s]) return FB200_EBADARG;
     if (((uintptr_t)params[s]) & 15) return FB200_EALIGN;
+    if (!is_device_ptr_cached(params[s])) return FB200_EUNSUPPORTED;
   }
   if ((((uintptr_t)img) & 15) || (((uintptr_t)ws) & 255)) return FB200_EALIGN;
+  // text_in rows are read with 128-bit loads whenever its width allows it: the base must then be 16-byte aligned
+  // (widths 85 / 13 / 11 take the scalar loaders of the FFMA kernel, any 4-byte alignment)
+  if (((uintptr_t)txt) & 3) return FB200_EALIGN;
+  if (plan.acts[1].cols % 4 == 0 && (((uintptr_t)txt) & 15)) return FB200_EALIGN;
+  return FB200_OK;
+}
+
+// optional device pointers of a call (labels, class weights, denominator, dropout masks, rng state): NULL is fine, a host
+// pointer is refused with a status instead of an illegal-address fault that would kill the context
+static int check_optional_device(std::initializer_list<const void*> ptrs, const uint8_t* const* masks) {
+  for (const void* q : ptrs) if (q && !is_device_ptr_cached(q)) return FB200_EUNSUPPORTED;
+  if (masks) for (int i = 0; i < FB200_NUM_DROPOUT_SITES; ++i) if (masks[i] && !is_device_ptr_cached(masks[i])) return FB200_EUNSUPPORTED;
   return FB200_OK;
 }
 
@@ -732,6 +767,7 @@ int fb200_head_forward(const fb200_desc* d, const void* const* params, const voi
   int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
   if (rc != FB200_OK) return rc;
   if (!logits) return FB200_EBADARG;
+  rc = check_optional_device({rng_state, logits}, masks); if (rc != FB200_OK) return rc;
   Ctx c{plan, params, img_feat, text_in, logits, nullptr, nullptr, nullptr, nullptr, masks, seed, offset, (const uint64_t*)rng_state, (char*)ws, (cudaStream_t)stream, dev};
   return run_forward(c);
 }
@@ -745,6 +781,7 @@ int fb200_head_backward(const fb200_desc* d, const void* const* params, const vo
   if (!dlogits || !grads) return FB200_EBADARG;
   if ((d->flags & FB200_FLAG_NEED_DIMG) && !d_img_feat) return FB200_EBADARG;
   if ((d->flags & FB200_FLAG_NEED_DTEXT) && !d_text_in) return FB200_EBADARG;
+  rc = check_optional_device({rng_state, dlogits, grads, d_img_feat, d_text_in}, masks); if (rc != FB200_OK) return rc;
   Ctx c{plan, params, img_feat, text_in, nullptr, dlogits,
         (d->flags & FB200_FLAG_NEED_DIMG) ? d_img_feat : nullptr, (d->flags & FB200_FLAG_NEED_DTEXT) ? d_text_in : nullptr,
         (float*)grads, masks, seed, offset, (const uint64_t*)rng_state, (char*)ws, (cudaStream_t)stream, dev};
@@ -754,6 +791,7 @@ int fb200_head_backward(const fb200_desc* d, const void* const* params, const vo
 int fb200_cross_entropy(const void* logits, const int64_t* labels, const float* class_w, const float* denom, int B, int C,
                         float* loss_out, void* dlogits, void* stream) {
   if (!logits || !is_device_ptr(logits)) return logits ? FB200_EUNSUPPORTED : FB200_EBADARG;
+  { int rc = check_optional_device({labels, class_w, denom, loss_out, dlogits}, nullptr); if (rc != FB200_OK) return rc; }
   return ce_launch(logits, labels, class_w, denom, B, C, loss_out, dlogits, (cudaStream_t)stream);
 }
 
@@ -782,6 +820,7 @@ int fb200_head_train_step_dp(const fb200_desc* d, const void* const* params, con
   if (!logits || !labels || !loss_out || !grads) return FB200_EBADARG;
   if ((d->flags & FB200_FLAG_NEED_DIMG) && !d_img_feat) return FB200_EBADARG;
   if ((d->flags & FB200_FLAG_NEED_DTEXT) && !d_text_in) return FB200_EBADARG;
+  rc = check_optional_device({labels, class_w, denom, rng_state, logits, loss_out, grads, d_img_feat, d_text_in}, masks); if (rc != FB200_OK) return rc;
   // dlogits live at the tail of the workspace (fb200_workspace_bytes reserves them)
   char* w = (char*)ws;
   float* dlog = (float*)(w + plan.ws_bytes - (((size_t)d->B * d->C * sizeof(float) + 255) & ~size_t(255)) - 256);

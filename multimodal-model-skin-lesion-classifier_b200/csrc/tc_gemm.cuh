@@ -20,6 +20,9 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 namespace fb200 {
 
@@ -629,7 +632,7 @@ inline PFN_encodeTiled get_encode_fn() {
 struct TcOperand {
   const void* base; int64_t plane_elems; int ld; int inner, outer;
 };
-inline int make_operand_map(CUtensorMap* map, int kind, const TcOperand& o, int box_inner, int box_outer, bool mn_major) {
+inline int encode_operand_map(CUtensorMap* map, int kind, const TcOperand& o, int box_inner, int box_outer, bool mn_major) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return FB200_ECUDA;
   const int es = kind == 0 ? 2 : 4;
@@ -642,6 +645,38 @@ inline int make_operand_map(CUtensorMap* map, int kind, const TcOperand& o, int 
   CUresult r = enc(map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)o.base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, (kind == 1 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? FB200_OK : FB200_ECUDA;
+}
+
+// cuTensorMapEncodeTiled costs ~1 us of host time; the eager drop-in route (model(x, meta) -> loss.backward(), one library
+// call per pass, no CUDA graph) encodes two maps per GEMM per call.  Weights, workspace buffers and gradient slices recur
+// with the same address and shape call after call, so encoded maps are kept per (pointer, geometry, box, kind) and per
+// host thread (forward runs on the caller's thread, backward on autograd's worker: no lock, no sharing).  A tensor map
+// holds no reference to the memory - it is an address plus strides - so a recycled address with the same geometry may
+// reuse it safely.
+struct TcMapKey {
+  const void* base; int ld, inner, outer, box_inner, box_outer, kind_mn;
+  bool operator==(const TcMapKey& o) const { return std::memcmp(this, &o, sizeof(TcMapKey)) == 0; }
+};
+struct TcMapKeyHash {
+  size_t operator()(const TcMapKey& k) const {
+    uint64_t h = (uint64_t)(uintptr_t)k.base * 0x9E3779B97F4A7C15ull;
+    auto mix = [&h](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+    mix((uint64_t)k.ld << 32 | (uint32_t)k.inner); mix((uint64_t)k.outer << 32 | (uint32_t)k.box_inner); mix((uint64_t)k.box_outer << 8 | (uint32_t)k.kind_mn);
+    return (size_t)h;
+  }
+};
+inline int make_operand_map(CUtensorMap* map, int kind, const TcOperand& o, int box_inner, int box_outer, bool mn_major) {
+  static thread_local std::unordered_map<TcMapKey, CUtensorMap, TcMapKeyHash> cache;
+  TcMapKey key; std::memset(&key, 0, sizeof(key));
+  key.base = o.base; key.ld = o.ld; key.inner = o.inner; key.outer = o.outer; key.box_inner = box_inner; key.box_outer = box_outer;
+  key.kind_mn = kind * 2 + (mn_major ? 1 : 0);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *map = it->second; return FB200_OK; }
+  const int rc = encode_operand_map(map, kind, o, box_inner, box_outer, mn_major);
+  if (rc != FB200_OK) return rc;
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *map);
+  return FB200_OK;
 }
 
 struct TcGemmArgs {
@@ -661,11 +696,11 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   if (rc != FB200_OK) return rc;
   rc = make_operand_map(&mb, KIND, g.B, B_MN ? Cfg::EPC : Cfg::BK, B_MN ? Cfg::BK : BN, B_MN);
   if (rc != FB200_OK) return rc;
-  static bool attr_set = false;                   // idempotent; a benign race sets it twice
   auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN>;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
-    attr_set = true;
+  {                                                // forward runs on the caller's thread, backward on autograd's worker
+    static std::once_flag once; static cudaError_t attr_rc = cudaSuccess;
+    std::call_once(once, [&] { attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+    if (attr_rc != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
   }
   const int tiles_m = (g.M + TC_BM - 1) / TC_BM, tiles_n = (g.N + BN - 1) / BN;
   const int total_kb = (g.K + Cfg::BK - 1) / Cfg::BK;
@@ -734,11 +769,11 @@ inline int tc_launch_grouped_tn(const TcGroupProblem* probs, int nprob, int K, c
     tiles += ((probs[p].M + TC_BM - 1) / TC_BM) * ((probs[p].N + BN - 1) / BN);
   }
   g.tile_begin[nprob] = tiles; g.nprob = nprob; g.K = K;
-  static bool attr_set = false;
   auto kern = tc_gemm_grouped_tn_kernel<KIND, BN>;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
-    attr_set = true;
+  {
+    static std::once_flag once; static cudaError_t attr_rc = cudaSuccess;
+    std::call_once(once, [&] { attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+    if (attr_rc != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
   }
   if (pdl_launch(kern, dim3(tiles, 1, 1), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, g) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
   return FB200_OK;

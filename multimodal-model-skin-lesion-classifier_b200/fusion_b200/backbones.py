@@ -2,11 +2,16 @@
 
 Mirrors the interface of the reference's ``loadModels`` (loadImageModelClassifier.py:41-203):
 ``loadModelImageEncoder(name, common_dim, backbone_train_mode) -> (module, cnn_dim_output)``.
-Pretrained weights are used when torchvision can find them locally; otherwise the
-architecture is built with random init (no network in the build/bench containers).
+Pretrained weights are required, like the reference (``pretrained=True`` everywhere).  Where they
+cannot be loaded (no network in the build / bench containers) the architecture is built with random
+init ONLY on explicit opt-in - ``FB200_ALLOW_RANDOM_BACKBONE=1`` or the ``random:`` name prefix, e.g.
+``"random:resnet-50"`` - and a warning is emitted; otherwise the loading error is re-raised.
 Extra names for head-only work: ``"identity:<F>"`` (the "image" is already the [B,F] feature).
 """
 from __future__ import annotations
+
+import os
+import warnings
 
 import torch.nn as nn
 
@@ -37,13 +42,30 @@ def set_backbone_train_mode(model, mode="frozen_weights", last_n_layers=1):
         raise ValueError(f"Invalid backbone_train_mode: {mode}")
 
 
-def _tv_model(factory):
+def _random_init_allowed(explicit):
+    return explicit or os.environ.get("FB200_ALLOW_RANDOM_BACKBONE", "0") == "1"
+
+
+def _pretrained_or_optin(load_pretrained, load_random, what, explicit_random):
+    """Pretrained weights, or - only on opt-in - a randomly initialised copy of the architecture (with a warning).
+    A frozen random backbone trains the head on noise, so a silent fallback is never right."""
+    if explicit_random:
+        warnings.warn(f"{what}: random-init backbone requested explicitly (no pretrained weights)")
+        return load_random()
+    try:
+        return load_pretrained()
+    except Exception as exc:
+        if not _random_init_allowed(False):
+            raise RuntimeError(f"{what}: pretrained weights could not be loaded ({exc!r}); set FB200_ALLOW_RANDOM_BACKBONE=1 "
+                               f"or use the 'random:' name prefix to build the architecture with random init") from exc
+        warnings.warn(f"{what}: pretrained weights unavailable ({exc!r}); using RANDOM init (FB200_ALLOW_RANDOM_BACKBONE=1)")
+        return load_random()
+
+
+def _tv_model(factory, explicit_random=False):
     from torchvision import models
     fn = getattr(models, factory)
-    try:
-        return fn(weights="DEFAULT")
-    except Exception:       # offline: same architecture, random init
-        return fn(weights=None)
+    return _pretrained_or_optin(lambda: fn(weights="DEFAULT"), lambda: fn(weights=None), f"torchvision.{factory}", explicit_random)
 
 
 class loadModels:
@@ -51,9 +73,12 @@ class loadModels:
     def loadModelImageEncoder(cnn_model_name, common_dim, backbone_train_mode="frozen", device="cpu"):
         if cnn_model_name.startswith("identity:"):
             return nn.Identity(), int(cnn_model_name.split(":", 1)[1])
+        explicit_random = cnn_model_name.startswith("random:")
+        if explicit_random:
+            cnn_model_name = cnn_model_name.split(":", 1)[1]
         if cnn_model_name in _TORCHVISION:
             factory, head, width = _TORCHVISION[cnn_model_name]
-            model = _tv_model(factory)
+            model = _tv_model(factory, explicit_random)
             setattr(model, head, nn.Identity())
             if cnn_model_name == "densenet169" and backbone_train_mode == "partial":
                 for p in model.parameters():
@@ -64,7 +89,7 @@ class loadModels:
                 set_backbone_train_mode(model, backbone_train_mode, last_n_layers=1)
             return model, width
         if cnn_model_name == "vgg16":
-            model = _tv_model("vgg16")
+            model = _tv_model("vgg16", explicit_random)
             model.classifier = nn.Sequential(*list(model.classifier.children())[:-1])
             set_backbone_train_mode(model, backbone_train_mode, last_n_layers=1)
             return model, 4096
@@ -73,10 +98,8 @@ class loadModels:
         except ImportError:
             timm = None
         if timm is not None and cnn_model_name in timm.list_models():
-            try:
-                model = timm.create_model(cnn_model_name, pretrained=True)
-            except Exception:
-                model = timm.create_model(cnn_model_name, pretrained=False)
+            model = _pretrained_or_optin(lambda: timm.create_model(cnn_model_name, pretrained=True),
+                                         lambda: timm.create_model(cnn_model_name, pretrained=False), f"timm.{cnn_model_name}", explicit_random)
             if hasattr(model, "reset_classifier"):
                 model.reset_classifier(0)
             set_backbone_train_mode(model, backbone_train_mode)

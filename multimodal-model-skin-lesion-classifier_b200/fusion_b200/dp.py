@@ -19,6 +19,7 @@ import torch.distributed as dist
 def global_denominator(labels, class_weights, group=None, out=None):
     """sum over ALL ranks of class_weights[labels]; returns a 1-element tensor on labels' device."""
     w = class_weights[labels].sum().reshape(1) if class_weights is not None else labels.new_tensor([labels.numel()], dtype=torch.float32)
+    w = w.to(torch.float32)                       # the kernels read ONE fp32 scalar (float64 class weights are cast here)
     if out is not None:
         out.copy_(w)
         w = out
@@ -37,6 +38,8 @@ def allreduce_gradients(flat_grad, group=None, async_op=False, ranges=None):
         return None
     if not ranges or len(ranges) == 1 and ranges[0] == (0, flat_grad.numel()):
         return dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    if async_op:
+        raise ValueError("allreduce_gradients: async_op is only supported for the whole-buffer all-reduce (ranges=None)")
     views = [flat_grad[b:e] for b, e in ranges]
     staging = torch.cat(views)
     dist.all_reduce(staging, op=dist.ReduceOp.SUM, group=group)
@@ -135,7 +138,13 @@ class DataParallelHead:
         self.model, self.group = model, group
 
     def train_step(self, image, text_metadata, label, class_weights=None):
+        """Returns (loss, logits): `loss` is the GLOBAL weighted-mean loss (the per-rank numerators over the global
+        denominator, summed over the ranks), i.e. what one process would report on the global batch; `logits` are this
+        rank's rows."""
         denom = global_denominator(label.to(self.model.device), None if class_weights is None else class_weights.to(self.model.device), self.group)
         loss, logits = self.model.forward_loss(image, text_metadata, label, class_weights, denom=denom)
         allreduce_gradients(self.model.flat_grad, self.group)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            loss = loss.clone()
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
         return loss, logits

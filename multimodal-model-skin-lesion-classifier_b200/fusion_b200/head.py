@@ -32,6 +32,19 @@ def make_desc(mechanism, B, F, V, T, D, H, Cn, n=2, text_mode=0, dtype="fp32", t
                      dtype=dt, train=1 if train else 0, flags=flags, reserved=0)
 
 
+def denom_arg(denom, device):
+    """The weighted-CE denominator reaches the kernels as a raw pointer to ONE fp32 device scalar: cast and move it here
+    (float64 class weights from numpy / sklearn, or a host tensor, would otherwise be read as garbage).  A tensor that
+    already is fp32 on `device` is returned as is, so static buffers of captured graphs keep their address."""
+    if denom is None:
+        return None
+    if not isinstance(denom, torch.Tensor):
+        denom = torch.tensor([float(denom)], dtype=torch.float32)
+    if denom.numel() != 1:
+        raise ValueError(f"denom must hold one element, got shape {tuple(denom.shape)}")
+    return denom.to(device=device, dtype=torch.float32).reshape(1).contiguous()
+
+
 def _check_input(t, name, cols):
     if not t.is_cuda:
         raise _lib.Fb200Error(-2, f"{name} must be a CUDA tensor (fusion_b200 has no CPU path)")
@@ -134,6 +147,7 @@ def cross_entropy(logits, labels, class_w=None, denom=None, want_grad=True):
     w = None if class_w is None else class_w.to(device=z.device, dtype=torch.float32).contiguous()
     out = torch.empty(3, dtype=torch.float32, device=z.device)
     dl = torch.empty_like(z) if want_grad else None
+    denom = denom_arg(denom, z.device)
     with torch.cuda.device(z.device):
         _lib.check(L.fb200_cross_entropy(_ptr(z), _ptr(y), _ptr(w), _ptr(denom), z.shape[0], z.shape[1], _ptr(out), _ptr(dl), _stream()),
                    "fb200_cross_entropy")

@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import _lib
 from .backbones import loadModels
-from .head import FusedHeadFunction, ParamTable, _check_input, _mask_table, _ptr, _stream, make_desc
+from .head import FusedHeadFunction, ParamTable, _check_input, _mask_table, _ptr, _stream, denom_arg, make_desc
 
 RG_ATT = "att-intramodal+residual+cross-attention-metadados"
 
@@ -181,6 +181,7 @@ class MultimodalModel(nn.Module):
         d_txt = torch.empty_like(t) if need_dtxt else None
         y = label.to(device=dev, dtype=torch.int64).contiguous()
         w = None if class_weights is None else class_weights.to(device=dev, dtype=torch.float32).contiguous()
+        denom = denom_arg(denom, dev)
         marr, _keep = _mask_table(self._injected_masks)
         if self._rng_state is None or self._rng_state.device != dev:
             # Philox key lives on the device so that a captured CUDA graph draws new masks on every replay

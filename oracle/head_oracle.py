@@ -71,6 +71,7 @@ class Tape:
     def __init__(self):
         self.steps = []
         self.relu_margin = np.inf      # smallest |pre-activation| any ReLU saw (ties make gradients discontinuous)
+        self.relu_margin_rows = None   # the same per batch row (tests redraw the rows that sit on a tie)
 
     def push(self, fn):
         self.steps.append(fn)
@@ -103,7 +104,12 @@ def linear(t, x, W, b):
 def relu(t, x):
     y = Var(np.maximum(x.v, 0))
     if x.v.size:
-        t.relu_margin = min(t.relu_margin, float(np.abs(x.v).min()))
+        rows = np.abs(x.v).min(axis=-1).reshape(-1)
+        t.relu_margin = min(t.relu_margin, float(rows.min()))
+        if t.relu_margin_rows is None or t.relu_margin_rows.shape != rows.shape:
+            t.relu_margin_rows = rows.copy() if t.relu_margin_rows is None else t.relu_margin_rows
+        else:
+            t.relu_margin_rows = np.minimum(t.relu_margin_rows, rows)
 
     def bwd():
         if y.grad is not None:
@@ -549,7 +555,8 @@ def head_forward_backward(cfg, params, img_feat, text_in, labels=None, class_w=N
     else:
         raise ValueError(f"Attention mechanism '{m}' not implemented.")
 
-    out = {"logits": logits.v, "loss": None, "grads": None, "d_img_feat": None, "d_text_in": None, "relu_margin": t.relu_margin}
+    out = {"logits": logits.v, "loss": None, "grads": None, "d_img_feat": None, "d_text_in": None, "relu_margin": t.relu_margin,
+           "relu_margin_rows": t.relu_margin_rows}
     if labels is None and dlogits is None:
         return out
     if dlogits is None:

@@ -20,6 +20,15 @@ def rel_err(a, b):
     return d / s if s > 0 else d
 
 
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2 over the whole tensor (reported next to the max-norm figure: DESIGN.md section 5)."""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    n = np.linalg.norm(b)
+    d = np.linalg.norm(a - b)
+    return d / n if n > 0 else d
+
+
 def load_golden(name):
     return np.load(os.path.join(C.GOLDEN_DIR, name + ".npz"), allow_pickle=False)
 

@@ -79,9 +79,16 @@ def test_tab_transformer_text_mode():
 
 def test_backbone_modes():
     from fusion_b200.backbones import loadModels
-    enc, width = loadModels.loadModelImageEncoder("resnet-18", 512, "frozen_weights")
+    # no network here: the pretrained weights the reference asks for cannot be fetched, and a silent random-init
+    # fallback is refused - random init is an explicit opt-in ("random:" prefix or FB200_ALLOW_RANDOM_BACKBONE=1)
+    import os
+    if os.environ.get("FB200_ALLOW_RANDOM_BACKBONE", "0") != "1":
+        with pytest.raises(RuntimeError, match="pretrained weights could not be loaded"):
+            loadModels.loadModelImageEncoder("resnet-18", 512, "frozen_weights")
+    with pytest.warns(UserWarning, match="random-init backbone"):
+        enc, width = loadModels.loadModelImageEncoder("random:resnet-18", 512, "frozen_weights")
     assert width == 512 and not any(p.requires_grad for p in enc.parameters())
-    with pytest.raises(ValueError):
-        loadModels.loadModelImageEncoder("resnet-18", 512, "false")        # conf/.env.test:8 pitfall, same error as the reference
+    with pytest.raises(ValueError), pytest.warns(UserWarning):
+        loadModels.loadModelImageEncoder("random:resnet-18", 512, "false")        # conf/.env.test:8 pitfall, same error as the reference
     with pytest.raises(ValueError):
         loadModels.loadModelImageEncoder("not-a-backbone", 512, "frozen_weights")
