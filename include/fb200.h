@@ -77,6 +77,7 @@ enum fb200_mechanism {
 #define FB200_FLAG_NEED_DTEXT  2   /* backward also produces d(text_in) (trainable encoder)  */
 #define FB200_FLAG_FORCE_SIMT  4   /* never use the tcgen05 GEMM (exact-fp32 FFMA everywhere) */
 #define FB200_FLAG_FORCE_TC    8   /* use the tcgen05 GEMM wherever its shape rules allow     */
+#define FB200_FLAG_NO_MEGA    32   /* small fp32 batches: keep the per-op kernels instead of the persistent step kernel */
 #define FB200_FLAG_ONE_STREAM 16   /* launch everything on the caller's stream (default: the metadata chain of large
                                       batches runs on an internal side stream, forked from and joined back into the
                                       caller's stream inside the call - graph-capturable, invisible to the caller) */
@@ -171,6 +172,10 @@ int fb200_debug_gemm_replay(const fb200_desc* d, const void* const* params, cons
  * off for every kernel launched afterwards; returns the previous setting. */
 int fb200_debug_set_pdl(int on);
 int fb200_debug_tc_trace(void* device_buf);
+/* debug: clock64 stamps of CTA 0 of the persistent step kernel (>= 2 + 2 * stages int64; NULL disables), and that kernel
+ * with `nstages` empty stages (launch + grid-barrier cost alone; ws256: 256 bytes of device memory) */
+int fb200_debug_mega_trace(void* device_buf);
+int fb200_debug_mega_barriers(int nstages, void* ws256, void* stream);
 
 /* rng_state[1] += increment, on `stream` (one tiny kernel; graph-capturable). */
 int fb200_rng_advance(void* rng_state, uint64_t increment, void* stream);

@@ -34,11 +34,14 @@ __device__ __forceinline__ float tf32_round(float x) {
 }
 
 // ---- scalar access ----------------------------------------------------------------
+// Activations and their gradients are read with ld.global.cg (L2 only): inside the persistent step kernel (mega.cuh) they
+// were written by OTHER CTAs of the same launch a grid barrier earlier, which the non-coherent path (__ldg) does not
+// allow; the stand-alone row kernels stream every element once, so bypassing L1 costs them nothing.
 __device__ __forceinline__ float ld1(const TRef& t, int64_t r, int c) {
   int64_t i = r * t.ld + c;
-  if (t.fmt == FMT_F32) return __ldg((const float*)t.p + i);
-  if (t.fmt == FMT_PAIR) return __ldg((const float*)t.p + i) + __ldg((const float*)t.p + t.plane + i);
-  return __bfloat162float(((const __nv_bfloat16*)t.p)[i]);
+  if (t.fmt == FMT_F32) return __ldcg((const float*)t.p + i);
+  if (t.fmt == FMT_PAIR) return __ldcg((const float*)t.p + i) + __ldcg((const float*)t.p + t.plane + i);
+  return __bfloat162float(__ushort_as_bfloat16(__ldcg((const unsigned short*)t.p + i)));
 }
 __device__ __forceinline__ void st1(const TRef& t, int64_t r, int c, float v) {
   int64_t i = r * t.ld + c;
@@ -50,13 +53,13 @@ __device__ __forceinline__ void st1(const TRef& t, int64_t r, int c, float v) {
 // ---- 4-wide access (column multiple of 4, 16-byte aligned rows) ----------------------
 __device__ __forceinline__ float4 ld4(const TRef& t, int64_t r, int c) {
   int64_t i = r * t.ld + c;
-  if (t.fmt == FMT_F32) return __ldg((const float4*)((const float*)t.p + i));
+  if (t.fmt == FMT_F32) return __ldcg((const float4*)((const float*)t.p + i));
   if (t.fmt == FMT_PAIR) {
-    float4 h = __ldg((const float4*)((const float*)t.p + i));
-    float4 l = __ldg((const float4*)((const float*)t.p + t.plane + i));
+    float4 h = __ldcg((const float4*)((const float*)t.p + i));
+    float4 l = __ldcg((const float4*)((const float*)t.p + t.plane + i));
     return make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
   }
-  uint2 raw = __ldg((const uint2*)((const __nv_bfloat16*)t.p + i));
+  uint2 raw = __ldcg((const uint2*)((const __nv_bfloat16*)t.p + i));
   __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
   __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
   float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);

@@ -4,6 +4,7 @@
 #include "rowwise.cuh"
 #include "tc_gemm.cuh"
 #include "attention.cuh"
+#include "mega.cuh"
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -72,6 +73,33 @@ struct Ctx {
   // two-lane execution (Plan::two_lanes): lane 0 = the caller's stream, lane 1 = a side stream for the metadata chain
   cudaStream_t lane_st[2] = {nullptr, nullptr};
   void* mid_event = nullptr;  // fb200_head_train_step_dp: recorded once every gradient below Plan::dp_split is final
+  // persistent step kernel (Plan::use_mega): the executors emit ops into `mega` instead of launching kernels.  Stage in which
+  // a buffer is complete: vready per activation value, gready per activation gradient, pready per parameter gradient.
+  MegaBuilder* mega = nullptr;
+  std::vector<int> vready, gready; int pready[NUM_SLOTS] = {};
+  int vr(int b) const { return b >= 0 ? vready[b] : 0; }
+  int gr(int b) const { return b >= 0 ? gready[b] : 0; }
+  // Row ops that only depend on the SAME rows of the row op emitted right before them (LayerNorm -> classifier head -> cross
+  // entropy -> their backward) run chained inside one task of the step kernel instead of one grid-wide stage each.
+  struct LastRow { size_t nrow = 0, ngemm = 0; int stage = -1, tiles = 0; int vbuf = -1; int gbuf[3] = {-1, -1, -1}; } lastrow;
+  struct Dep { int ready; int buf; bool is_grad; };
+  // stage of a warp-per-row op with the given dependencies; `chain` = it can run in the previous row op's task
+  int row_stage(std::initializer_list<Dep> deps, int tiles, bool mappable, bool& chain) const {
+    int all = 0, other = 0; bool hit = false;
+    for (const Dep& d : deps) {
+      if (d.buf < 0) continue;
+      all = std::max(all, d.ready);
+      const bool from_last = d.is_grad ? (d.buf == lastrow.gbuf[0] || d.buf == lastrow.gbuf[1] || d.buf == lastrow.gbuf[2]) : (d.buf == lastrow.vbuf);
+      if (from_last && d.ready == lastrow.stage) hit = true; else other = std::max(other, d.ready);
+    }
+    chain = mega && mappable && hit && lastrow.stage >= 1 && lastrow.nrow == mega->r.size() && lastrow.ngemm == mega->g.size() &&
+            tiles == lastrow.tiles && other <= lastrow.stage - 1;
+    return chain ? lastrow.stage : 1 + all;
+  }
+  void row_emitted(int stage, int tiles, bool mappable, int vbuf, int g0 = -1, int g1 = -1, int g2 = -1) {
+    lastrow.nrow = mega->r.size(); lastrow.ngemm = mega->g.size(); lastrow.stage = mappable ? stage : -1; lastrow.tiles = tiles;
+    lastrow.vbuf = vbuf; lastrow.gbuf[0] = g0; lastrow.gbuf[1] = g1; lastrow.gbuf[2] = g2;
+  }
 
   TRef value(const View& v) const {
     const Act& a = p.acts[v.buf];
@@ -185,7 +213,8 @@ static TRef weight_operand(const Ctx& c, const Op& o) {
 
 static int run_forward(Ctx& c) {
   const Plan& p = c.p; const int B = p.d.B;
-  if (p.splitk_bytes && !c.gemm_only) CUDA_OK(cudaMemsetAsync(c.ws + p.counters_off, 0, 4096 * sizeof(unsigned), c.st));
+  if (c.mega) { c.vready.assign(p.acts.size(), 0); }
+  if (p.splitk_bytes && !c.gemm_only && !c.mega) CUDA_OK(cudaMemsetAsync(c.ws + p.counters_off, 0, 4096 * sizeof(unsigned), c.st));
   for (size_t base = 0; base < p.wprep.size(); base += 32) {
     PrepArgs a{}; a.fmt = p.fmt; a.nseg = 0;
     for (size_t i = base; i < p.wprep.size() && a.nseg < 32; ++i) {
@@ -201,6 +230,8 @@ static int run_forward(Ctx& c) {
   for (const Op& o : p.ops) {
     c.st = c.lane_st[o.lane];
     for (int b : {o.in0.buf, o.in1.buf, o.in2.buf}) { int rc = ls.wait_for(o.lane, b); if (rc != FB200_OK) return rc; }
+    const int mst = c.mega ? 1 + std::max(c.vr(o.in0.buf), std::max(c.vr(o.in1.buf), c.vr(o.in2.buf))) : 0;   // stage of this op in the step kernel
+    int mout = mst;                                                                                            // stage after which its output is complete
     switch (o.kind) {
       case OP_CAST: {
         const TRef src = c.value(o.in0);
@@ -223,6 +254,13 @@ static int run_forward(Ctx& c) {
           // classifier head: warp-per-row kernel instead of a >90% padded GEMM tile
           SmallNArgs a{}; a.x = c.value(o.in0); a.y = c.value(o.out); a.W = c.param(o.w_slot, (int64_t)o.w_row0 * o.in0.cols);
           a.bias = c.param(o.b_slot, o.w_row0); a.B = B; a.K = o.in0.cols; a.C = o.out.cols;
+          if (c.mega) {
+            const int tiles = (B + ROW_WARPS - 1) / ROW_WARPS; bool chain;
+            mout = c.row_stage({{c.vr(o.in0.buf), o.in0.buf, false}}, tiles, true, chain);
+            c.mega->add_row(MR_SMALLN_FWD, mout, tiles, chain).u.smalln = a;
+            c.row_emitted(mout, tiles, true, o.out.buf);
+            break;
+          }
           CUDA_OK(launch_smalln_fwd(a, c.dev.num_sms, c.st));
           break;
         }
@@ -230,12 +268,20 @@ static int run_forward(Ctx& c) {
         g.A = c.value(o.in0); g.B = make_ref((void*)c.param(o.w_slot, (int64_t)o.w_row0 * o.in0.cols), o.in0.cols, FMT_F32);
         g.C = c.value(o.out); g.M = B; g.N = o.out.cols; g.K = o.in0.cols; g.a_kc = 1; g.b_kc = 1;
         g.bias = c.param(o.b_slot, o.w_row0); g.relu = o.relu; g.mask_src.p = nullptr; g.accumulate = 0; g.split_k = 1; g.colsum_a = nullptr;
+        if (c.mega) { mout = c.mega->add_gemm(g, mst); break; }
         c.enable_fixup(g, o.lane);
         CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
       } break;
       case OP_LNRD: {
         LnrdArgs a{}; a.x = c.value(o.in0); a.y = c.value(o.out); a.gamma = c.param(o.ln_w[0]); a.beta = c.param(o.ln_b[0]);
         a.stats = (float*)(c.ws + o.stats_off); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
+        if (c.mega) {
+          const int tiles = MegaBuilder::row_tiles(B, a.N); bool chain;
+          mout = c.row_stage({{c.vr(o.in0.buf), o.in0.buf, false}}, tiles, a.N <= 512, chain);
+          c.mega->add_row(MR_LNRD_FWD, mout, tiles, chain).u.lnrd = a;
+          c.row_emitted(mout, tiles, a.N <= 512, o.out.buf);
+          break;
+        }
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) pdl_launch(lnrd_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
@@ -243,6 +289,7 @@ static int run_forward(Ctx& c) {
       } break;
       case OP_GATE: {
         GateArgs a{}; a.x = c.value(o.in0); a.z = c.value(o.in1); a.y = c.value(o.out); a.B = B; a.N = o.out.cols;
+        if (c.mega) { c.mega->add_row(MR_GATE_FWD, mst, MegaBuilder::row_tiles(B, a.N)).u.gate = a; break; }
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) pdl_launch(gate_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
@@ -252,6 +299,7 @@ static int run_forward(Ctx& c) {
         GrbArgs a{}; a.q = c.value(o.in0); a.a = c.value(o.in1); a.z = c.value(o.in2); a.y = c.value(o.out);
         a.gamma = c.param(o.ln_w[0]); a.beta = c.param(o.ln_b[0]); a.stats = (float*)(c.ws + o.stats_off);
         a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
+        if (c.mega) { c.mega->add_row(MR_GRB_FWD, mst, MegaBuilder::row_tiles(B, a.N)).u.grb = a; break; }
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) pdl_launch(grb_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
@@ -261,6 +309,7 @@ static int run_forward(Ctx& c) {
         MetaArgs a{}; a.v = c.value(o.in0); a.f = c.value(o.in1); a.g = c.value(o.in2); a.y = c.value(o.out);
         a.gamma_f = c.param(o.ln_w[0]); a.beta_f = c.param(o.ln_b[0]); a.gamma_g = c.param(o.ln_w[1]); a.beta_g = c.param(o.ln_b[1]);
         a.stats = (float*)(c.ws + o.stats_off); a.B = B; a.N = o.out.cols;
+        if (c.mega) { c.mega->add_row(MR_META_FWD, mst, MegaBuilder::row_tiles(B, a.N)).u.meta = a; break; }
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) pdl_launch(meta_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
@@ -269,6 +318,7 @@ static int run_forward(Ctx& c) {
       default: return FB200_EBADARG;
     }
     CUDA_OK(cudaGetLastError());
+    if (c.mega) c.vready[o.out.buf] = std::max(c.vready[o.out.buf], mout);
     { int rc = ls.touched(o.lane, {o.out.buf}); if (rc != FB200_OK) return rc; }
   }
   c.st = main_st;
@@ -278,6 +328,10 @@ static int run_forward(Ctx& c) {
 // ------------------------------------------------------------------------------- backward
 static int run_backward(Ctx& c) {
   const Plan& p = c.p; const int B = p.d.B;
+  if (c.mega) {                     // a stand-alone backward pass starts with every value and dlogits complete (stage 0)
+    if (c.vready.empty()) c.vready.assign(p.acts.size(), 0);
+    if (c.gready.empty()) c.gready.assign(p.acts.size(), 0);
+  }
   if (!c.gemm_only) CUDA_OK(cudaMemsetAsync(c.grads, 0, (size_t)p.grad_elems * sizeof(float), c.st));
   std::vector<char> gwritten(p.acts.size(), 0);       // has the gradient buffer been written yet?
   std::vector<char> pwritten(NUM_SLOTS, 0);           // has this weight gradient been written yet?
@@ -298,6 +352,8 @@ static int run_backward(Ctx& c) {
     return true;
   };
 
+  struct MegaDw { GemmArgs g; int slot; int dy_ready; };
+  std::vector<MegaDw> mega_dw;
   std::vector<ColsumSeg> colsums;
   std::vector<std::vector<TcGroupProblem>> dw_round;   // [k]: k-th application of a weight (k > 0 accumulates, in launch order)
   std::vector<int> tc_uses(NUM_SLOTS, 0);
@@ -358,6 +414,15 @@ static int run_backward(Ctx& c) {
             a.dx = c.grad(o.dx_view); a.dx_accumulate = is_written(o.dx_view);
             if (p.acts[o.in0.buf].relu_out) a.mask_src = c.value(o.in0);
           }
+          if (c.mega) {
+            const int tiles = (B + ROW_WARPS - 1) / ROW_WARPS; bool chain;
+            const int st = c.row_stage({{c.gr(o.out.buf), o.out.buf, true}, {a.dx.p ? c.gr(o.dx_view.buf) : 0, a.dx.p ? o.dx_view.buf : -1, true}}, tiles, true, chain);
+            c.mega->add_row(MR_SMALLN_BWD, st, tiles, chain).u.smalln = a;
+            if (a.dx.p) { c.gready[o.dx_view.buf] = st; set_written(o.dx_view); }
+            c.row_emitted(st, tiles, true, -1, a.dx.p ? o.dx_view.buf : -1);
+            pwritten[o.w_slot] = 1;
+            break;
+          }
           CUDA_OK(launch_smalln_bwd(a, c.dev.num_sms, c.st));
           pwritten[o.w_slot] = 1;
           if (a.dx.p) set_written(o.dx_view);
@@ -369,7 +434,9 @@ static int run_backward(Ctx& c) {
         g.C = make_ref(c.pgrad(o.w_slot, (int64_t)o.w_row0 * K), K, FMT_F32);
         g.M = N; g.N = K; g.K = B; g.bias = nullptr; g.relu = 0; g.mask_src.p = nullptr;
         g.accumulate = pwritten[o.w_slot]; g.split_k = 0; g.colsum_a = c.pgrad(o.b_slot, o.w_row0);
-        CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
+        if (c.mega) {               // the weight gradient has no consumer: all of them run after the dX chain, as the last stage(s)
+          mega_dw.push_back({g, o.w_slot, c.gr(o.out.buf)});
+        } else CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
         pwritten[o.w_slot] = 1;
         // dX[B,K] (+)= dY W, masked by the producer's ReLU when the input came out of Linear+ReLU
         if (grad_wanted(o.dx_view)) {
@@ -379,8 +446,13 @@ static int run_backward(Ctx& c) {
           h.mask_src.p = nullptr;
           if (p.acts[o.in0.buf].relu_out) h.mask_src = c.value(o.in0);
           h.accumulate = is_written(o.dx_view); h.split_k = 1; h.colsum_a = nullptr;
-          c.enable_fixup(h, o.lane);
-          CUDA_OK(launch_simt_gemm(h, c.dev.num_sms, c.st));
+          if (c.mega) {
+            const int st = 1 + std::max(c.gr(o.out.buf), c.gr(o.dx_view.buf));
+            c.mega->add_gemm(h, st); c.gready[o.dx_view.buf] = st;
+          } else {
+            c.enable_fixup(h, o.lane);
+            CUDA_OK(launch_simt_gemm(h, c.dev.num_sms, c.st));
+          }
           set_written(o.dx_view);
         }
       } break;
@@ -389,6 +461,13 @@ static int run_backward(Ctx& c) {
         a.gamma = c.param(o.ln_w[0]); a.stats = (float*)(c.ws + o.stats_off);
         a.dgamma = c.pgrad(o.ln_w[0]); a.dbeta = c.pgrad(o.ln_b[0]); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
         if (is_written(o.in0)) return FB200_EUNSUPPORTED;     // LN input has exactly one consumer in every program
+        if (c.mega) {
+          const int tiles = MegaBuilder::row_tiles(B, a.N); bool chain;
+          const int st = c.row_stage({{c.gr(o.out.buf), o.out.buf, true}, {c.gr(o.in0.buf), o.in0.buf, true}}, tiles, a.N <= 512, chain);
+          c.mega->add_row(MR_LNRD_BWD, st, tiles, chain).u.lnrd = a; c.gready[o.in0.buf] = st;
+          c.row_emitted(st, tiles, a.N <= 512, -1, o.in0.buf);
+          set_written(o.in0); break;
+        }
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) pdl_launch(lnrd_bwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
@@ -399,6 +478,11 @@ static int run_backward(Ctx& c) {
         GateArgs a{}; a.x = c.value(o.in0); a.z = c.value(o.in1); a.dy = c.grad(o.out); a.dz = c.grad(o.in1); a.dx = c.grad(o.in0);
         a.dx_accumulate = is_written(o.in0); a.B = B; a.N = o.out.cols;
         if (is_written(o.in1)) return FB200_EUNSUPPORTED;
+        if (c.mega) {
+          const int st = 1 + std::max(c.gr(o.out.buf), std::max(c.gr(o.in0.buf), c.gr(o.in1.buf)));
+          c.mega->add_row(MR_GATE_BWD, st, MegaBuilder::row_tiles(B, a.N)).u.gate = a; c.gready[o.in0.buf] = c.gready[o.in1.buf] = st;
+          set_written(o.in0); set_written(o.in1); break;
+        }
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) pdl_launch(gate_bwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
@@ -411,6 +495,12 @@ static int run_backward(Ctx& c) {
         a.gamma = c.param(o.ln_w[0]); a.stats = (float*)(c.ws + o.stats_off);
         a.dgamma = c.pgrad(o.ln_w[0]); a.dbeta = c.pgrad(o.ln_b[0]); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
         if (is_written(o.in1) || is_written(o.in2)) return FB200_EUNSUPPORTED;
+        if (c.mega) {
+          const int st = 1 + std::max(std::max(c.gr(o.out.buf), c.gr(o.in0.buf)), std::max(c.gr(o.in1.buf), c.gr(o.in2.buf)));
+          c.mega->add_row(MR_GRB_BWD, st, MegaBuilder::row_tiles(B, a.N)).u.grb = a;
+          c.gready[o.in0.buf] = c.gready[o.in1.buf] = c.gready[o.in2.buf] = st;
+          set_written(o.in0); set_written(o.in1); set_written(o.in2); break;
+        }
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) pdl_launch(grb_bwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
@@ -427,6 +517,13 @@ static int run_backward(Ctx& c) {
         a.dgamma_f = c.pgrad(o.ln_w[0]); a.dbeta_f = c.pgrad(o.ln_b[0]); a.dgamma_g = c.pgrad(o.ln_w[1]); a.dbeta_g = c.pgrad(o.ln_b[1]);
         a.B = B; a.N = o.out.cols;
         if (is_written(o.in1) || is_written(o.in2)) return FB200_EUNSUPPORTED;
+        if (c.mega) {
+          const int st = 1 + std::max(std::max(c.gr(o.out.buf), a.dv.p ? c.gr(o.in0.buf) : 0), std::max(c.gr(o.in1.buf), c.gr(o.in2.buf)));
+          c.mega->add_row(MR_META_BWD, st, MegaBuilder::row_tiles(B, a.N)).u.meta = a;
+          if (a.dv.p) { c.gready[o.in0.buf] = st; set_written(o.in0); }
+          c.gready[o.in1.buf] = c.gready[o.in2.buf] = st;
+          set_written(o.in1); set_written(o.in2); break;
+        }
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) pdl_launch(meta_bwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
@@ -441,6 +538,17 @@ static int run_backward(Ctx& c) {
   }
   c.st = main_st;
   { int rc = ls.join(c); if (rc != FB200_OK) return rc; }
+  if (c.mega) {
+    // Weight gradients interleaved with the dX chain doubled the tasks of every backward stage (two rounds per CTA, each stage
+    // as long as its slowest CTA); as ONE final stage they are ~7 back-to-back tasks per CTA of the same hot loop.
+    int last = 0;
+    for (int b = 0; b < (int)c.gready.size(); ++b) last = std::max(last, c.gready[b]);
+    for (auto& m : mega_dw) last = std::max(last, m.dy_ready);
+    for (auto& m : mega_dw) {
+      const int st = std::max(last + 1, c.pready[m.slot] + 1);       // a weight applied twice accumulates: its second gradient runs a stage later
+      c.mega->add_gemm(m.g, st); c.pready[m.slot] = st;
+    }
+  }
   // Every dY is written now.  The bias gradients (HBM-bound column sums over all dY buffers) go to the side stream and run
   // next to the grouped weight-gradient launch (tensor-bound) instead of after it.
   { int rc = ls.begin(c, 0); if (rc != FB200_OK) return rc; }
@@ -518,6 +626,28 @@ static int check_optional_device(std::initializer_list<const void*> ptrs, const 
   for (const void* q : ptrs) if (q && !is_device_ptr_cached(q)) return FB200_EUNSUPPORTED;
   if (masks) for (int i = 0; i < FB200_NUM_DROPOUT_SITES; ++i) if (masks[i] && !is_device_ptr_cached(masks[i])) return FB200_EUNSUPPORTED;
   return FB200_OK;
+}
+
+// Persistent step kernel: emit the weighted cross entropy as a row task (train step) and launch the finished program.
+static void mega_emit_ce(Ctx& c, const void* logits, const int64_t* labels, const float* class_w, const float* denom, float* loss_out, void* dlogits) {
+  const Plan& p = c.p;
+  const int tiles = (p.d.B + ROW_WARPS - 1) / ROW_WARPS; bool chain;
+  const int st = c.row_stage({{c.vr(p.logits.buf), p.logits.buf, false}}, tiles, true, chain);
+  c.mega->add_row(MR_CE, st, tiles, chain).u.ce = CeArgs{(const float*)logits, labels, class_w, denom, loss_out, (float*)dlogits, p.d.B, p.d.C};
+  c.gready.assign(p.acts.size(), 0);
+  c.gready[p.logits.buf] = st;
+  c.row_emitted(st, tiles, true, -1, p.logits.buf);
+}
+static int mega_finish(Ctx& c) {
+  static thread_local MegaProg prog;             // 25 KB: not on the stack of autograd's worker thread
+  int rc = c.mega->finalize(prog, (unsigned*)(c.ws + c.p.mega_bar_off));
+  if (rc != FB200_OK) return rc;
+  return mega_launch(prog, c.dev.num_sms, c.st);
+}
+static void mega_begin(Ctx& c, MegaBuilder& mb) {
+  if (!c.p.use_mega || c.gemm_only) return;
+  mb.scratch = c.ws + c.p.splitk_off; mb.scratch_bytes = c.p.splitk_bytes;
+  c.mega = &mb;
 }
 
 static int ce_launch(const void* logits, const int64_t* labels, const float* class_w, const float* denom, int B, int C,
@@ -620,6 +750,11 @@ int fb200_launch_count(const fb200_desc* d, int* forward, int* backward) {
   if (!d) return FB200_EBADARG;
   Plan p; int rc = build_plan(*d, p); if (rc != FB200_OK) return rc;
   int f = 0, b = 0;
+  if (p.use_mega) {                  // one persistent kernel per pass (a fused train step is ONE launch: the caller counts forward only)
+    if (forward) *forward = 1;
+    if (backward) *backward = 1;
+    return FB200_OK;
+  }
   const bool need_dimg = d->flags & FB200_FLAG_NEED_DIMG, need_dtxt = d->flags & FB200_FLAG_NEED_DTEXT;
   f += (int)((p.wprep.size() + 31) / 32);
   int ntc = 0, rounds = 0; int uses[NUM_SLOTS] = {};
@@ -664,6 +799,18 @@ __global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { pdl_sync(); 
 /* debug: device buffer of >= 8*k_blocks int64 receiving pipeline time stamps of CTA (0,0,0) of every tcgen05 GEMM launched afterwards; NULL disables */
 int fb200_debug_set_pdl(int on) { const int prev = pdl_enabled() ? 1 : 0; pdl_flag() = on ? 1 : 0; return prev; }
 int fb200_debug_tc_trace(void* device_buf) { tc_trace_buffer() = (long long*)device_buf; return FB200_OK; }
+/* debug: device buffer of >= 2 + 2 * stages int64 receiving clock64 stamps of CTA 0 of the persistent step kernel
+ * ([0] entry, [1 + 2s] own tasks of stage s done, [2 + 2s] barrier after stage s passed); NULL disables */
+int fb200_debug_mega_trace(void* device_buf) { mega_trace_buffer() = (long long*)device_buf; return FB200_OK; }
+/* debug: the step kernel with `nstages` EMPTY stages - the cost of the launch and of the grid barriers alone */
+int fb200_debug_mega_barriers(int nstages, void* ws256, void* stream) {
+  if (nstages < 1 || nstages > MEGA_MAX_STAGES || !ws256) return FB200_EBADARG;
+  DeviceInfo dev; int rc = get_device_info(dev); if (rc != FB200_OK) return rc;
+  static thread_local MegaProg prog;
+  for (int s = 0; s < nstages; ++s) prog.st[s] = MStage{0, 0, 0, 0};
+  prog.nstages = nstages; prog.ngemm = 0; prog.nrow = 0; prog.barrier = (unsigned*)ws256; prog.trace = mega_trace_buffer(); prog.pad_ = 0;
+  return mega_launch(prog, dev.num_sms, (cudaStream_t)stream);
+}
 
 
 
@@ -727,7 +874,9 @@ int fb200_rng_advance(void* rng_state, uint64_t increment, void* stream) {
 int fb200_debug_gemm_replay(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
                             void* logits, void* grads, void* ws, void* stream) {
   Plan plan; DeviceInfo dev;
-  int rc = check_common(d, params, img_feat, text_in, ws, plan, dev);
+  if (!d) return FB200_EBADARG;
+  fb200_desc dd = *d; dd.flags |= FB200_FLAG_NO_MEGA;          // the replay times the per-op GEMM kernels
+  int rc = check_common(&dd, params, img_feat, text_in, ws, plan, dev);
   if (rc != FB200_OK) return rc;
   if (!logits || !grads) return FB200_EBADARG;
   char* w = (char*)ws;
@@ -769,7 +918,10 @@ int fb200_head_forward(const fb200_desc* d, const void* const* params, const voi
   if (!logits) return FB200_EBADARG;
   rc = check_optional_device({rng_state, logits}, masks); if (rc != FB200_OK) return rc;
   Ctx c{plan, params, img_feat, text_in, logits, nullptr, nullptr, nullptr, nullptr, masks, seed, offset, (const uint64_t*)rng_state, (char*)ws, (cudaStream_t)stream, dev};
-  return run_forward(c);
+  MegaBuilder mb; mega_begin(c, mb);
+  rc = run_forward(c);
+  if (rc != FB200_OK || !c.mega) return rc;
+  return mega_finish(c);
 }
 
 int fb200_head_backward(const fb200_desc* d, const void* const* params, const void* img_feat, const void* text_in,
@@ -785,7 +937,10 @@ int fb200_head_backward(const fb200_desc* d, const void* const* params, const vo
   Ctx c{plan, params, img_feat, text_in, nullptr, dlogits,
         (d->flags & FB200_FLAG_NEED_DIMG) ? d_img_feat : nullptr, (d->flags & FB200_FLAG_NEED_DTEXT) ? d_text_in : nullptr,
         (float*)grads, masks, seed, offset, (const uint64_t*)rng_state, (char*)ws, (cudaStream_t)stream, dev};
-  return run_backward(c);
+  MegaBuilder mb; mega_begin(c, mb);
+  rc = run_backward(c);
+  if (rc != FB200_OK || !c.mega) return rc;
+  return mega_finish(c);
 }
 
 int fb200_cross_entropy(const void* logits, const int64_t* labels, const float* class_w, const float* denom, int B, int C,
@@ -828,8 +983,16 @@ int fb200_head_train_step_dp(const fb200_desc* d, const void* const* params, con
         (d->flags & FB200_FLAG_NEED_DIMG) ? d_img_feat : nullptr, (d->flags & FB200_FLAG_NEED_DTEXT) ? d_text_in : nullptr,
         (float*)grads, masks, seed, offset, (const uint64_t*)rng_state, w, (cudaStream_t)stream, dev};
   c.mid_event = mid_event;
+  MegaBuilder mb; mega_begin(c, mb);
   rc = run_forward(c);
   if (rc != FB200_OK) return rc;
+  if (c.mega) {
+    CUDA_OK(cudaMemsetAsync(loss_out, 0, 3 * sizeof(float), c.st));      // the row-parallel cross entropy accumulates the loss with atomics
+    mega_emit_ce(c, logits, labels, class_w, denom, loss_out, dlog);
+    rc = run_backward(c);
+    if (rc != FB200_OK) return rc;
+    return mega_finish(c);
+  }
   rc = ce_launch(logits, labels, class_w, denom, d->B, d->C, loss_out, dlog, c.st);
   if (rc != FB200_OK) return rc;
   return run_backward(c);

@@ -196,7 +196,12 @@ int build_plan(const fb200_desc& d, Plan& p) {
   // engine policy: bf16 always rides the tensor cores; fp32 switches to the 3xTF32 tensor path above 32 rows (measured
   // with the r01 kernels: 0.365 vs 0.371 ms per step at B=32, 0.374 vs 0.402 at 64, 0.391 vs 0.494 at 128; up to 32 rows
   // the exact FFMA kernel with split-K fix-up costs the same and is bit-faithful fp32)
-  p.use_tc = !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B > 32);
+  // fp32 batches up to 64 rows (the reference's own BATCH_SIZE=32, conf/.env.test:2): one persistent cooperative kernel
+  // walks the whole op program (mega.cuh) - exact FFMA arithmetic, one launch per pass.  FB200_MEGA=0 / FB200_FLAG_NO_MEGA
+  // keep the per-op kernels (A/B measurements, and the FFMA / tcgen05 engines stay covered by the tests through FORCE_*).
+  static const bool mega_env_off = [] { const char* e = getenv("FB200_MEGA"); return e && e[0] == '0'; }();
+  p.use_mega = d.dtype == FB200_F32 && d.B <= 64 && !(d.flags & (FB200_FLAG_FORCE_SIMT | FB200_FLAG_FORCE_TC | FB200_FLAG_NO_MEGA)) && !mega_env_off;
+  p.use_tc = !p.use_mega && !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B > 32);
   p.fmt = d.dtype == FB200_BF16 ? FMT_BF16 : FMT_F32;    // fp32-strict keeps everything fp32 in memory (hi/lo split happens in smem)
 
   Builder b(p);
@@ -336,7 +341,7 @@ int build_plan(const fb200_desc& d, Plan& p) {
       color[o.out.buf] |= c;
     }
     static const bool env_off = [] { const char* e = getenv("FB200_LANES"); return e && e[0] == '0'; }();   // A/B measurements
-    p.two_lanes = n1 > 0 && n1 < (int)p.ops.size() && !(d.flags & FB200_FLAG_ONE_STREAM) && !env_off;
+    p.two_lanes = n1 > 0 && n1 < (int)p.ops.size() && !(d.flags & FB200_FLAG_ONE_STREAM) && !env_off && !p.use_mega;
     if (!p.two_lanes) for (auto& o : p.ops) o.lane = 0;
   }
 
@@ -403,6 +408,7 @@ int build_plan(const fb200_desc& d, Plan& p) {
   }
   // small batches on the FFMA path: split-K fix-up scratch (partial tiles) + per-tile arrival counters
   if (!p.use_tc || d.B <= 128) { p.splitk_off = cur; p.splitk_bytes = (size_t)16 << 20; cur = align(cur + p.splitk_bytes); p.counters_off = cur; cur = align(cur + 4096 * sizeof(unsigned)); }
+  if (p.use_mega) { p.mega_bar_off = cur; cur = align(cur + 256); }
   // tail: dlogits of the fused train step (exec.cu addresses it from the end)
   cur = align(cur + (size_t)d.B * d.C * sizeof(float));
   p.ws_bytes = cur + 256;

@@ -74,6 +74,8 @@ struct Plan {
   fb200_desc d;
   bool use_tc = false;               // tcgen05 GEMMs enabled for this call
   bool two_lanes = false;            // image chain and metadata chain are launched on two streams (exec.cu)
+  bool use_mega = false;             // small fp32 batches: the whole pass runs as ONE persistent cooperative kernel (mega.cuh)
+  size_t mega_bar_off = 0;           // grid-barrier counter of that kernel in the workspace
   std::vector<WPrep> wprep;
   int fmt = FMT_F32;                 // GEMM operand format of workspace activations (F32 / PAIR / BF16)
   std::vector<Act> acts;

@@ -22,9 +22,11 @@ constexpr float LN_EPS = 1e-5f;
 template <int TPR>
 struct Grp {
   int t, row0, rstep;
-  __device__ __forceinline__ Grp() {
-    if (TPR == 32) { t = threadIdx.x & 31; row0 = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5); rstep = gridDim.x * ROW_WARPS; }
-    else { t = threadIdx.x; row0 = blockIdx.x; rstep = gridDim.x; }
+  // bid / nblk: index of this CTA among the CTAs that share the op (blockIdx.x / gridDim.x for a stand-alone launch,
+  // tile / tiles when the op is one task of the persistent step kernel - mega.cuh)
+  __device__ __forceinline__ Grp(int bid, int nblk) {
+    if (TPR == 32) { t = threadIdx.x & 31; row0 = bid * ROW_WARPS + (threadIdx.x >> 5); rstep = nblk * ROW_WARPS; }
+    else { t = threadIdx.x; row0 = bid; rstep = nblk; }
   }
   // sums of a and b over the group (all threads of the group must call)
   __device__ __forceinline__ float2 sum2(float a, float b, float2* scratch) const {
@@ -122,8 +124,8 @@ struct LnrdArgs {
 };
 
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_fwd_kernel(const LnrdArgs a) { pdl_sync();
-  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+__device__ __forceinline__ void lnrd_fwd_body(const LnrdArgs& a, const int bid, const int nblk, float2* scratch, float* red) {
+  const Grp<TPR> G(bid, nblk);
   float4 gam[NV], bet[NV];
   row_load_param<NV, TPR>(G, a.gamma, a.N, gam);
   row_load_param<NV, TPR>(G, a.beta, a.N, bet);
@@ -146,6 +148,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_fwd_kernel(const LnrdArgs
     }
     row_store<NV, TPR>(G, a.y, row, a.N, v);
   }
+}
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_fwd_kernel(const LnrdArgs a) { pdl_sync();
+  __shared__ float2 scratch[ROW_WARPS];
+  lnrd_fwd_body<NV, TPR>(a, blockIdx.x, gridDim.x, scratch, nullptr);
 }
 
 // LayerNorm backward core for one row: given dyh = d(out)/d(LN output) (already multiplied by
@@ -190,9 +197,8 @@ __device__ __forceinline__ void normalize(const Grp<TPR>& G, float4 (&v)[NV], fl
 }
 
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_bwd_kernel(const LnrdArgs a) { pdl_sync();
-  __shared__ __align__(16) float red[ROW_WARPS * 512];
-  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+__device__ __forceinline__ void lnrd_bwd_body(const LnrdArgs& a, const int bid, const int nblk, float2* scratch, float* red) {
+  const Grp<TPR> G(bid, nblk);
   float4 gam[NV], dgam[NV], dbet[NV];
   row_load_param<NV, TPR>(G, a.gamma, a.N, gam);
   zero4<NV>(dgam); zero4<NV>(dbet);
@@ -216,6 +222,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_bwd_kernel(const LnrdArgs
   cta_colsum_atomic<NV, TPR>(G, dgam, a.N, a.dgamma, red);
   cta_colsum_atomic<NV, TPR>(G, dbet, a.N, a.dbeta, red);
 }
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_bwd_kernel(const LnrdArgs a) { pdl_sync();
+  __shared__ float2 scratch[ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
+  lnrd_bwd_body<NV, TPR>(a, blockIdx.x, gridDim.x, scratch, red);
+}
 
 // ------------------------------------------------------------------ gate: y = sigmoid(z) * x
 struct GateArgs {
@@ -224,8 +235,8 @@ struct GateArgs {
   int B, N;
 };
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) gate_fwd_kernel(const GateArgs a) { pdl_sync();
-  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+__device__ __forceinline__ void gate_fwd_body(const GateArgs& a, const int bid, const int nblk, float2* scratch, float* red) {
+  const Grp<TPR> G(bid, nblk);
   for (int64_t row = G.row0; row < a.B; row += G.rstep) {
     float4 x[NV], z[NV];
     row_load<NV, TPR>(G, a.x, row, a.N, x);
@@ -239,8 +250,13 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) gate_fwd_kernel(const GateArgs
   }
 }
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) gate_bwd_kernel(const GateArgs a) { pdl_sync();
-  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+__global__ void __launch_bounds__(ROW_WARPS * 32) gate_fwd_kernel(const GateArgs a) { pdl_sync();
+  __shared__ float2 scratch[ROW_WARPS];
+  gate_fwd_body<NV, TPR>(a, blockIdx.x, gridDim.x, scratch, nullptr);
+}
+template <int NV, int TPR>
+__device__ __forceinline__ void gate_bwd_body(const GateArgs& a, const int bid, const int nblk, float2* scratch, float* red) {
+  const Grp<TPR> G(bid, nblk);
   for (int64_t row = G.row0; row < a.B; row += G.rstep) {
     float4 x[NV], z[NV], dy[NV], dx[NV];
     row_load<NV, TPR>(G, a.x, row, a.N, x);
@@ -260,6 +276,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) gate_bwd_kernel(const GateArgs
     row_store<NV, TPR>(G, a.dx, row, a.N, dx);
   }
 }
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) gate_bwd_kernel(const GateArgs a) { pdl_sync();
+  __shared__ float2 scratch[ROW_WARPS];
+  gate_bwd_body<NV, TPR>(a, blockIdx.x, gridDim.x, scratch, nullptr);
+}
 
 // ------------------------------------------------------------------ gated residual + LN
 struct GrbArgs {
@@ -272,8 +293,8 @@ struct GrbArgs {
   int B, N;
 };
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p) { pdl_sync();
-  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+__device__ __forceinline__ void grb_fwd_body(const GrbArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
+  const Grp<TPR> G(bid, nblk);
   float4 gam[NV], bet[NV];
   row_load_param<NV, TPR>(G, p.gamma, p.N, gam);
   row_load_param<NV, TPR>(G, p.beta, p.N, bet);
@@ -304,9 +325,13 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p
   }
 }
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) grb_bwd_kernel(const GrbArgs p) { pdl_sync();
-  __shared__ __align__(16) float red[ROW_WARPS * 512];
-  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+__global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p) { pdl_sync();
+  __shared__ float2 scratch[ROW_WARPS];
+  grb_fwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, nullptr);
+}
+template <int NV, int TPR>
+__device__ __forceinline__ void grb_bwd_body(const GrbArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
+  const Grp<TPR> G(bid, nblk);
   float4 gam[NV], dgam[NV], dbet[NV];
   row_load_param<NV, TPR>(G, p.gamma, p.N, gam);
   zero4<NV>(dgam); zero4<NV>(dbet);
@@ -352,6 +377,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) grb_bwd_kernel(const GrbArgs p
   cta_colsum_atomic<NV, TPR>(G, dgam, p.N, p.dgamma, red);
   cta_colsum_atomic<NV, TPR>(G, dbet, p.N, p.dbeta, red);
 }
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) grb_bwd_kernel(const GrbArgs p) { pdl_sync();
+  __shared__ float2 scratch[ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
+  grb_bwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, red);
+}
 
 // ------------------------------------------------------------------ MetaBlock modulation
 struct MetaArgs {
@@ -364,8 +394,8 @@ struct MetaArgs {
   int B, N;
 };
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) meta_fwd_kernel(const MetaArgs p) { pdl_sync();
-  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+__device__ __forceinline__ void meta_fwd_body(const MetaArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
+  const Grp<TPR> G(bid, nblk);
   for (int64_t row = G.row0; row < p.B; row += G.rstep) {
     float4 f[NV], g[NV], v[NV], pr[NV];
     row_load<NV, TPR>(G, p.f, row, p.N, f);
@@ -393,11 +423,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) meta_fwd_kernel(const MetaArgs
     row_store<NV, TPR>(G, p.y, row, p.N, f);
   }
 }
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) meta_fwd_kernel(const MetaArgs p) { pdl_sync();
+  __shared__ float2 scratch[ROW_WARPS];
+  meta_fwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, nullptr);
+}
 // Backward in two sweeps per row so that at most ~6 row-vectors are live (F up to 4096).
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) meta_bwd_kernel(const MetaArgs p) { pdl_sync();
-  __shared__ __align__(16) float red[ROW_WARPS * 512];
-  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+__device__ __forceinline__ void meta_bwd_body(const MetaArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
+  const Grp<TPR> G(bid, nblk);
   float4 dgf[NV], dbf[NV], dgg[NV], dbg[NV];
   zero4<NV>(dgf); zero4<NV>(dbf); zero4<NV>(dgg); zero4<NV>(dbg);
   for (int64_t row = G.row0; row < p.B; row += G.rstep) {
@@ -448,6 +482,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) meta_bwd_kernel(const MetaArgs
   cta_colsum_atomic<NV, TPR>(G, dbf, p.N, p.dbeta_f, red);
   cta_colsum_atomic<NV, TPR>(G, dgg, p.N, p.dgamma_g, red);
   cta_colsum_atomic<NV, TPR>(G, dbg, p.N, p.dbeta_g, red);
+}
+template <int NV, int TPR>
+__global__ void __launch_bounds__(ROW_WARPS * 32) meta_bwd_kernel(const MetaArgs p) { pdl_sync();
+  __shared__ float2 scratch[ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
+  meta_bwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, red);
 }
 
 // ------------------------------------------------------------------ cross entropy
@@ -507,10 +546,10 @@ struct SmallNArgs {
   int B, K, C;
 };
 template <int MAXC>
-__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_fwd_kernel(const SmallNArgs a) { pdl_sync();
+__device__ __forceinline__ void smalln_fwd_body(const SmallNArgs& a, const int bid, const int nblk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nch = a.K / 4;
-  for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < a.B; row += (int64_t)gridDim.x * ROW_WARPS) {
+  for (int64_t row = (int64_t)bid * ROW_WARPS + warp; row < a.B; row += (int64_t)nblk * ROW_WARPS) {
     float acc[MAXC];
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) acc[c] = 0.f;
@@ -530,8 +569,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_fwd_kernel(const SmallN
     if (lane < a.C) ((float*)a.y.p)[row * a.y.ld + lane] = out + (a.bias ? __ldg(a.bias + lane) : 0.f);
   }
 }
-template <int MAXC, int CH>      // CH = 128-bit chunks of K per lane (K <= 128 * CH)
-__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallNArgs a) { pdl_sync();
+template <int MAXC>
+__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_fwd_kernel(const SmallNArgs a) { pdl_sync(); smalln_fwd_body<MAXC>(a, blockIdx.x, gridDim.x); }
+template <int MAXC, int CH>      // CH = 128-bit chunks of K per lane (K <= 128 * CH); sm_dw: [C*K + C] floats of shared memory
+__device__ __forceinline__ void smalln_bwd_body(const SmallNArgs& a, const int bid, const int nblk, float* sm_dw) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nch = a.K / 4;
   float4 dw[MAXC][CH];
@@ -540,10 +581,10 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallN
   for (int c = 0; c < MAXC; ++c) { dbacc[c] = 0.f;
 #pragma unroll
     for (int i = 0; i < CH; ++i) dw[c][i] = make_float4(0.f, 0.f, 0.f, 0.f); }
-  for (int64_t row = (int64_t)blockIdx.x * ROW_WARPS + warp; row < a.B; row += (int64_t)gridDim.x * ROW_WARPS) {
+  for (int64_t row = (int64_t)bid * ROW_WARPS + warp; row < a.B; row += (int64_t)nblk * ROW_WARPS) {
     float dl[MAXC];
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) { dl[c] = c < a.C ? __ldg((const float*)a.dy.p + row * a.dy.ld + c) : 0.f; dbacc[c] += dl[c]; }
+    for (int c = 0; c < MAXC; ++c) { dl[c] = c < a.C ? __ldcg((const float*)a.dy.p + row * a.dy.ld + c) : 0.f; dbacc[c] += dl[c]; }
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const int j = lane + 32 * i;
@@ -567,8 +608,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallN
     }
   }
   // warp partials -> CTA totals in shared memory (fast shared atomics) -> one global atomic per element per CTA
-  extern __shared__ float sm_dw[];                       // [C*K + C], zeroed below
-  const int tot = a.C * a.K + a.C;
+  const int tot = a.C * a.K + a.C;                        // sm_dw: zeroed below
   for (int i = threadIdx.x; i < tot; i += blockDim.x) sm_dw[i] = 0.f;
   __syncthreads();
 #pragma unroll
@@ -590,6 +630,11 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallN
     const float v = sm_dw[i];
     if (i < a.C * a.K) atomicAdd(a.dW + i, v); else atomicAdd(a.db + (i - a.C * a.K), v);
   }
+}
+template <int MAXC, int CH>
+__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallNArgs a) { pdl_sync();
+  extern __shared__ float smalln_dyn_smem[];
+  smalln_bwd_body<MAXC, CH>(a, blockIdx.x, gridDim.x, smalln_dyn_smem);
 }
 inline bool smalln_ok(int C, int K) { return C <= 8 && K % 4 == 0 && K <= 512; }
 inline cudaError_t launch_smalln_fwd(const SmallNArgs& a, int num_sms, cudaStream_t st) {
@@ -729,7 +774,7 @@ __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ 
 template <int NV, int TPR>
 __global__ void __launch_bounds__(ROW_WARPS * 32) colsum_kernel(TRef x, int B, int N, float* dst) { pdl_sync();
   __shared__ __align__(16) float red[ROW_WARPS * 512];
-  const Grp<TPR> G; __shared__ float2 scratch[ROW_WARPS];
+  const Grp<TPR> G(blockIdx.x, gridDim.x);
   float4 acc[NV];
   zero4<NV>(acc);
   for (int64_t row = G.row0; row < B; row += G.rstep) {

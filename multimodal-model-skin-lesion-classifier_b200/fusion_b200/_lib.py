@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfb200.so")
 
 F32, BF16 = 0, 1
-FLAG_NEED_DIMG, FLAG_NEED_DTEXT, FLAG_FORCE_SIMT, FLAG_FORCE_TC, FLAG_ONE_STREAM = 1, 2, 4, 8, 16
+FLAG_NEED_DIMG, FLAG_NEED_DTEXT, FLAG_FORCE_SIMT, FLAG_FORCE_TC, FLAG_ONE_STREAM, FLAG_NO_MEGA = 1, 2, 4, 8, 16, 32
 NUM_DROPOUT_SITES = 6
 DROP_SITES = ("img_res", "txt_res", "img_res2", "txt_res2", "fc1", "fc2")
 
@@ -83,6 +83,8 @@ def lib():
     sig("fb200_debug_gemm_replay", i32, dp, pp, vp, vp, vp, vp, vp, vp)
     sig("fb200_debug_tc_trace", i32, vp)
     sig("fb200_debug_set_pdl", i32, i32)
+    sig("fb200_debug_mega_trace", i32, vp)
+    sig("fb200_debug_mega_barriers", i32, i32, vp, vp)
     mp = C.POINTER(MhaDesc)
     sig("fb200_mha_workspace_bytes", i32, mp, C.POINTER(sz))
     sig("fb200_mha_forward", i32, mp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp)

@@ -189,7 +189,8 @@ def test_engine_policy_and_launch_counts_on_host():
 
     g32, _ = gemms(32)
     assert {e for _, e, *_ in g32} == {0}                                          # FFMA everywhere
-    g64, _ = gemms(64)
+    assert {e for _, e, *_ in gemms(64)[0]} == {0}                                # up to 64 rows: persistent step kernel, FFMA arithmetic
+    g64, _ = gemms(64, flags=_lib.FLAG_NO_MEGA)
     assert {e for _, e, *_ in g64} == {0, 1}
     assert all(e == 0 for lay, e, M, N, K in g64 if 85 in (N, K))                  # text_fc.0: K = 85 is not TMA-legal
     assert all(e == 1 for lay, e, M, N, K in g64 if 85 not in (N, K))

@@ -84,14 +84,15 @@ def test_two_lane_execution_equals_one_stream(mech, B):
     dependency shows up as a stale or half-written operand now and then."""
     dims = dict(F=512, V=85, C=6)
     case = dict(cfg=dict(dims, mechanism=mech), B=B, seed=11, train=False, full_grads=False)
-    cfg, one = build_model(case, "fp32", flags=_lib.FLAG_ONE_STREAM)
-    _, two = build_model(case, "fp32")
+    cfg, one = build_model(case, "fp32", flags=_lib.FLAG_ONE_STREAM | _lib.FLAG_NO_MEGA)
+    _, two = build_model(case, "fp32", flags=_lib.FLAG_NO_MEGA)
+    _, mega = build_model(case, "fp32")            # B = 32: the persistent step kernel (repeated steps: its grid barrier and stage order)
     x, tin, y, cw, _ = case_inputs(cfg, case)
-    one.eval(); two.eval()
+    one.eval(); two.eval(); mega.eval()
     l_ref, g_ref = _grads_once(one, x, tin, y, cw, True)
-    for fused in (True, False):
+    for model, fused in ((two, True), (two, False)) + (((mega, True), (mega, False)) if B <= 64 else ()):
         for _ in range(15):
-            l, g = _grads_once(two, x, tin, y, cw, fused)
+            l, g = _grads_once(model, x, tin, y, cw, fused)
             assert abs(float(l) - float(l_ref)) < 2e-6 * abs(float(l_ref))
             assert g.keys() == g_ref.keys()
             for k in g_ref:
