@@ -229,6 +229,16 @@ int64_t fb200_dp_bucket_split(const fb200_desc* d);
  * loss_out: device float; dlogits: [B,C] fp32 out or NULL. */
 int fb200_aux_loss(int kind, const void* logits, const void* targets, const float* weight, float gamma, int B, int C,
                    float* loss_out, void* dlogits, void* stream);
+/* Metadata one-hot + StandardScaler on the device: replaces np.hstack((ohe.transform(categorical), scaler.transform(
+ * numerical))) of SkinLesionDataset.one_hot_encoding (models/skinLesionDatasets.py:133-176; same construction in
+ * skinLesionDatasetsISIC2019.py / ...ISIC2020.py).  codes [B, n_cat] int32: index of each categorical value inside its
+ * column's fitted category list, < 0 for an unknown value (handle_unknown='ignore' -> all-zero group); col_of [cat_total]:
+ * the categorical column an output position belongs to; col_base [n_cat]: first output position of a column; numeric
+ * [B, n_num] float64 raw values (NaN already replaced by -1 as at :152); mean / scale [n_num] float64 = StandardScaler.mean_
+ * / .scale_.  out [B, cat_total + n_num] fp32, bit-identical to the float64 scikit-learn result rounded to fp32. */
+int fb200_metadata_encode(const int32_t* codes, const int32_t* col_of, const int32_t* col_base, const double* numeric,
+                          const double* mean, const double* scale, int B, int n_cat, int cat_total, int n_num, float* out, void* stream);
+
 /* Evaluation tail: probs = softmax(logits) and pred = argmax (utils/model_metrics.py:57-58); either output may be NULL. */
 int fb200_softmax_argmax(const void* logits, int B, int C, void* probs, int64_t* pred, void* stream);
 

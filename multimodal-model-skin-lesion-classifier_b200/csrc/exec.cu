@@ -827,6 +827,19 @@ int fb200_aux_loss(int kind, const void* logits, const void* targets, const floa
   return FB200_OK;
 }
 
+int fb200_metadata_encode(const int32_t* codes, const int32_t* col_of, const int32_t* col_base, const double* numeric,
+                          const double* mean, const double* scale, int B, int n_cat, int cat_total, int n_num, float* out, void* stream) {
+  if (!out || B < 1 || n_cat < 0 || cat_total < 0 || n_num < 0 || cat_total + n_num < 1) return FB200_EBADARG;
+  if ((cat_total > 0 && (!codes || !col_of || !col_base || n_cat < 1)) || (n_num > 0 && (!numeric || !mean || !scale))) return FB200_EBADARG;
+  if (!is_device_ptr(out)) return FB200_EUNSUPPORTED;
+  { int rc = check_optional_device({codes, col_of, col_base, numeric, mean, scale}, nullptr); if (rc != FB200_OK) return rc; }
+  const int64_t total = (int64_t)B * (cat_total + n_num);
+  int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+  pdl_launch(metadata_encode_kernel, grid, 256, 0, (cudaStream_t)stream, codes, col_of, col_base, numeric, mean, scale, B, n_cat, cat_total, n_num, out);
+  CUDA_OK(cudaGetLastError());
+  return FB200_OK;
+}
+
 int fb200_softmax_argmax(const void* logits, int B, int C, void* probs, int64_t* pred, void* stream) {
   if (!logits || B < 1 || C < 1 || (!probs && !pred)) return FB200_EBADARG;
   if (!is_device_ptr(logits)) return FB200_EUNSUPPORTED;

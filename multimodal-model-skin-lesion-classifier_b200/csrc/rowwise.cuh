@@ -638,12 +638,14 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallN
 }
 inline bool smalln_ok(int C, int K) { return C <= 8 && K % 4 == 0 && K <= 512; }
 inline cudaError_t launch_smalln_fwd(const SmallNArgs& a, int num_sms, cudaStream_t st) {
-  int grid = (a.B + ROW_WARPS * 2 - 1) / (ROW_WARPS * 2); if (grid > num_sms * 4) grid = num_sms * 4; if (grid < 1) grid = 1;
+  int grid = (a.B + ROW_WARPS - 1) / ROW_WARPS; if (grid > num_sms * 8) grid = num_sms * 8; if (grid < 1) grid = 1;      // one row per warp
   pdl_launch(smalln_fwd_kernel<8>, grid, ROW_WARPS * 32, 0, st, a);
   return cudaGetLastError();
 }
 inline cudaError_t launch_smalln_bwd(const SmallNArgs& a, int num_sms, cudaStream_t st) {
-  int grid = (a.B + ROW_WARPS * 2 - 1) / (ROW_WARPS * 2); if (grid > num_sms * 2) grid = num_sms * 2; if (grid < 1) grid = 1;
+  // two rows per warp: each CTA ends with one global atomic per weight-gradient element, so the grid is also the number of
+  // atomics every address receives
+  int grid = (a.B + ROW_WARPS * 2 - 1) / (ROW_WARPS * 2); if (grid > num_sms * 3) grid = num_sms * 3; if (grid < 1) grid = 1;
   const size_t smem = (size_t)(a.C * a.K + a.C) * sizeof(float);          // <= 8 * 512 * 4 + 32 = 16.4 KB
   if (a.K <= 128) pdl_launch(smalln_bwd_kernel<8, 1>, grid, ROW_WARPS * 32, smem, st, a);
   else if (a.K <= 256) pdl_launch(smalln_bwd_kernel<8, 2>, grid, ROW_WARPS * 32, smem, st, a);
@@ -760,6 +762,32 @@ __global__ void __launch_bounds__(256) softmax_argmax_kernel(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------ metadata one-hot + StandardScaler
+// The dense metadata vector the datasets feed the head (models/skinLesionDatasets.py:133-176: np.hstack((OneHotEncoder
+// (handle_unknown='ignore').transform(categorical), StandardScaler().transform(numerical))) built on the device from the
+// per-column category codes (code < 0 = unknown category -> an all-zero group, like handle_unknown='ignore') and the raw
+// numeric columns.  The scaler runs in float64 like scikit-learn and rounds once to fp32 (the dataset's
+// torch.tensor(..., dtype=float32)): bit-identical to the reference pipeline.  One thread per output element, coalesced.
+__global__ void __launch_bounds__(256) metadata_encode_kernel(const int32_t* __restrict__ codes, const int32_t* __restrict__ col_of,
+                                                              const int32_t* __restrict__ col_base, const double* __restrict__ numeric,
+                                                              const double* __restrict__ mean, const double* __restrict__ scale,
+                                                              int B, int n_cat, int cat_total, int n_num, float* __restrict__ out) { pdl_sync();
+  const int V = cat_total + n_num;
+  const int64_t total = (int64_t)B * V;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / V; const int j = (int)(i - b * V);
+    float v;
+    if (j < cat_total) {
+      const int c = __ldg(col_of + j);
+      v = (__ldg(codes + b * n_cat + c) == j - __ldg(col_base + c)) ? 1.f : 0.f;
+    } else {
+      const int q = j - cat_total;
+      v = (float)((__ldg(numeric + b * n_num + q) - __ldg(mean + q)) / __ldg(scale + q));
+    }
+    out[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------ format conversion
 // fp32 [rows, cols] (ld_in) -> FMT_PAIR / FMT_BF16 / FMT_F32 copy (ld_out); any alignment.
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ in, int ld_in, TRef out, int64_t rows, int cols) { pdl_sync();
@@ -830,8 +858,11 @@ __global__ void __launch_bounds__(256) colsum_batch_kernel(const ColsumBatch a) 
 
 // ---- launch helpers ------------------------------------------------------------------
 inline int row_grid(int B, int num_sms) {
-  int ctas = (B + ROW_WARPS * 4 - 1) / (ROW_WARPS * 4);      // aim at >= 4 rows per warp
-  int cap = num_sms * 4;
+  // ONE row per warp while the rows fit one wave of resident CTAs (8 CTAs of 8 warps per SM): these kernels are a chain of
+  // dependent latencies per row (load -> row statistics -> store), so rows in flight are what reaches HBM bandwidth.  r01
+  // gave every warp 4 rows in turn: lnrd_fwd<4,32> at B = 4096 ran at 0.20 of the measured HBM peak (profiles/r01 launch list).
+  int ctas = (B + ROW_WARPS - 1) / ROW_WARPS;
+  int cap = num_sms * 8;
   if (ctas > cap) ctas = cap;
   return ctas < 1 ? 1 : ctas;
 }

@@ -14,5 +14,6 @@ from .head import (FusedCrossEntropyLoss, FusedFocalLoss, FusedHeadFunction, Fus
 from .attention import FusedMHAFunction, MultiheadAttention
 from .model import GraphedTrainStep, MultimodalModel
 from .optim import FusedAdam
+from .metadata import MetadataEncoder
 
-__all__ = ["MultimodalModel", "MultiheadAttention", "FusedMHAFunction", "GraphedTrainStep", "FusedAdam", "FusedCrossEntropyLoss", "FusedFocalLoss", "FusedSoftTargetCrossEntropy", "softmax_argmax", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]
+__all__ = ["MetadataEncoder", "MultimodalModel", "MultiheadAttention", "FusedMHAFunction", "GraphedTrainStep", "FusedAdam", "FusedCrossEntropyLoss", "FusedFocalLoss", "FusedSoftTargetCrossEntropy", "softmax_argmax", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]

@@ -79,6 +79,7 @@ def lib():
     sig("fb200_rng_advance", i32, vp, u64, vp)
     sig("fb200_aux_loss", i32, i32, vp, vp, vp, C.c_float, i32, i32, vp, vp, vp)
     sig("fb200_softmax_argmax", i32, vp, i32, i32, vp, vp, vp)
+    sig("fb200_metadata_encode", i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp)
     sig("fb200_adam_step", i32, i32, pp, pp, pp, pp, C.POINTER(i64), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_float, vp)
     sig("fb200_debug_gemm_replay", i32, dp, pp, vp, vp, vp, vp, vp, vp)
     sig("fb200_debug_tc_trace", i32, vp)

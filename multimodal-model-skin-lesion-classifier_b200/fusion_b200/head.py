@@ -53,6 +53,23 @@ def _check_input(t, name, cols):
     return t.contiguous()
 
 
+_table_cache = {}
+
+
+def param_table(tensors):
+    """ParamTable for `tensors`, cached on their device pointers: the eager drop-in route builds one per pass, and
+    filling a 78-entry ctypes array costs more host time than the whole persistent-kernel launch it precedes."""
+    key = tuple(0 if t is None else t.data_ptr() for t in tensors)
+    hit = _table_cache.get(key)
+    if hit is None:
+        if len(_table_cache) > 64:
+            _table_cache.clear()
+        hit = _table_cache[key] = ParamTable(tensors)
+    else:
+        hit.tensors = list(tensors)          # same storage, possibly new tensor objects: keep these alive
+    return hit
+
+
 class ParamTable:
     """Array of the 78 parameter pointers in slot order (NULL for absent slots)."""
 
@@ -89,7 +106,10 @@ class FusedHeadFunction(torch.autograd.Function):
     Once differentiable (Grad-CAM++ style double backward is not supported - SURVEY 8b)."""
 
     @staticmethod
-    def forward(ctx, img_feat, text_in, cfg, masks, seed, offset, *params):
+    def forward(ctx, img_feat, text_in, cfg, masks, seed, offset, slots, all_params, *params):
+        """`params`: the LIVE parameters only (the ones the fusion string differentiates; `slots` = their slot numbers) -
+        autograd's per-argument bookkeeping is host time on the critical path of a 100-microsecond step; `all_params`:
+        every slot's tensor (or None), for the pointer table."""
         L = _lib.lib()
         B = img_feat.shape[0]
         need_dimg = bool(img_feat.requires_grad)
@@ -99,7 +119,7 @@ class FusedHeadFunction(torch.autograd.Function):
                          cfg["text_mode"], cfg["dtype"], cfg["train"], flags)
         x = _check_input(img_feat.detach(), "img_feat", cfg["F"])
         t = _check_input(text_in.detach(), "text_metadata", cfg["T"] if cfg["text_mode"] else cfg["V"])
-        table = ParamTable([p.detach() if p is not None else None for p in params])
+        table = param_table(all_params)
         ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=x.device)
         logits = torch.empty(B, cfg["C"], dtype=torch.float32, device=x.device)
         marr, mkeep = _mask_table(masks)
@@ -109,7 +129,7 @@ class FusedHeadFunction(torch.autograd.Function):
         ctx.desc, ctx.table, ctx.ws, ctx.x, ctx.t = desc, table, ws, x, t
         ctx.marr, ctx.mkeep, ctx.seed, ctx.offset = marr, mkeep, seed, offset
         ctx.need = (need_dimg, need_dtxt)
-        ctx.nparams = len(params)
+        ctx.slots = slots
         return logits
 
     @staticmethod
@@ -127,14 +147,11 @@ class FusedHeadFunction(torch.autograd.Function):
                                              _ptr(dl), _ptr(flat), _ptr(d_img), _ptr(d_txt), _ptr(ctx.ws), _stream()),
                        "fb200_head_backward")
         grads = []
-        for s in range(ctx.nparams):
-            p = ctx.table.tensors[s]
-            if p is None or s not in offs:
-                grads.append(None)          # same None pattern as the reference's autograd
-            else:
-                grads.append(flat[offs[s]: offs[s] + p.numel()].view(p.shape))
+        for s in ctx.slots:                 # parameters outside `slots` never entered the graph: they keep grad=None like in
+            p = ctx.table.tensors[s]        # the reference's autograd
+            grads.append(flat[offs[s]: offs[s] + p.numel()].view(p.shape))
         ctx.ws = None
-        return (d_img, d_txt, None, None, None, None, *grads)
+        return (d_img, d_txt, None, None, None, None, None, None, *grads)
 
 
 def cross_entropy(logits, labels, class_w=None, denom=None, want_grad=True):

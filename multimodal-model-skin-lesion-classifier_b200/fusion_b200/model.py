@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import _lib
 from .backbones import loadModels
-from .head import FusedHeadFunction, ParamTable, _check_input, _mask_table, _ptr, _stream, denom_arg, make_desc
+from .head import FusedHeadFunction, ParamTable, _check_input, _mask_table, _ptr, _stream, denom_arg, make_desc, param_table
 
 RG_ATT = "att-intramodal+residual+cross-attention-metadados"
 
@@ -109,8 +109,36 @@ class MultimodalModel(nn.Module):
                     dtype=self.compute_dtype, train=train, flags=self.engine_flags)
 
     def _params_in_slot_order(self):
+        """The 78 head parameters in slot order (None for absent ones).  Cached: walking named_parameters() (backbone included)
+        on every pass costs more host time than the step kernel's launch; `_apply` (.to / .cuda / .float) keeps nn.Parameter
+        objects and replaces their .data, load_state_dict copies in place, so object identity is a valid cache key - a
+        parameter object that was REPLACED shows up as a different id and rebuilds the list."""
+        cache = self.__dict__.get("_slot_cache")
+        if cache is not None and all(p is q for p, q in zip(cache[1], (self._parameters_of(m).get(n) for m, n in cache[0]))):
+            return cache[2]
         named = dict(self.named_parameters())
-        return [named.get(k) for k in self._slot_names]
+        owners = []
+        for k in self._slot_names:
+            mod_path, _, leaf = k.rpartition(".")
+            try:
+                owners.append((self.get_submodule(mod_path) if mod_path else self, leaf))
+            except AttributeError:
+                owners.append((None, leaf))
+        plist = [named.get(k) for k in self._slot_names]
+        self.__dict__["_slot_cache"] = (owners, list(plist), plist)
+        return plist
+
+    @staticmethod
+    def _parameters_of(module):
+        return module._parameters if module is not None else {}
+
+    def _live_slots(self, desc):
+        key = _lib.desc_key(desc)[:10]
+        hit = self.__dict__.setdefault("_live_cache", {}).get(key)
+        if hit is None:
+            _, offs = _lib.grad_layout(desc)
+            hit = self.__dict__["_live_cache"][key] = tuple(sorted(offs))
+        return hit
 
     def inject_dropout_masks(self, masks):
         """Parity tests: use explicit {0,1} keep-masks instead of the in-kernel Philox stream."""
@@ -141,9 +169,14 @@ class MultimodalModel(nn.Module):
         train = bool(self.training)
         if train:
             self._step += 1
-        return FusedHeadFunction.apply(img_feat, text_in, self._cfg(train), self._injected_masks,
-                                       torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, self._step,
-                                       *self._params_in_slot_order())
+        cfg = self._cfg(train)
+        params = self._params_in_slot_order()
+        desc = make_desc(cfg["mechanism"], img_feat.shape[0], cfg["F"], cfg["V"], cfg["T"], cfg["D"], cfg["H"], cfg["C"], cfg["n"],
+                         cfg["text_mode"], cfg["dtype"], train, cfg["flags"])
+        slots = tuple(s for s in self._live_slots(desc) if params[s] is not None)
+        return FusedHeadFunction.apply(img_feat, text_in, cfg, self._injected_masks,
+                                       torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, self._step, slots,
+                                       [None if p is None else p.detach() for p in params], *[params[s] for s in slots])
 
     # ------------------------------------------------------------------ fused train step (opt-in)
     def forward_loss(self, image, text_metadata, label, class_weights=None, denom=None, zero_grad=True, mid_event=None):
@@ -170,7 +203,7 @@ class MultimodalModel(nn.Module):
         x = _check_input(img_feat.detach(), "img_feat", cfg["F"])
         t = _check_input(text_in.detach(), "text_metadata", cfg["T"] if cfg["text_mode"] else cfg["V"])
         params = self._params_in_slot_order()
-        table = ParamTable([p.detach() if p is not None else None for p in params])
+        table = param_table([p.detach() if p is not None else None for p in params])
         dev = x.device
         ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
         total, offs = _lib.grad_layout(desc)
