@@ -418,6 +418,10 @@ def main():
             extras = {"mha_tokens": time_token_attention(torch, fb, dev)}
         except Exception as exc:                                    # never lose the headline line to an extra
             extras = {"mha_tokens": {"error": repr(exc)}}
+        try:
+            extras["e2e_backbone"] = time_backbone_e2e(torch, fb, dev, wl)
+        except Exception as exc:
+            extras["e2e_backbone"] = {"error": repr(exc)}
 
     if rank == 0:
         line = {
@@ -626,6 +630,59 @@ def run_dp_check(torch, dist, fb, _lib, dev, wl, build, rank, world, rows_per_ra
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
     return {"max_rel_err": worst[0].item(), "rel_l2": worst[1].item(), "loss_rel_err": worst[2].item(), "global_batch": Bg,
             "how": f"{world} ranks x {rows_per_rank} rows, global denominator, NCCL SUM all-reduce of the flat gradient vs one process on {Bg} rows (eval mode)"}
+
+
+def time_backbone_e2e(torch, fb, dev, wl, Bsz=32, steps=20, warm=5):
+    """End-to-end train step WITH the stock image backbone (north star: "end-to-end step time is reported"): 224x224 fp32
+    images from pinned host memory -> torchvision ResNet-50 (random init: no network for pretrained weights; frozen, stock
+    PyTorch kernels, outside the optimisation target) -> fused head step -> loss read back.  Batch 32 = conf/.env.test:2."""
+    import warnings
+    mech, F, V, Cn, T, tm, dtype = wl
+    name = {2048: "resnet-50", 512: "resnet-18", 1664: "densenet169"}.get(F)
+    if name is None or tm != 0:
+        return {"skipped": f"no stock torchvision backbone of width {F} / one-hot metadata for this workload"}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(1234)
+        model = fb.MultimodalModel(Cn, 8, dev, f"random:{name}", "one-hot-encoder", vocab_size=V, attention_mecanism=mech,
+                                   unfreeze_weights="frozen_weights", compute_dtype=dtype).to(dev).train()
+    model.image_encoder.eval()                                   # frozen backbone: no batch-norm statistics updates
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(Bsz, 3, 224, 224, generator=g).pin_memory(); meta = torch.randn(Bsz, V, generator=g).pin_memory()
+    y = torch.randint(0, Cn, (Bsz,), generator=g).pin_memory()
+    cw = torch.ones(Cn, device=dev)
+    host_loss = torch.empty(1).pin_memory()
+    d_img = torch.empty(Bsz, 3, 224, 224, device=dev); d_meta = torch.empty(Bsz, V, device=dev); d_y = torch.empty(Bsz, dtype=torch.int64, device=dev)
+
+    def timed(fn):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def full():
+        d_img.copy_(img, non_blocking=True); d_meta.copy_(meta, non_blocking=True); d_y.copy_(y, non_blocking=True)
+        loss, _ = model.forward_loss(d_img, d_meta, d_y, cw)
+        host_loss.copy_(loss.reshape(1), non_blocking=True)
+
+    def backbone_only():
+        with torch.no_grad():
+            model.image_encoder(d_img)
+
+    feat = torch.randn(Bsz, F, device=dev)
+    head_model = fb.MultimodalModel(Cn, 8, dev, f"identity:{F}", "one-hot-encoder", vocab_size=V, attention_mecanism=mech, compute_dtype=dtype).to(dev).train()
+
+    def head_only():
+        head_model.forward_loss(feat, d_meta, d_y, cw)
+    t_full, t_bb, t_head = timed(full), timed(backbone_only), timed(head_only)
+    return {"backbone": f"torchvision {name} (random init, frozen, fp32, stock PyTorch eager)", "batch": Bsz, "image": "3x224x224 fp32",
+            "ms_per_step": t_full, "backbone_forward_ms": t_bb, "head_step_ms": t_head, "samples_per_s": Bsz / (t_full * 1e-3),
+            "h2d_bytes_per_step": Bsz * (3 * 224 * 224 + V) * 4 + Bsz * 8,
+            "note": "head_step_ms is eager forward_loss (no CUDA graph); the frozen backbone needs no backward"}
 
 
 def time_token_attention(torch, fb, dev, Sq=197, Skv=85, B=32, D=512, H=8, reps=20):

@@ -55,8 +55,11 @@ class _MetaBlockParams(nn.Module):
 class MultimodalModel(nn.Module):
     def __init__(self, num_classes, num_heads, device, cnn_model_name, text_model_name, batch_size=32,
                  common_dim=512, text_encoder_dim_output=512, vocab_size=91, unfreeze_weights="frozen_weights",
-                 attention_mecanism="concatenation", n=2, compute_dtype="fp32", engine_flags=0):
+                 attention_mecanism="concatenation", n=2, compute_dtype="fp32", engine_flags=0, backend="b200"):
         super().__init__()
+        if backend not in ("b200", "reference"):
+            raise ValueError(f"backend must be 'b200' or 'reference', got {backend!r}")
+        self.backend = backend               # "reference": stock torch.nn composition for double-backward callers (reference_backend.py)
         self.device = device
         self.common_dim, self.num_heads, self.n = common_dim, num_heads, n
         self.attention_mecanism = attention_mecanism
@@ -159,6 +162,8 @@ class MultimodalModel(nn.Module):
             ids = text_metadata["input_ids"].squeeze(1).to(self.device)
             att = text_metadata["attention_mask"].squeeze(1).to(self.device)
             text_in = self.text_encoder(input_ids=ids, attention_mask=att).last_hidden_state[:, 0, :]
+        if self.backend == "reference":
+            return img_feat, text_in                                     # stock torch ops: any floating dtype
         return img_feat.float(), text_in.float()
 
     # ------------------------------------------------------------------ reference API
@@ -166,6 +171,9 @@ class MultimodalModel(nn.Module):
         if _lib.mechanism_id(self.attention_mecanism) < 0:
             raise ValueError(f"Attention mechanism '{self.attention_mecanism}' not implemented.")
         img_feat, text_in = self._encode(image, text_metadata)
+        if self.backend == "reference":
+            from .reference_backend import reference_forward
+            return reference_forward(self, img_feat, text_in)
         train = bool(self.training)
         if train:
             self._step += 1
