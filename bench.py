@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
     ap.add_argument("--dtype", default=None, choices=[None, "fp32", "bf16"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch rows per GPU; strong: --batch rows in total, split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"], help="GEMM engine policy (auto: tcgen05 from B > 32 in fp32, always in bf16)")
@@ -177,10 +178,16 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
     if world > 1:
+        numa_cpus = fb.dp.bind_to_gpu_numa_node(local)           # before any pinned allocation: host staging buffers become node-local
         dist.init_process_group("nccl", device_id=dev)
     mech, F, V, Cn, T, tm, dtype = wl
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    if args.scaling == "strong":
+        if B % world:
+            raise SystemExit(f"--scaling strong: --batch {B} must be a multiple of the {world} GPUs")
+        B //= world
 
     def build(Bsz):
         torch.manual_seed(1234)
@@ -207,6 +214,23 @@ def main():
         counts = torch.bincount(y, minlength=Cn).clamp_min(1).float()
         return (y.numel() / (Cn * counts)).to(dev)
 
+    # ---- data-parallel gradient all-reduce: the hand-written one-kernel NVSwitch (multimem) / peer all-reduce over a
+    #      symmetric-memory gradient bucket (csrc/dp_comm.cuh), captured into the step's CUDA graph; NCCL when symmetric
+    #      memory is unavailable or FB200_DP_COMM=nccl.  One bucket serves every batch size (sized for the largest layout).
+    comm = {"kind": "none"}
+    if world > 1:
+        want = os.environ.get("FB200_DP_COMM", "auto")
+        comm = {"kind": "nccl"}
+        if want != "nccl":
+            try:
+                total_max, _ = _lib.grad_layout(fb.make_desc(mech, B, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype))
+                bucket = fb.dp.SymmetricGradBucket(total_max, dev, mode="auto" if want == "auto" else want)
+                comm = {"kind": bucket.mode, "bucket": bucket}
+            except Exception as exc:
+                if want != "auto":
+                    raise
+                comm = {"kind": "nccl", "symm_error": repr(exc)[:200]}
+
     def run_config(Bsz, steps, warm, sample_clocks=False):
         model = build(Bsz)
         in_bytes = Bsz * (F + (V if tm == 0 else T)) * 4
@@ -231,13 +255,24 @@ def main():
                 mids = [torch.cuda.Event() for _ in range(nb)]
                 for ev in mids:
                     ev.record()
-            bar = fb.dp.BucketedAllReduce(dev)
+            bar = fb.dp.BucketedAllReduce(dev, bucket=comm.get("bucket"))
         split = _lib.dp_bucket_split(fb.make_desc(mech, Bsz, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype, train=True,
                                                   flags={"auto": 0, "simt": 4, "tc": 8}[args.engine])) if world > 1 else 0
         graphs = []
+        bucket = comm.get("bucket")
+        flat_out = bucket.tensor if bucket is not None else None
+        span = (min(b for b, _ in live_ranges), max(e for _, e in live_ranges))
+        in_graph = world > 1 and use_graph and os.environ.get("FB200_DP_OVERLAP", "0") != "1" and os.environ.get("FB200_DP_IN_GRAPH", "1") == "1"
+
+        def reduce_grads(flat):
+            if bucket is not None:
+                bucket.all_reduce(live_ranges)                      # barrier + ONE kernel over the live slices + barrier
+            else:
+                dist.all_reduce(flat[span[0]:span[1]])              # NCCL, one in-place collective over the contiguous live span
         if use_graph:
             for j in range(nb):
-                graphs.append(fb.GraphedTrainStep(model, xs[j], ts[j], ys[j], cw, denom=denoms[j], mid_event=mids[j]))
+                graphs.append(fb.GraphedTrainStep(model, xs[j], ts[j], ys[j], cw, denom=denoms[j], mid_event=mids[j], flat_out=flat_out,
+                                                  after_step=reduce_grads if in_graph else None))
 
         # The global weighted-CE denominator of a batch only needs its labels, which the loader has one step ahead:
         # it is all-reduced on a side stream while the previous step computes (dp.DenominatorPrefetcher).
@@ -255,12 +290,18 @@ def main():
                 loss = graphs[j].run()
                 flat = graphs[j].flat_grad
             else:
-                loss, _ = model.forward_loss(xs[j], ts[j], ys[j], cw, denom=denoms[j], mid_event=mids[j])
+                loss, _ = model.forward_loss(xs[j], ts[j], ys[j], cw, denom=denoms[j], mid_event=mids[j], flat_out=flat_out)
                 flat = model.flat_grad
             if world > 1:
-                bar.start(flat, live_ranges, split, mids[j])       # bucket 1 on the communication stream, under the tail of the step
-                pref.mark_consumed(j)
-                bar.finish(flat)                                    # bucket 2 (SUM: the global denominator already averages; only live slices travel)
+                if in_graph:
+                    pref.mark_consumed(j)                           # the collective was captured with the step: one graph launch did both
+                elif os.environ.get("FB200_DP_OVERLAP", "0") != "1":
+                    pref.mark_consumed(j)
+                    reduce_grads(flat)
+                else:
+                    bar.start(flat, live_ranges, split, mids[j])   # bucket 1 on the communication stream, under the tail of the step
+                    pref.mark_consumed(j)
+                    bar.finish(flat)                                # bucket 2 (SUM: the global denominator already averages; only live slices travel)
             return loss
 
         for i in range(warm):
@@ -296,31 +337,56 @@ def main():
     def run_e2e(Bsz, steps, warm):
         m2 = build(Bsz)
         nbh = 4
-        hx, ht, hy = make_pool(Bsz, nbh, pinned=True)
+        hx, ht, hy = make_pool(Bsz, nbh, pinned=False)
+        hx, ht, hy = [v.cpu() for v in hx], [v.cpu() for v in ht], [v.cpu() for v in hy]
         cw = class_weights(hy)
         copy_stream = torch.cuda.Stream(device=dev)
-        slots = [dict(x=torch.zeros(Bsz, F, device=dev), t=torch.zeros(Bsz, ht[0].shape[1], device=dev),
-                      y=torch.zeros(Bsz, dtype=torch.int64, device=dev), ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        Wt = ht[0].shape[1]
+        nx, nt, ny = Bsz * F * 4, Bsz * Wt * 4, Bsz * 8
+        # ONE packed pinned staging buffer per batch (features | metadata | labels) and ONE cudaMemcpyAsync per step into a
+        # device buffer the step reads through typed views
+        staged = []
+        for j in range(nbh):
+            hb = torch.empty(nx + nt + ny, dtype=torch.uint8).pin_memory()
+            hb[:nx].view(torch.float32).copy_(hx[j].reshape(-1)); hb[nx:nx + nt].view(torch.float32).copy_(ht[j].reshape(-1))
+            hb[nx + nt:].view(torch.int64).copy_(hy[j])
+            staged.append(hb)
+        slots = []
+        for _ in range(2):
+            db = torch.zeros(nx + nt + ny, dtype=torch.uint8, device=dev)
+            slots.append(dict(buf=db, x=db[:nx].view(torch.float32).view(Bsz, F), t=db[nx:nx + nt].view(torch.float32).view(Bsz, Wt),
+                              y=db[nx + nt:].view(torch.int64), ready=torch.cuda.Event(), free=torch.cuda.Event()))
         host_loss = torch.empty(warm + 3 * steps, dtype=torch.float32).pin_memory()
 
         def prefetch(i):
             s = slots[i % 2]; j = i % nbh
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(s["free"])
-                s["x"].copy_(hx[j], non_blocking=True); s["t"].copy_(ht[j], non_blocking=True); s["y"].copy_(hy[j], non_blocking=True)
+                s["buf"].copy_(staged[j], non_blocking=True)
                 s["ready"].record(copy_stream)
 
         use_graph = not args.no_graph
         live_ranges2 = _lib.grad_live_ranges(fb.make_desc(mech, Bsz, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype))
-        bar2 = fb.dp.BucketedAllReduce(dev) if world > 1 else None
+        bar2 = fb.dp.BucketedAllReduce(dev, bucket=comm.get("bucket")) if world > 1 else None
         split2 = _lib.dp_bucket_split(fb.make_desc(mech, Bsz, F, V, T, 512, 8, Cn, text_mode=tm, dtype=dtype, train=True,
                                                    flags={"auto": 0, "simt": 4, "tc": 8}[args.engine])) if world > 1 else 0
+        bucket = comm.get("bucket")
+        flat_out2 = bucket.tensor if bucket is not None else None
+        span2 = (min(b for b, _ in live_ranges2), max(e for _, e in live_ranges2))
+
+        def reduce2(flat):
+            if bucket is not None:
+                bucket.all_reduce(live_ranges2)
+            else:
+                dist.all_reduce(flat[span2[0]:span2[1]])
+        in_graph2 = world > 1 and use_graph and os.environ.get("FB200_DP_OVERLAP", "0") != "1" and os.environ.get("FB200_DP_IN_GRAPH", "1") == "1"
         for s in slots:
             s["denom"] = torch.zeros(1, device=dev) if world > 1 else None
             s["mid"] = None
             if world > 1 and os.environ.get("FB200_DP_OVERLAP", "0") == "1":
                 s["mid"] = torch.cuda.Event(); s["mid"].record()
-            s["graph"] = fb.GraphedTrainStep(m2, s["x"], s["t"], s["y"], cw, denom=s["denom"], mid_event=s["mid"]) if use_graph else None
+            s["graph"] = fb.GraphedTrainStep(m2, s["x"], s["t"], s["y"], cw, denom=s["denom"], mid_event=s["mid"], flat_out=flat_out2,
+                                             after_step=reduce2 if in_graph2 else None) if use_graph else None
 
         def run(n, base):
             cur = torch.cuda.current_stream()
@@ -335,10 +401,13 @@ def main():
                 if use_graph:
                     loss = s["graph"].run(); flat = s["graph"].flat_grad
                 else:
-                    loss, _ = m2.forward_loss(s["x"], s["t"], s["y"], cw, denom=s["denom"], mid_event=s["mid"]); flat = m2.flat_grad
-                if world > 1:
-                    bar2.start(flat, live_ranges2, split2, s["mid"])
-                    bar2.finish(flat)
+                    loss, _ = m2.forward_loss(s["x"], s["t"], s["y"], cw, denom=s["denom"], mid_event=s["mid"], flat_out=flat_out2); flat = m2.flat_grad
+                if world > 1 and not in_graph2:
+                    if os.environ.get("FB200_DP_OVERLAP", "0") != "1":
+                        reduce2(flat)
+                    else:
+                        bar2.start(flat, live_ranges2, split2, s["mid"])
+                        bar2.finish(flat)
                 host_loss[i:i + 1].copy_(loss.reshape(1), non_blocking=True)       # D2H read of the step's result
                 s["free"].record(cur)
         for s in slots:
@@ -402,7 +471,7 @@ def main():
 
     dp_check = None
     if world > 1:
-        dp_check = run_dp_check(torch, dist, fb, _lib, dev, wl, build, rank, world)
+        dp_check = run_dp_check(torch, dist, fb, _lib, dev, wl, build, rank, world, comm.get("bucket"))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -426,17 +495,26 @@ def main():
     if rank == 0:
         line = {
             "metric": "fusion-head train samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32" if dtype == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC.get(args.workload, args.workload), "mechanism": mech, "per_gpu_batch": B, "global_batch": B * world,
-                       "F": F, "V": V, "C": Cn, "D": 512, "heads": 8, "parallelism": f"dp{world}", "launch": ("eager" if args.no_graph else "one CUDA graph per train step") + "; every kernel launched with programmatic dependent launch; metadata chain on an internal side stream",
+                       "F": F, "V": V, "C": Cn, "D": 512, "heads": 8, "parallelism": f"dp{world}", "grad_allreduce": ({"multimem": "hand-written one-kernel NVSwitch multimem.ld_reduce / multimem.st all-reduce over the live gradient ranges of a symmetric-memory bucket (csrc/dp_comm.cuh), captured in the step graph",
+                                                          "peer": "hand-written one-kernel peer-load / peer-store all-reduce over the live gradient ranges of a symmetric-memory bucket (csrc/dp_comm.cuh), captured in the step graph",
+                                                          "nccl": "NCCL all_reduce over the live span, captured in the step graph", "none": None}[comm["kind"]]), "launch": ("eager" if args.no_graph else "one CUDA graph per train step") + "; every kernel launched with programmatic dependent launch; metadata chain on an internal side stream",
                        "l2": f"inputs rotate over a pool of {nb} batches = {nb * in_bytes / 1e6:.0f} MB (> 126 MB L2 when >= 127); weights ({plive * 4 / 1e6:.1f} MB) stay L2-resident by design"},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "how": "one packed pinned staging buffer (features | metadata | labels) and one cudaMemcpyAsync per step, double-buffered on a copy stream; loss read back per step"
+                           + (f"; rank pinned to the {len(numa_cpus)} cores of its GPU's NUMA node" if numa_cpus else "")},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "loss": last_loss, "sweep": sweep or None,
             "incumbent": incumbent, "dp_check": dp_check, "extras": extras,
         }
         emit(line)
     if world > 1:
+        if comm.get("bucket") is not None:
+            # tearing down a process group that holds symmetric-memory rendezvous state hung for minutes here (probe run,
+            # gpurun_out/r02_probe_symm_2gpu.txt): everything is flushed and the line is printed - leave without the teardown
+            torch.cuda.synchronize(); dist.barrier(); sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -602,7 +680,7 @@ def time_incumbents(torch, fb, dev, wl, Bsz, build, steps=30, warm=5):
     return out
 
 
-def run_dp_check(torch, dist, fb, _lib, dev, wl, build, rank, world, rows_per_rank=192):
+def run_dp_check(torch, dist, fb, _lib, dev, wl, build, rank, world, bucket=None, rows_per_rank=192):
     """N ranks + NCCL + global denominator against ONE process at the global batch, on the hardware: every rank draws the same
     global batch, runs its shard through forward_loss with the global weighted-CE denominator and SUM-all-reduces the flat
     gradient; the result must equal forward_loss on the whole batch (eval mode: dropout draws depend on the local row index)."""
@@ -617,18 +695,24 @@ def run_dp_check(torch, dist, fb, _lib, dev, wl, build, rank, world, rows_per_ra
     model.eval()
     lo, hi = fb.dp.shard_rows(Bg, rank, world)
     denom = fb.dp.global_denominator(y[lo:hi], cw)
-    loss_s, _ = model.forward_loss(x[lo:hi], t[lo:hi], y[lo:hi], cw, denom=denom)
-    flat_s = model.flat_grad.clone()
-    fb.dp.allreduce_gradients(flat_s)
+    if bucket is not None:           # the hand-written all-reduce kernel on the symmetric-memory bucket, live ranges only
+        loss_s, _ = model.forward_loss(x[lo:hi], t[lo:hi], y[lo:hi], cw, denom=denom, flat_out=bucket.tensor)
+        bucket.all_reduce(_lib.grad_live_ranges(model.last_desc))
+        flat_s = model.flat_grad[: _lib.grad_layout(model.last_desc)[0]].clone()
+    else:
+        loss_s, _ = model.forward_loss(x[lo:hi], t[lo:hi], y[lo:hi], cw, denom=denom)
+        flat_s = model.flat_grad.clone()
+        fb.dp.allreduce_gradients(flat_s)
     loss_s = loss_s.clone(); dist.all_reduce(loss_s)
     loss_g, _ = model.forward_loss(x, t, y, cw)
-    flat_g = model.flat_grad
+    flat_g = model.flat_grad[: flat_s.numel()]
     torch.cuda.synchronize()
     err = ((flat_s - flat_g).abs().max() / flat_g.abs().max()).item()
     l2 = ((flat_s - flat_g).norm() / flat_g.norm()).item()
     worst = torch.tensor([err, l2, abs(loss_s.item() - loss_g.item()) / abs(loss_g.item())], device=dev)
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
     return {"max_rel_err": worst[0].item(), "rel_l2": worst[1].item(), "loss_rel_err": worst[2].item(), "global_batch": Bg,
+            "collective": bucket.mode if bucket is not None else "nccl",
             "how": f"{world} ranks x {rows_per_rank} rows, global denominator, NCCL SUM all-reduce of the flat gradient vs one process on {Bg} rows (eval mode)"}
 
 

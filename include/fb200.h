@@ -209,6 +209,20 @@ int fb200_head_train_step(const fb200_desc* d, const void* const* params,
                           void* logits, float* loss_out, void* grads,
                           void* d_img_feat, void* d_text_in, void* ws, void* stream);
 
+/* Data-parallel gradient SUM all-reduce over NVLink / NVSwitch in ONE kernel, in place, over the live ranges of the flat
+ * gradient buffer only (the reference has no collective - single process, train_pad_20.py:509).  The buffer
+ * of every rank lives in symmetric memory: `multicast_ptr` = the NVSwitch multicast address aliasing all ranks' buffers
+ * (multimem.ld_reduce / multimem.st: the switch adds and broadcasts), or NULL with `peer_ptrs[world]` = every rank's
+ * buffer mapped into this process (plain peer loads / stores).  ranges: nranges pairs [begin, end) of element offsets
+ * (multiples of 4, ascending; fb200_grad_live_ranges).  The caller brackets the call with two cross-rank barriers on the
+ * stream: every rank's gradients complete before, every rank's stores complete after.  max_ctas: 0 = full grid; a small
+ * value (e.g. 32) keeps the kernel beside a GEMM it overlaps with (256-thread CTAs, no shared memory).
+ * signal_pads[world] != NULL: the two barriers run INSIDE the kernel on uint32 slots [slot, slot + 2 * world) of every rank's
+ * zero-initialised, peer-mapped signal pad (`state`: 16 bytes of local device memory for the kernel's own bookkeeping); NULL:
+ * the caller brackets the call with its own barriers. */
+int fb200_dp_allreduce(void* multicast_ptr, void* const* peer_ptrs, const int64_t* ranges, int nranges, int rank, int world, int max_ctas,
+                       void* const* signal_pads, void* state, int slot, void* stream);
+
 /* Data-parallel variant of fb200_head_train_step (the head's gradients are all-reduced after every step).
  * Every gradient whose offset in the flat buffer is below fb200_dp_bucket_split(d) is final when `mid_event`
  * (a cudaEvent_t; recorded on `stream`, as an external event-record node when the stream is being captured) fires;

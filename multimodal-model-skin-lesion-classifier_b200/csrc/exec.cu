@@ -5,6 +5,7 @@
 #include "tc_gemm.cuh"
 #include "attention.cuh"
 #include "mega.cuh"
+#include "dp_comm.cuh"
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -969,6 +970,13 @@ int fb200_head_train_step(const fb200_desc* d, const void* const* params, const 
                           void* logits, float* loss_out, void* grads, void* d_img_feat, void* d_text_in, void* ws, void* stream) {
   return fb200_head_train_step_dp(d, params, img_feat, text_in, labels, class_w, denom, masks, seed, offset, rng_state,
                                   logits, loss_out, grads, d_img_feat, d_text_in, ws, stream, nullptr);
+}
+
+int fb200_dp_allreduce(void* multicast_ptr, void* const* peer_ptrs, const int64_t* ranges, int nranges, int rank, int world, int max_ctas,
+                       void* const* signal_pads, void* state, int slot, void* stream) {
+  DeviceInfo dev; int rc = get_device_info(dev); if (rc != FB200_OK) return rc;
+  return dp_allreduce_launch((float*)multicast_ptr, (float* const*)peer_ptrs, ranges, nranges, rank, world, dev.num_sms, max_ctas,
+                             (uint32_t* const*)signal_pads, (uint32_t*)state, slot, (cudaStream_t)stream);
 }
 
 int64_t fb200_dp_bucket_split(const fb200_desc* d) {

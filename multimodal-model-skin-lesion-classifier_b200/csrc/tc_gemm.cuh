@@ -157,6 +157,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+template <int N> __device__ __forceinline__ void tmem_ldN(uint32_t taddr, uint32_t (&r)[N]);
+template <> __device__ __forceinline__ void tmem_ldN<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+template <> __device__ __forceinline__ void tmem_ldN<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+
 // Shared-memory matrix descriptor (tcgen05 "SmemDescriptor"): start address, leading / stride
 // byte offsets (all >> 4), version 1 (bits 46-47), 128-byte swizzle (layout type 2 in bits 61-63).
 //   K-major  tile: rows of 128 B (the K slice), 8-row swizzle atoms 1024 B apart      -> SBO = 1024, LBO unused (1)
@@ -381,12 +394,13 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       const int ab = ch & (Cfg::ACC_BUFS - 1);
       mbar_wait(&tmem_full[ab], (ch / Cfg::ACC_BUFS) & 1);
       tc_fence_after();
+      constexpr int LDW = HN < 32 ? HN : 32;                                           // columns per tcgen05.ld
 #pragma unroll
-      for (int c0 = 0; c0 < HN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * HN + c0), r);
+      for (int c0 = 0; c0 < HN; c0 += LDW) {
+        uint32_t r[LDW];
+        tmem_ldN<LDW>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * HN + c0), r);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        for (int j = 0; j < LDW; ++j) acc[c0 + j] += __uint_as_float(r[j]);
       }
       tc_fence_before();
       __syncwarp();
@@ -501,68 +515,76 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       const int r_begin = h * RPW;
       const int r_end = rows_valid < r_begin + RPW ? rows_valid : r_begin + RPW;
       const bool plain = !ep.atomic && !ep.mask_src.p && !ep.accumulate && ep.C.fmt == FMT_F32;
-      const int c4 = lane;                                                           // BN = 128: lane owns 4 columns of every row
+      // BN / 4 lanes cover one row with four columns each: a 128-wide tile is one row per warp store (512 contiguous
+      // bytes), a 64-wide tile two rows of 256 bytes
+      constexpr int CPR = BN / 4, RPI = 32 / CPR, UNR = RPW / RPI;
+      static_assert(BN == 128 || BN == 64, "the epilogue maps BN/4 lanes to one row");
+      const int c4 = lane % CPR, rsub = lane / CPR;
       const int n = n0 + c4 * 4;
-      static_assert(BN == 128, "the epilogue maps one lane to four columns");
       if (n < N && r_end > r_begin) {
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.bias) bv = __ldg((const float4*)(ep.bias + n));
         const uint32_t rbase = wbase + (uint32_t)(c4 * 16);
+        const float floor_v = ep.relu ? 0.f : -INFINITY;
         if (plain) {
-          // hot path, branch-free: every data-dependent branch costs its full latency
-          // (measured: 280 cycles per row in the generic loop, 9 k cycles per tile)
-          const float floor_v = ep.relu ? 0.f : -INFINITY;
+          // hot path: all loads of the warp's rows first, then the stores (every data-dependent branch costs its full latency:
+          // measured 280 cycles per row in a generic loop, 9 k cycles per tile)
           float* cp = (float*)ep.C.p + row_base * ep.C.ld + n;
-          int r = r_begin;
-          for (; r + 8 <= r_end; r += 8) {
-            float4 v[8];
+          float4 v[UNR];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(rbase + (uint32_t)((r + u) * LDS_ROW * 4)));
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              v[u].x = fmaxf(v[u].x + bv.x, floor_v); v[u].y = fmaxf(v[u].y + bv.y, floor_v);
-              v[u].z = fmaxf(v[u].z + bv.z, floor_v); v[u].w = fmaxf(v[u].w + bv.w, floor_v);
-              *(float4*)(cp + (int64_t)(r + u) * ep.C.ld) = v[u];
-            }
+          for (int u = 0; u < UNR; ++u) {
+            const int r = r_begin + u * RPI + rsub;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(rbase + (uint32_t)(r * LDS_ROW * 4)));
           }
-          for (; r < r_end; ++r) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rbase + (uint32_t)(r * LDS_ROW * 4)));
-            v.x = fmaxf(v.x + bv.x, floor_v); v.y = fmaxf(v.y + bv.y, floor_v); v.z = fmaxf(v.z + bv.z, floor_v); v.w = fmaxf(v.w + bv.w, floor_v);
-            *(float4*)(cp + (int64_t)r * ep.C.ld) = v;
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int r = r_begin + u * RPI + rsub;
+            v[u].x = fmaxf(v[u].x + bv.x, floor_v); v[u].y = fmaxf(v[u].y + bv.y, floor_v);
+            v[u].z = fmaxf(v[u].z + bv.z, floor_v); v[u].w = fmaxf(v[u].w + bv.w, floor_v);
+            if (r < r_end) *(float4*)(cp + (int64_t)r * ep.C.ld) = v[u];
           }
         } else if (ep.atomic) {
-          for (int r = r_begin; r < r_end; ++r) {
+          // split-K slice: fp32 atomic add into the (pre-zeroed or accumulated-into) output; the bias rides on slice 0, a
+          // ReLU-backward mask is linear and applies per slice
+          const bool has_mask = ep.mask_src.p != nullptr;
+          for (int r = r_begin + rsub; r < r_end; r += RPI) {
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rbase + (uint32_t)(r * LDS_ROW * 4)));
+            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+            if (has_mask) {
+              const float4 mk = ld4(ep.mask_src, row_base + r, n);
+              v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f; v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+            }
             float* c = (float*)ep.C.p + (row_base + r) * ep.C.ld + n;
             atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
           }
         } else {
-          // any output format, ReLU-backward mask, accumulate-into-gradient: four rows per trip, every global load of the
-          // trip issued before the first use (the flags are warp-uniform: predicated, no divergence)
-          const float floor_v = ep.relu ? 0.f : -INFINITY;
+          // any output format, ReLU-backward mask, accumulate-into-gradient: every global load of the trip issued before
+          // the first use (the flags are warp-uniform: predicated, no divergence)
           const bool has_mask = ep.mask_src.p != nullptr, acc_c = ep.accumulate != 0;
-          for (int r = r_begin; r < r_end; r += 4) {
-            float4 v[4], mk[4], o[4];
+          constexpr int U2 = UNR < 4 ? UNR : 4;
+          for (int r0 = r_begin; r0 < r_end; r0 += U2 * RPI) {
+            float4 v[U2], mk[U2], o[U2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const bool ok = r + u < r_end;
-              const int64_t row = row_base + (ok ? r + u : r);
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(rbase + (uint32_t)((ok ? r + u : r) * LDS_ROW * 4)));
+            for (int u = 0; u < U2; ++u) {
+              const int r = r0 + u * RPI + rsub;
+              const bool ok = r < r_end;
+              const int rr = ok ? r : r_begin;
+              const int64_t row = row_base + rr;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(rbase + (uint32_t)(rr * LDS_ROW * 4)));
               mk[u] = has_mask ? ld4(ep.mask_src, row, n) : make_float4(1.f, 1.f, 1.f, 1.f);
               o[u] = acc_c ? ld4(ep.C, row, n) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (r + u >= r_end) break;
+            for (int u = 0; u < U2; ++u) {
+              const int r = r0 + u * RPI + rsub;
+              if (r >= r_end) continue;
               float4 w;
               w.x = fmaxf(v[u].x + bv.x, floor_v); w.y = fmaxf(v[u].y + bv.y, floor_v);
               w.z = fmaxf(v[u].z + bv.z, floor_v); w.w = fmaxf(v[u].w + bv.w, floor_v);
               w.x = (mk[u].x > 0.f ? w.x : 0.f) + o[u].x; w.y = (mk[u].y > 0.f ? w.y : 0.f) + o[u].y;
               w.z = (mk[u].z > 0.f ? w.z : 0.f) + o[u].z; w.w = (mk[u].w > 0.f ? w.w : 0.f) + o[u].w;
-              st4(ep.C, row_base + r + u, n, w);
+              st4(ep.C, row_base + r, n, w);
             }
           }
         }
@@ -740,9 +762,15 @@ inline bool tc_shape_ok(int layout, int M, int N, int K) {
   return M % 8 == 0;                                  // A [K,M], B [K,N]: the reduction length is free
 }
 
+// Tile width: 128 x 128 tiles are tensor-pipe-bound per k-block (twelve 128x128x8 TS-mode tf32 MMAs = ~1170 cycles against
+// ~650 for the operand split), so when the 128-wide grid fills at most half the chip - batches up to ~2k rows against a
+// 512-wide layer - 128 x 64 tiles double the CTAs and halve the per-tile MMA time: the k-loop of every CTA gets ~1.8x shorter.
 inline int launch_tc_gemm(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
-  if (g.kind == 0) return tc_launch_major<0, 128>(g, num_sms, st);
-  return tc_launch_major<1, 128>(g, num_sms, st);
+  const int t128 = ((g.M + TC_BM - 1) / TC_BM) * ((g.N + 127) / 128);
+  static const int force_bn = [] { const char* e = getenv("FB200_TC_BN"); return e ? atoi(e) : 0; }();     // A/B measurements
+  const bool narrow = force_bn ? force_bn == 64 : (2 * t128 <= num_sms && g.N >= 64);
+  if (g.kind == 0) return narrow ? tc_launch_major<0, 64>(g, num_sms, st) : tc_launch_major<0, 128>(g, num_sms, st);
+  return narrow ? tc_launch_major<1, 64>(g, num_sms, st) : tc_launch_major<1, 128>(g, num_sms, st);
 }
 
 

@@ -96,6 +96,7 @@ def lib():
     sig("fb200_head_train_step", i32, dp, pp, vp, vp, vp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp)
     sig("fb200_head_train_step_dp", i32, dp, pp, vp, vp, vp, vp, vp, pp, u64, u64, vp, vp, vp, vp, vp, vp, vp, vp, vp)
     sig("fb200_dp_bucket_split", i64, dp)
+    sig("fb200_dp_allreduce", i32, vp, pp, C.POINTER(i64), i32, i32, i32, i32, pp, vp, i32, vp)
     f32 = C.c_float
     sig("fb200_gemm", i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, vp, sz, vp)
     sig("fb200_gemm_workspace_bytes", i32, i32, i32, i32, i32, i32, C.POINTER(sz))

@@ -187,13 +187,16 @@ class MultimodalModel(nn.Module):
                                        [None if p is None else p.detach() for p in params], *[params[s] for s in slots])
 
     # ------------------------------------------------------------------ fused train step (opt-in)
-    def forward_loss(self, image, text_metadata, label, class_weights=None, denom=None, zero_grad=True, mid_event=None):
+    def forward_loss(self, image, text_metadata, label, class_weights=None, denom=None, zero_grad=True, mid_event=None, flat_out=None):
         """forward + weighted CE + backward of the head in ONE library call.
 
         Writes ``.grad`` of every live head parameter (views of one flat buffer, summed into
         existing grads unless ``zero_grad``), back-propagates into the backbone when it has
         trainable parameters, and returns (loss, logits) as device tensors without syncing.
         ``denom``: device scalar with the global sum of class weights (data parallel runs).
+        ``flat_out``: caller-owned fp32 tensor of at least ``_lib.grad_layout(desc)[0]`` elements that receives the flat
+        gradient buffer (data parallel: a symmetric-memory buffer, dp.SymmetricGradBucket, so that the all-reduce kernel
+        works on it in place).
         ``mid_event``: a recorded-once ``torch.cuda.Event``; the library records it as soon as every gradient below
         ``_lib.dp_bucket_split(desc)`` in ``flat_grad`` is final (fb200_head_train_step_dp) - dp.BucketedAllReduce
         all-reduces that bucket while the remaining weight gradients are still being computed."""
@@ -215,7 +218,12 @@ class MultimodalModel(nn.Module):
         dev = x.device
         ws = torch.empty(_lib.workspace_bytes(desc), dtype=torch.uint8, device=dev)
         total, offs = _lib.grad_layout(desc)
-        flat = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+        if flat_out is not None:
+            if flat_out.dtype != torch.float32 or flat_out.device != dev or flat_out.numel() < total or not flat_out.is_contiguous():
+                raise ValueError(f"flat_out must be a contiguous fp32 tensor on {dev} with at least {total} elements")
+            flat = flat_out
+        else:
+            flat = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
         logits = torch.empty(B, cfg["C"], dtype=torch.float32, device=dev)
         loss_out = torch.empty(3, dtype=torch.float32, device=dev)
         d_img = torch.empty_like(x) if need_dimg else None
@@ -263,20 +271,27 @@ class GraphedTrainStep:
         x.copy_(next_x); ...; step.run(); optimizer.step()
     """
 
-    def __init__(self, model, image, text_metadata, label, class_weights=None, denom=None, warmup=2, mid_event=None):
+    def __init__(self, model, image, text_metadata, label, class_weights=None, denom=None, warmup=2, mid_event=None, flat_out=None,
+                 after_step=None):
+        """``after_step``: optional callable run inside the capture right after the step (data parallel: the gradient
+        all-reduce, so that one graph launch = step + collective)."""
         if any(p.requires_grad for p in model.image_encoder.parameters()):
             raise ValueError("GraphedTrainStep captures the head only: use a frozen backbone (or feed features)")
-        self.model, self.args = model, (image, text_metadata, label, class_weights, denom, True, mid_event)
+        self.model, self.args = model, (image, text_metadata, label, class_weights, denom, True, mid_event, flat_out)
         self.mid_event = mid_event
         side = torch.cuda.Stream(device=image.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 model.forward_loss(*self.args)
+                if after_step is not None:
+                    after_step(model.flat_grad)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.logits = model.forward_loss(*self.args)
+            if after_step is not None:
+                after_step(model.flat_grad)
         self.flat_grad = model.flat_grad
         self.desc = model.last_desc
 
