@@ -76,6 +76,10 @@ struct Ctx {
   void* mid_event = nullptr;  // fb200_head_train_step_dp: recorded once every gradient below Plan::dp_split is final
   // persistent step kernel (Plan::use_mega): the executors emit ops into `mega` instead of launching kernels.  Stage in which
   // a buffer is complete: vready per activation value, gready per activation gradient, pready per parameter gradient.
+  // large batches, fused train step: the classifier tail (last LayerNorm -> head -> cross entropy -> their backward) is ONE launch
+  bool tail_fuse = false; int tail_ln_op = -1, tail_head_op = -1; bool tail_have_fwd = false;
+  TailArgs tail{};
+  std::vector<GemmArgs> deferred_simt_dw;      // FFMA weight gradients of a tcgen05 step: launched beside the grouped dW, not in the dX chain
   MegaBuilder* mega = nullptr;
   std::vector<int> vready, gready; int pready[NUM_SLOTS] = {};
   int vr(int b) const { return b >= 0 ? vready[b] : 0; }
@@ -262,6 +266,7 @@ static int run_forward(Ctx& c) {
             c.row_emitted(mout, tiles, true, o.out.buf);
             break;
           }
+          if (c.tail_fuse && (int)(&o - p.ops.data()) == c.tail_head_op) { c.tail.head_fwd = a; break; }      // runs inside the tail kernel
           CUDA_OK(launch_smalln_fwd(a, c.dev.num_sms, c.st));
           break;
         }
@@ -283,6 +288,7 @@ static int run_forward(Ctx& c) {
           c.row_emitted(mout, tiles, a.N <= 512, o.out.buf);
           break;
         }
+        if (c.tail_fuse && (int)(&o - p.ops.data()) == c.tail_ln_op) { c.tail.ln_fwd = a; c.tail_have_fwd = true; break; }   // runs inside the tail kernel
         const int grid = row_grid_for(B, a.N, c.dev.num_sms);
 #define CALL(NV, TPR) pdl_launch(lnrd_fwd_kernel<NV, TPR>, grid, ROW_WARPS * 32, 0, c.st, a)
         if (!c.gemm_only) FB200_ROW_DISPATCH(a.N, CALL);
@@ -415,6 +421,11 @@ static int run_backward(Ctx& c) {
             a.dx = c.grad(o.dx_view); a.dx_accumulate = is_written(o.dx_view);
             if (p.acts[o.in0.buf].relu_out) a.mask_src = c.value(o.in0);
           }
+          if (c.tail_fuse && oi == c.tail_head_op) {                // ran inside the tail kernel
+            c.tail.head_bwd = a; pwritten[o.w_slot] = 1;
+            if (a.dx.p) set_written(o.dx_view);
+            break;
+          }
           if (c.mega) {
             const int tiles = (B + ROW_WARPS - 1) / ROW_WARPS; bool chain;
             const int st = c.row_stage({{c.gr(o.out.buf), o.out.buf, true}, {a.dx.p ? c.gr(o.dx_view.buf) : 0, a.dx.p ? o.dx_view.buf : -1, true}}, tiles, true, chain);
@@ -437,6 +448,8 @@ static int run_backward(Ctx& c) {
         g.accumulate = pwritten[o.w_slot]; g.split_k = 0; g.colsum_a = c.pgrad(o.b_slot, o.w_row0);
         if (c.mega) {               // the weight gradient has no consumer: all of them run after the dX chain, as the last stage(s)
           mega_dw.push_back({g, o.w_slot, c.gr(o.out.buf)});
+        } else if (p.use_tc && !c.gemm_only) {
+          c.deferred_simt_dw.push_back(g);   // e.g. text_fc.0 (K = 85 is not TMA-legal): beside the grouped tcgen05 weight gradients, on the side lane
         } else CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
         pwritten[o.w_slot] = 1;
         // dX[B,K] (+)= dY W, masked by the producer's ReLU when the input came out of Linear+ReLU
@@ -462,6 +475,11 @@ static int run_backward(Ctx& c) {
         a.gamma = c.param(o.ln_w[0]); a.stats = (float*)(c.ws + o.stats_off);
         a.dgamma = c.pgrad(o.ln_w[0]); a.dbeta = c.pgrad(o.ln_b[0]); a.drop = c.drop(o); a.B = B; a.N = o.out.cols;
         if (is_written(o.in0)) return FB200_EUNSUPPORTED;     // LN input has exactly one consumer in every program
+        if (c.tail_fuse && oi == c.tail_ln_op) {                // the tail kernel: launched HERE, at the position of its last member
+          c.tail.ln_bwd = a;
+          CUDA_OK(launch_tail_chain(c.tail, c.dev.num_sms, c.st));
+          set_written(o.in0); break;
+        }
         if (c.mega) {
           const int tiles = MegaBuilder::row_tiles(B, a.N); bool chain;
           const int st = c.row_stage({{c.gr(o.out.buf), o.out.buf, true}, {c.gr(o.in0.buf), o.in0.buf, true}}, tiles, a.N <= 512, chain);
@@ -554,6 +572,8 @@ static int run_backward(Ctx& c) {
   // next to the grouped weight-gradient launch (tensor-bound) instead of after it.
   { int rc = ls.begin(c, 0); if (rc != FB200_OK) return rc; }
   c.st = c.lane_st[1];
+  for (auto& g : c.deferred_simt_dw) CUDA_OK(launch_simt_gemm(g, c.dev.num_sms, c.st));
+  c.deferred_simt_dw.clear();
   for (size_t base = 0; base < colsums.size(); base += 24) {
     ColsumBatch cb{}; cb.B = B; cb.nseg = 0;
     for (size_t i = base; i < colsums.size() && cb.nseg < 24; ++i) cb.seg[cb.nseg++] = colsums[i];
@@ -634,7 +654,7 @@ static void mega_emit_ce(Ctx& c, const void* logits, const int64_t* labels, cons
   const Plan& p = c.p;
   const int tiles = (p.d.B + ROW_WARPS - 1) / ROW_WARPS; bool chain;
   const int st = c.row_stage({{c.vr(p.logits.buf), p.logits.buf, false}}, tiles, true, chain);
-  c.mega->add_row(MR_CE, st, tiles, chain).u.ce = CeArgs{(const float*)logits, labels, class_w, denom, loss_out, (float*)dlogits, p.d.B, p.d.C};
+  c.mega->add_row(MR_CE, st, tiles, chain).u.ce = CeArgs{(const float*)logits, labels, class_w, denom, loss_out, (float*)dlogits, p.d.B, p.d.C, nullptr};
   c.gready.assign(p.acts.size(), 0);
   c.gready[p.logits.buf] = st;
   c.row_emitted(st, tiles, true, -1, p.logits.buf);
@@ -1005,6 +1025,21 @@ int fb200_head_train_step_dp(const fb200_desc* d, const void* const* params, con
         (float*)grads, masks, seed, offset, (const uint64_t*)rng_state, w, (cudaStream_t)stream, dev};
   c.mid_event = mid_event;
   MegaBuilder mb; mega_begin(c, mb);
+  if (!c.mega && !c.gemm_only) {
+    // the program ends with LayerNorm+ReLU+dropout (<= 512 wide) -> C-wide classifier head into the logits: fuse the tail
+    // Measured on B200 (cfg2, B = 4096): 0.758 ms per step with the fused tail against 0.737 ms with its six kernels - one
+    // wave of 512 CTAs walking five cold bodies in turn loses to six fully parallel launches overlapped by PDL.  Kept behind
+    // FB200_TAIL_FUSE=1 (the persistent step kernel chains the same bodies for small batches, where launches dominate).
+    static const bool on = [] { const char* e = getenv("FB200_TAIL_FUSE"); return e && e[0] == '1'; }();
+    const int n = (int)plan.ops.size();
+    if (on && n >= 2) {
+      const Op& hd = plan.ops[n - 1]; const Op& ln = plan.ops[n - 2];
+      if (hd.kind == OP_LINEAR && hd.engine == 0 && plan.acts[hd.out.buf].ext == 3 && smalln_ok(hd.out.cols, hd.in0.cols) && !hd.relu &&
+          ln.kind == OP_LNRD && ln.out.buf == hd.in0.buf && ln.out.cols <= 512 && hd.in0.cols % 4 == 0) {
+        c.tail_fuse = true; c.tail_ln_op = n - 2; c.tail_head_op = n - 1;
+      }
+    }
+  }
   rc = run_forward(c);
   if (rc != FB200_OK) return rc;
   if (c.mega) {
@@ -1013,6 +1048,15 @@ int fb200_head_train_step_dp(const fb200_desc* d, const void* const* params, con
     rc = run_backward(c);
     if (rc != FB200_OK) return rc;
     return mega_finish(c);
+  }
+  if (c.tail_fuse && c.tail_have_fwd) {
+    // cross entropy inside the tail kernel: loss_out accumulates by atomics, the batch's own weight sum comes from a 1-CTA kernel
+    float* den_local = (float*)(w + plan.mega_bar_off);          // 256 spare bytes of the workspace (unused outside the step kernel)
+    CUDA_OK(cudaMemsetAsync(loss_out, 0, 3 * sizeof(float), c.st));
+    pdl_launch(ce_den_kernel, 1, 256, 0, c.st, labels, class_w, d->B, d->C, den_local);
+    CUDA_OK(cudaGetLastError());
+    c.tail.ce = CeArgs{(const float*)logits, labels, class_w, denom, loss_out, dlog, d->B, d->C, den_local};
+    return run_backward(c);
   }
   rc = ce_launch(logits, labels, class_w, denom, d->B, d->C, loss_out, dlog, c.st);
   if (rc != FB200_OK) return rc;

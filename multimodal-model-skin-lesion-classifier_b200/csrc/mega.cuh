@@ -49,7 +49,8 @@ struct MGemm {                 // one GEMM op of a stage (fp32, row-major views)
 
 enum MRowKind : int { MR_LNRD_FWD = 0, MR_LNRD_BWD, MR_GATE_FWD, MR_GATE_BWD, MR_GRB_FWD, MR_GRB_BWD, MR_META_FWD, MR_META_BWD,
                       MR_SMALLN_FWD, MR_SMALLN_BWD, MR_CE, MR_REDUCE };
-struct CeArgs { const float* logits; const int64_t* labels; const float* class_w; const float* denom; float* loss_out; float* dlogits; int B, C; };
+struct CeArgs { const float* logits; const int64_t* labels; const float* class_w; const float* denom; float* loss_out; float* dlogits; int B, C;
+                const float* den_local; /* optional: this batch's sum of w[y], precomputed (large batches) */ };
 struct ReduceArgs { const float* part; float* y; const float* bias; int splits, M, N, ldy, relu; };
 struct MRowOp {
   int kind, tiles, stage;
@@ -330,11 +331,14 @@ __device__ __forceinline__ void mega_run_gemm(const MGemm& g, int tile, float* s
 __device__ __forceinline__ void ce_rows_body(const CeArgs& a, int bid, int nblk, float* sm /* >= ROW_WARPS floats */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float den_local = 0.f;
-  for (int r = lane; r < a.B; r += 32) {
-    const int64_t yl = a.labels[r];
-    den_local += (yl >= 0 && yl < a.C) ? (a.class_w ? __ldg(a.class_w + (int)yl) : 1.f) : 0.f;      // ignore_index and anything out of range weigh nothing
+  if (a.den_local) den_local = __ldcg(a.den_local);
+  else {
+    for (int r = lane; r < a.B; r += 32) {
+      const int64_t yl = a.labels[r];
+      den_local += (yl >= 0 && yl < a.C) ? (a.class_w ? __ldg(a.class_w + (int)yl) : 1.f) : 0.f;    // ignore_index and anything out of range weigh nothing
+    }
+    den_local = warp_sum(den_local);
   }
-  den_local = warp_sum(den_local);
   const float den = a.denom ? __ldcg(a.denom) : den_local;
   const float inv_den = 1.f / den;
   float num = 0.f;
@@ -380,6 +384,46 @@ __device__ __forceinline__ void reduce_body(const ReduceArgs& a, int bid, int nb
     if (a.relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
     *(float4*)(a.y + (int64_t)m * a.ldy + n) = s;
   }
+}
+
+// ----------------------------------------------------------------------------- the classifier tail as ONE kernel (large batches)
+// dropout(relu(LN(z2))) -> classifier head -> weighted cross entropy -> head backward -> LayerNorm backward are all row-wise
+// on rows up to 512 wide with the same row -> warp mapping, so one launch runs the five bodies back to back (a CTA only ever
+// touches its own rows; __syncthreads makes its global writes visible to its next body): 6 launches -> 1 (+ the 1-CTA
+// denominator kernel below, off the critical path), "classifier fused with the loss" of SURVEY.md 2.1 K5/K6.
+struct TailArgs { LnrdArgs ln_fwd; SmallNArgs head_fwd; CeArgs ce; SmallNArgs head_bwd; LnrdArgs ln_bwd; };
+template <int NV>
+__global__ void __launch_bounds__(ROW_WARPS * 32) tail_chain_kernel(const __grid_constant__ TailArgs a) { pdl_sync();
+  extern __shared__ __align__(16) float tail_smem[];
+  float* red = tail_smem; float2* scratch = (float2*)(tail_smem + ROW_WARPS * 512); float* sm_dw = tail_smem + ROW_WARPS * 512 + 64;
+  const int bid = blockIdx.x, nblk = gridDim.x;
+  lnrd_fwd_body<NV, 32>(a.ln_fwd, bid, nblk, scratch, red); __syncthreads();
+  smalln_fwd_body<8>(a.head_fwd, bid, nblk); __syncthreads();
+  ce_rows_body(a.ce, bid, nblk, red); __syncthreads();
+  if (a.head_bwd.K <= 128) smalln_bwd_body<8, 1>(a.head_bwd, bid, nblk, sm_dw);
+  else if (a.head_bwd.K <= 256) smalln_bwd_body<8, 2>(a.head_bwd, bid, nblk, sm_dw);
+  else smalln_bwd_body<8, 4>(a.head_bwd, bid, nblk, sm_dw);
+  __syncthreads();
+  lnrd_bwd_body<NV, 32>(a.ln_bwd, bid, nblk, scratch, red);
+}
+// this batch's sum of class weights over its labels (the denominator of nn.CrossEntropyLoss(weight, reduction='mean')): one CTA
+__global__ void __launch_bounds__(256) ce_den_kernel(const int64_t* __restrict__ labels, const float* __restrict__ class_w, int B, int C, float* __restrict__ out) { pdl_sync();
+  __shared__ float s[8];
+  float d = 0.f;
+  for (int r = threadIdx.x; r < B; r += 256) { const int64_t y = labels[r]; d += (y >= 0 && y < C) ? (class_w ? __ldg(class_w + (int)y) : 1.f) : 0.f; }
+  d = warp_sum(d);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += s[w]; *out = t; }
+}
+inline cudaError_t launch_tail_chain(const TailArgs& a, int num_sms, cudaStream_t st) {
+  int grid = (a.ln_fwd.B + ROW_WARPS - 1) / ROW_WARPS; if (grid > num_sms * 4) grid = num_sms * 4; if (grid < 1) grid = 1;
+  const size_t smem = (size_t)(ROW_WARPS * 512 + 64 + 8 * 512 + 8) * sizeof(float);
+  const int N = a.ln_fwd.N;
+  if (N <= 128) pdl_launch(tail_chain_kernel<1>, grid, ROW_WARPS * 32, smem, st, a);
+  else if (N <= 256) pdl_launch(tail_chain_kernel<2>, grid, ROW_WARPS * 32, smem, st, a);
+  else pdl_launch(tail_chain_kernel<4>, grid, ROW_WARPS * 32, smem, st, a);
+  return cudaGetLastError();
 }
 
 #define MEGA_ROW_CASE(KIND, BODY, ARGS)                                                        \

@@ -408,7 +408,7 @@ int build_plan(const fb200_desc& d, Plan& p) {
   }
   // small batches on the FFMA path: split-K fix-up scratch (partial tiles) + per-tile arrival counters
   if (!p.use_tc || d.B <= 128) { p.splitk_off = cur; p.splitk_bytes = (size_t)16 << 20; cur = align(cur + p.splitk_bytes); p.counters_off = cur; cur = align(cur + 4096 * sizeof(unsigned)); }
-  if (p.use_mega) { p.mega_bar_off = cur; cur = align(cur + 256); }
+  p.mega_bar_off = cur; cur = align(cur + 256);      // step-kernel barrier / fused-tail scalar scratch
   // tail: dlogits of the fused train step (exec.cu addresses it from the end)
   cur = align(cur + (size_t)d.B * d.C * sizeof(float));
   p.ws_bytes = cur + 256;
