@@ -311,12 +311,127 @@ __device__ __forceinline__ void mega_gemm_tn(const MGemm& g, int tile, float* sm
   }
 }
 
+// ----------------------------------------------------------------------------- Linear forward / dX, K split across the warps
+// The first version gave every warp 4 rows and the whole K range: each of the 8 warps then streams the whole 8-column slice
+// of W through L1 (128 KB of L1 wavefronts per task next to 64 KB of activations) and the task is bound by the ~64 B/clk of
+// the L1 data path (measured: ~3 us per 32 x 8 x 512 task).  Here the 32 x 8 output tile is shared by all warps and the
+// REDUCTION dimension is split: warp w takes the 32-wide k-chunks w, w+8, ...; inside a chunk lane (rq, kq) loads one
+// float4 of k for the rows rq, rq+4, ..., rq+28 (8 lanes x 16 B = one 128-byte line per row: coalesced) and the matching
+// 4 x 8 block of W.  Every activation and every weight element enters the SM once (80 KB per task).  The 64 partial sums of
+// a lane are transposed-reduced over the 8 k-lanes (56 shuffles), the 8 warps meet in 8 KB of shared memory, and thread t
+// finishes output (t / 8, t % 8).  LAYOUT 0: C = A B^T (B = W[n, k]); LAYOUT 1: C = A B (B = W[k, n]).
+template <int LAYOUT>
+__device__ __forceinline__ void mega_gemm_ksplit(const MGemm& g, int tile, float* smem, long long* tr) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, rq = lane >> 3, kq = lane & 7;
+  const int ct = (g.N + MEGA_CT - 1) / MEGA_CT, rgs = (g.M + 31) >> 5;
+  const int c_idx = tile % ct; tile /= ct;
+  const int rg = tile % rgs; const int kz = tile / rgs;
+  const int n0 = c_idx * MEGA_CT, m0 = rg * 32;
+  int k0 = 0, k1 = g.K;
+  if (LAYOUT == 0 && g.splits > 1) { const int per = (((g.K + g.splits - 1) / g.splits) + 127) & ~127; k0 = kz * per; k1 = min(g.K, k0 + per); }
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
+  float acc[8][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+  const float* arow[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const int r = m0 + rq + 4 * j; arow[j] = g.A.p + (int64_t)(r < g.M ? r : m0) * g.A.ld; }
+  const int nchunk = (k1 - k0 + 31) >> 5;
+  for (int ch = warp; ch < nchunk; ch += ROW_WARPS) {
+    const int k = k0 + ch * 32 + 4 * kq;
+    if (k < k1) {                                                 // K % 4 == 0: a float4 of k is in or out as a whole
+      float4 a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = __ldcg((const float4*)(arow[j] + k));
+      float b[4][8];                                              // b[i][c] = W element for reduction index k + i and output column n0 + c
+      if (LAYOUT == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 w = __ldg((const float4*)(g.B.p + (int64_t)(n0 + c < g.N ? n0 + c : n0) * g.B.ld + k));
+          b[0][c] = w.x; b[1][c] = w.y; b[2][c] = w.z; b[3][c] = w.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* wr = g.B.p + (int64_t)(k + i) * g.B.ld + n0;
+          const float4 w0 = __ldg((const float4*)wr), w1 = __ldg((const float4*)(wr + 4));
+          b[i][0] = w0.x; b[i][1] = w0.y; b[i][2] = w0.z; b[i][3] = w0.w; b[i][4] = w1.x; b[i][5] = w1.y; b[i][6] = w1.z; b[i][7] = w1.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          acc[j][c] = fmaf(a[j].x, b[0][c], fmaf(a[j].y, b[1][c], fmaf(a[j].z, b[2][c], fmaf(a[j].w, b[3][c], acc[j][c]))));
+    }
+  }
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
+  // transpose-reduce the 64 sums over the 8 k-lanes: lane-bit 1 keeps rows j in {0..3} / {4..7}, bit 2 halves again, bit 4 again:
+  // each lane ends with ONE row j = 4 (kq & 1) + (kq & 2) + (kq >> 2) and all 8 columns
+  float v32[4][8], v16[2][8], v8[8];
+  {
+    const bool up = (kq & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float send = up ? acc[j][c] : acc[j + 4][c], keep = up ? acc[j + 4][c] : acc[j][c];
+        v32[j][c] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+  }
+  {
+    const bool up = (kq & 2) != 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float send = up ? v32[j][c] : v32[j + 2][c], keep = up ? v32[j + 2][c] : v32[j][c];
+        v16[j][c] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+  }
+  {
+    const bool up = (kq & 4) != 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float send = up ? v16[0][c] : v16[1][c], keep = up ? v16[1][c] : v16[0][c];
+      v8[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  const int jrow = 4 * (kq & 1) + (kq & 2) + (kq >> 2);
+  const int row_local = rq + 4 * jrow;                            // 0 .. 31
+  __syncthreads();                                                // the previous task is done with the exchange buffer
+  float* mine = smem + warp * 256 + row_local * 8;
+  *(float4*)mine = make_float4(v8[0], v8[1], v8[2], v8[3]);
+  *(float4*)(mine + 4) = make_float4(v8[4], v8[5], v8[6], v8[7]);
+  __syncthreads();
+  float v = 0.f;
+#pragma unroll
+  for (int w = 0; w < ROW_WARPS; ++w) v += smem[w * 256 + threadIdx.x];      // warp order: bit-reproducible
+  if (tr && threadIdx.x == 0) tr[2] = clock64();
+  const int m = m0 + (threadIdx.x >> 3), n = n0 + (threadIdx.x & 7);
+  if (m < g.M && n < g.N) {
+    if (LAYOUT == 0) {
+      if (g.splits > 1) { g.C.p[((int64_t)kz * g.M + m) * g.C.ld + n] = v; return; }    // partial tile: bias / ReLU belong to the REDUCE task
+      if (g.bias) v += __ldg(g.bias + n);
+      if (g.relu) v = fmaxf(v, 0.f);
+      g.C.p[(int64_t)m * g.C.ld + n] = v;
+    } else {
+      if (g.mask.p && !(__ldcg(g.mask.p + (int64_t)m * g.mask.ld + n) > 0.f)) v = 0.f;
+      float* dst = g.C.p + (int64_t)m * g.C.ld + n;
+      if (g.accumulate) v += __ldcg(dst);
+      *dst = v;
+    }
+  }
+}
+
 __device__ __forceinline__ void mega_run_gemm(const MGemm& g, int tile, float* smem, long long* tr) {
   const bool a16 = ((((uintptr_t)g.A.p) | ((uintptr_t)g.B.p)) & 15) == 0 && g.A.ld % 4 == 0 && g.B.ld % 4 == 0;
   if (g.layout == MG_NT) {
-    if (a16 && g.K % 4 == 0) mega_gemm_nt<true>(g, tile, tr); else mega_gemm_nt<false>(g, tile, tr);
+    if (a16 && g.K % 4 == 0) mega_gemm_ksplit<0>(g, tile, smem, tr); else mega_gemm_nt<false>(g, tile, tr);
   } else if (g.layout == MG_NN) {
-    if ((((uintptr_t)g.B.p) & 15) == 0 && g.B.ld % 4 == 0 && g.N % MEGA_CT == 0) mega_gemm_nn<true>(g, tile, smem); else mega_gemm_nn<false>(g, tile, smem);
+    if (a16 && g.K % 4 == 0 && g.N % MEGA_CT == 0) mega_gemm_ksplit<1>(g, tile, smem, tr); else mega_gemm_nn<false>(g, tile, smem);
   } else {
     const bool c16 = (((uintptr_t)g.C.p) & 15) == 0 && g.C.ld % 4 == 0;
     if (a16 && c16 && g.M % 4 == 0 && g.N % 4 == 0) mega_gemm_tn<true>(g, tile, smem); else mega_gemm_tn<false>(g, tile, smem);
@@ -429,12 +544,12 @@ inline cudaError_t launch_tail_chain(const TailArgs& a, int num_sms, cudaStream_
 #define MEGA_ROW_CASE(KIND, BODY, ARGS)                                                        \
   case KIND: {                                                                                 \
     const int N_ = (ARGS).N;                                                                   \
-    if (N_ <= 128) BODY<1, 32>(ARGS, tile, op.tiles, scratch, red);                            \
-    else if (N_ <= 256) BODY<2, 32>(ARGS, tile, op.tiles, scratch, red);                       \
-    else if (N_ <= 512) BODY<4, 32>(ARGS, tile, op.tiles, scratch, red);                       \
-    else if (N_ <= 1024) BODY<1, 256>(ARGS, tile, op.tiles, scratch, red);                     \
-    else if (N_ <= 2048) BODY<2, 256>(ARGS, tile, op.tiles, scratch, red);                     \
-    else BODY<4, 256>(ARGS, tile, op.tiles, scratch, red);                                     \
+    if (N_ <= 128) BODY<1, 32, true>(ARGS, tile, op.tiles, scratch, red);                            \
+    else if (N_ <= 256) BODY<2, 32, true>(ARGS, tile, op.tiles, scratch, red);                       \
+    else if (N_ <= 512) BODY<4, 32, true>(ARGS, tile, op.tiles, scratch, red);                       \
+    else if (N_ <= 1024) BODY<1, 256, true>(ARGS, tile, op.tiles, scratch, red);                     \
+    else if (N_ <= 2048) BODY<2, 256, true>(ARGS, tile, op.tiles, scratch, red);                     \
+    else BODY<4, 256, true>(ARGS, tile, op.tiles, scratch, red);                                     \
   } break;
 
 __device__ __noinline__ void mega_run_row_fwd(const MRowOp& op, int tile, float2* scratch, float* red) {

@@ -43,20 +43,23 @@ struct Grp {
 };
 #define COL(i) (((i) * TPR + G.t) * 4)
 
-template <int NV, int TPR>
+// F32 = true: the view is known to be plain fp32 at compile time (the persistent step kernel is fp32 only) - the three-format
+// dispatch of ld4 / st4 disappears from the body, which matters for code that runs cold once per step.
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void row_load(const Grp<TPR>& G, const TRef& t, int64_t row, int N, float4 (&v)[NV]) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     int c = COL(i);
-    v[i] = (c < N) ? ld4(t, row, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (F32) v[i] = (c < N) ? __ldcg((const float4*)((const float*)t.p + row * t.ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    else v[i] = (c < N) ? ld4(t, row, c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-template <int NV, int TPR>
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void row_store(const Grp<TPR>& G, const TRef& t, int64_t row, int N, const float4 (&v)[NV]) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     int c = COL(i);
-    if (c < N) st4(t, row, c, v[i]);
+    if (c < N) { if (F32) *(float4*)((float*)t.p + row * t.ld + c) = v[i]; else st4(t, row, c, v[i]); }
   }
 }
 template <int NV, int TPR>
@@ -123,7 +126,7 @@ struct LnrdArgs {
   int B, N;
 };
 
-template <int NV, int TPR>
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void lnrd_fwd_body(const LnrdArgs& a, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
   float4 gam[NV], bet[NV];
@@ -131,7 +134,7 @@ __device__ __forceinline__ void lnrd_fwd_body(const LnrdArgs& a, const int bid, 
   row_load_param<NV, TPR>(G, a.beta, a.N, bet);
   for (int64_t row = G.row0; row < a.B; row += G.rstep) {
     float4 v[NV];
-    row_load<NV, TPR>(G, a.x, row, a.N, v);
+    row_load<NV, TPR, F32>(G, a.x, row, a.N, v);
     float mean, rstd;
     row_stats<NV, TPR>(G, v, a.N, mean, rstd, scratch);
     if (G.t == 0) { a.stats[row * 2] = mean; a.stats[row * 2 + 1] = rstd; }
@@ -146,7 +149,7 @@ __device__ __forceinline__ void lnrd_fwd_body(const LnrdArgs& a, const int bid, 
         v[i].w = fmaxf((v[i].w - mean) * rstd * gam[i].w + bet[i].w, 0.f) * m.w;
       }
     }
-    row_store<NV, TPR>(G, a.y, row, a.N, v);
+    row_store<NV, TPR, F32>(G, a.y, row, a.N, v);
   }
 }
 template <int NV, int TPR>
@@ -196,7 +199,7 @@ __device__ __forceinline__ void normalize(const Grp<TPR>& G, float4 (&v)[NV], fl
   }
 }
 
-template <int NV, int TPR>
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void lnrd_bwd_body(const LnrdArgs& a, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
   float4 gam[NV], dgam[NV], dbet[NV];
@@ -205,9 +208,9 @@ __device__ __forceinline__ void lnrd_bwd_body(const LnrdArgs& a, const int bid, 
   const float scale = a.drop.active ? 1.0f / (1.0f - a.drop.p) : 1.0f;
   for (int64_t row = G.row0; row < a.B; row += G.rstep) {
     float4 xh[NV], yv[NV], g[NV];
-    row_load<NV, TPR>(G, a.x, row, a.N, xh);
-    row_load<NV, TPR>(G, a.y, row, a.N, yv);
-    row_load<NV, TPR>(G, a.dy, row, a.N, g);
+    row_load<NV, TPR, F32>(G, a.x, row, a.N, xh);
+    row_load<NV, TPR, F32>(G, a.y, row, a.N, yv);
+    row_load<NV, TPR, F32>(G, a.dy, row, a.N, g);
     const float mean = a.stats[row * 2], rstd = a.stats[row * 2 + 1];
     normalize<NV, TPR>(G, xh, mean, rstd, a.N);
     // y > 0  <=>  kept by dropout AND ReLU active, so no mask is needed here
@@ -217,7 +220,7 @@ __device__ __forceinline__ void lnrd_bwd_body(const LnrdArgs& a, const int bid, 
       g[i].z = yv[i].z > 0.f ? g[i].z * scale : 0.f; g[i].w = yv[i].w > 0.f ? g[i].w * scale : 0.f;
     }
     ln_bwd_row<NV, TPR>(G, scratch, xh, g, gam, rstd, a.N, dgam, dbet);
-    row_store<NV, TPR>(G, a.dx, row, a.N, g);
+    row_store<NV, TPR, F32>(G, a.dx, row, a.N, g);
   }
   cta_colsum_atomic<NV, TPR>(G, dgam, a.N, a.dgamma, red);
   cta_colsum_atomic<NV, TPR>(G, dbet, a.N, a.dbeta, red);
@@ -234,19 +237,19 @@ struct GateArgs {
   int dx_accumulate;
   int B, N;
 };
-template <int NV, int TPR>
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void gate_fwd_body(const GateArgs& a, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
   for (int64_t row = G.row0; row < a.B; row += G.rstep) {
     float4 x[NV], z[NV];
-    row_load<NV, TPR>(G, a.x, row, a.N, x);
-    row_load<NV, TPR>(G, a.z, row, a.N, z);
+    row_load<NV, TPR, F32>(G, a.x, row, a.N, x);
+    row_load<NV, TPR, F32>(G, a.z, row, a.N, z);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       x[i].x *= 1.f / (1.f + expf(-z[i].x)); x[i].y *= 1.f / (1.f + expf(-z[i].y));
       x[i].z *= 1.f / (1.f + expf(-z[i].z)); x[i].w *= 1.f / (1.f + expf(-z[i].w));
     }
-    row_store<NV, TPR>(G, a.y, row, a.N, x);
+    row_store<NV, TPR, F32>(G, a.y, row, a.N, x);
   }
 }
 template <int NV, int TPR>
@@ -254,15 +257,15 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) gate_fwd_kernel(const GateArgs
   __shared__ float2 scratch[ROW_WARPS];
   gate_fwd_body<NV, TPR>(a, blockIdx.x, gridDim.x, scratch, nullptr);
 }
-template <int NV, int TPR>
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void gate_bwd_body(const GateArgs& a, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
   for (int64_t row = G.row0; row < a.B; row += G.rstep) {
     float4 x[NV], z[NV], dy[NV], dx[NV];
-    row_load<NV, TPR>(G, a.x, row, a.N, x);
-    row_load<NV, TPR>(G, a.z, row, a.N, z);
-    row_load<NV, TPR>(G, a.dy, row, a.N, dy);
-    if (a.dx_accumulate) row_load<NV, TPR>(G, a.dx, row, a.N, dx); else zero4<NV>(dx);
+    row_load<NV, TPR, F32>(G, a.x, row, a.N, x);
+    row_load<NV, TPR, F32>(G, a.z, row, a.N, z);
+    row_load<NV, TPR, F32>(G, a.dy, row, a.N, dy);
+    if (a.dx_accumulate) row_load<NV, TPR, F32>(G, a.dx, row, a.N, dx); else zero4<NV>(dx);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
 #define GATE1(f)                                              \
@@ -272,8 +275,8 @@ __device__ __forceinline__ void gate_bwd_body(const GateArgs& a, const int bid, 
       GATE1(x) GATE1(y) GATE1(z) GATE1(w)
 #undef GATE1
     }
-    row_store<NV, TPR>(G, a.dz, row, a.N, z);
-    row_store<NV, TPR>(G, a.dx, row, a.N, dx);
+    row_store<NV, TPR, F32>(G, a.dz, row, a.N, z);
+    row_store<NV, TPR, F32>(G, a.dx, row, a.N, dx);
   }
 }
 template <int NV, int TPR>
@@ -292,7 +295,7 @@ struct GrbArgs {
   DropSpec drop;
   int B, N;
 };
-template <int NV, int TPR>
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void grb_fwd_body(const GrbArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
   float4 gam[NV], bet[NV];
@@ -300,9 +303,9 @@ __device__ __forceinline__ void grb_fwd_body(const GrbArgs& p, const int bid, co
   row_load_param<NV, TPR>(G, p.beta, p.N, bet);
   for (int64_t row = G.row0; row < p.B; row += G.rstep) {
     float4 q[NV], a[NV], z[NV];
-    row_load<NV, TPR>(G, p.q, row, p.N, q);
-    row_load<NV, TPR>(G, p.a, row, p.N, a);
-    row_load<NV, TPR>(G, p.z, row, p.N, z);
+    row_load<NV, TPR, F32>(G, p.q, row, p.N, q);
+    row_load<NV, TPR, F32>(G, p.a, row, p.N, a);
+    row_load<NV, TPR, F32>(G, p.z, row, p.N, z);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       int c = COL(i);
@@ -321,7 +324,7 @@ __device__ __forceinline__ void grb_fwd_body(const GrbArgs& p, const int bid, co
       q[i].x = (q[i].x - mean) * rstd * gam[i].x + bet[i].x; q[i].y = (q[i].y - mean) * rstd * gam[i].y + bet[i].y;
       q[i].z = (q[i].z - mean) * rstd * gam[i].z + bet[i].z; q[i].w = (q[i].w - mean) * rstd * gam[i].w + bet[i].w;
     }
-    row_store<NV, TPR>(G, p.y, row, p.N, q);
+    row_store<NV, TPR, F32>(G, p.y, row, p.N, q);
   }
 }
 template <int NV, int TPR>
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p
   __shared__ float2 scratch[ROW_WARPS];
   grb_fwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, nullptr);
 }
-template <int NV, int TPR>
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void grb_bwd_body(const GrbArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
   float4 gam[NV], dgam[NV], dbet[NV];
@@ -337,10 +340,10 @@ __device__ __forceinline__ void grb_bwd_body(const GrbArgs& p, const int bid, co
   zero4<NV>(dgam); zero4<NV>(dbet);
   for (int64_t row = G.row0; row < p.B; row += G.rstep) {
     float4 q[NV], a[NV], z[NV], u[NV], du[NV];
-    row_load<NV, TPR>(G, p.q, row, p.N, q);
-    row_load<NV, TPR>(G, p.a, row, p.N, a);
-    row_load<NV, TPR>(G, p.z, row, p.N, z);
-    row_load<NV, TPR>(G, p.dy, row, p.N, du);
+    row_load<NV, TPR, F32>(G, p.q, row, p.N, q);
+    row_load<NV, TPR, F32>(G, p.a, row, p.N, a);
+    row_load<NV, TPR, F32>(G, p.z, row, p.N, z);
+    row_load<NV, TPR, F32>(G, p.dy, row, p.N, du);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       int c = COL(i);
@@ -357,7 +360,7 @@ __device__ __forceinline__ void grb_bwd_body(const GrbArgs& p, const int bid, co
     normalize<NV, TPR>(G, u, mean, rstd, p.N);
     ln_bwd_row<NV, TPR>(G, scratch, u, du, gam, rstd, p.N, dgam, dbet);     // du now holds d(u)
     float4 dq[NV];
-    if (p.dq_accumulate) row_load<NV, TPR>(G, p.dq, row, p.N, dq); else zero4<NV>(dq);
+    if (p.dq_accumulate) row_load<NV, TPR, F32>(G, p.dq, row, p.N, dq); else zero4<NV>(dq);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       int c = COL(i);
@@ -370,9 +373,9 @@ __device__ __forceinline__ void grb_bwd_body(const GrbArgs& p, const int bid, co
       GRB3(x) GRB3(y) GRB3(z) GRB3(w)
 #undef GRB3
     }
-    row_store<NV, TPR>(G, p.da, row, p.N, a);
-    row_store<NV, TPR>(G, p.dz, row, p.N, z);
-    row_store<NV, TPR>(G, p.dq, row, p.N, dq);
+    row_store<NV, TPR, F32>(G, p.da, row, p.N, a);
+    row_store<NV, TPR, F32>(G, p.dz, row, p.N, z);
+    row_store<NV, TPR, F32>(G, p.dq, row, p.N, dq);
   }
   cta_colsum_atomic<NV, TPR>(G, dgam, p.N, p.dgamma, red);
   cta_colsum_atomic<NV, TPR>(G, dbet, p.N, p.dbeta, red);
@@ -393,18 +396,18 @@ struct MetaArgs {
   float *dgamma_f, *dbeta_f, *dgamma_g, *dbeta_g;
   int B, N;
 };
-template <int NV, int TPR>
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void meta_fwd_body(const MetaArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
   for (int64_t row = G.row0; row < p.B; row += G.rstep) {
     float4 f[NV], g[NV], v[NV], pr[NV];
-    row_load<NV, TPR>(G, p.f, row, p.N, f);
-    row_load<NV, TPR>(G, p.g, row, p.N, g);
+    row_load<NV, TPR, F32>(G, p.f, row, p.N, f);
+    row_load<NV, TPR, F32>(G, p.g, row, p.N, g);
     float mf, rf, mg, rg;
     row_stats<NV, TPR>(G, f, p.N, mf, rf, scratch);
     row_stats<NV, TPR>(G, g, p.N, mg, rg, scratch);
     if (G.t == 0) { float4 s = make_float4(mf, rf, mg, rg); *(float4*)(p.stats + row * 4) = s; }
-    row_load<NV, TPR>(G, p.v, row, p.N, v);
+    row_load<NV, TPR, F32>(G, p.v, row, p.N, v);
     row_load_param<NV, TPR>(G, p.gamma_f, p.N, pr);
 #pragma unroll
     for (int i = 0; i < NV; ++i) { f[i].x = (f[i].x - mf) * rf * pr[i].x; f[i].y = (f[i].y - mf) * rf * pr[i].y; f[i].z = (f[i].z - mf) * rf * pr[i].z; f[i].w = (f[i].w - mf) * rf * pr[i].w; }
@@ -420,7 +423,7 @@ __device__ __forceinline__ void meta_fwd_body(const MetaArgs& p, const int bid, 
       f[i].x = 1.f / (1.f + expf(-(f[i].x + g[i].x + pr[i].x))); f[i].y = 1.f / (1.f + expf(-(f[i].y + g[i].y + pr[i].y)));
       f[i].z = 1.f / (1.f + expf(-(f[i].z + g[i].z + pr[i].z))); f[i].w = 1.f / (1.f + expf(-(f[i].w + g[i].w + pr[i].w)));
     }
-    row_store<NV, TPR>(G, p.y, row, p.N, f);
+    row_store<NV, TPR, F32>(G, p.y, row, p.N, f);
   }
 }
 template <int NV, int TPR>
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) meta_fwd_kernel(const MetaArgs
   meta_fwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, nullptr);
 }
 // Backward in two sweeps per row so that at most ~6 row-vectors are live (F up to 4096).
-template <int NV, int TPR>
+template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void meta_bwd_body(const MetaArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
   float4 dgf[NV], dbf[NV], dgg[NV], dbg[NV];
@@ -438,14 +441,14 @@ __device__ __forceinline__ void meta_bwd_body(const MetaArgs& p, const int bid, 
     const float4 st = *(const float4*)(p.stats + row * 4);
     float4 xf[NV], ds[NV], v[NV], pr[NV], pb[NV];
     // ds = dy * y (1 - y)
-    row_load<NV, TPR>(G, p.y, row, p.N, xf);
-    row_load<NV, TPR>(G, p.dy, row, p.N, ds);
+    row_load<NV, TPR, F32>(G, p.y, row, p.N, xf);
+    row_load<NV, TPR, F32>(G, p.dy, row, p.N, ds);
 #pragma unroll
     for (int i = 0; i < NV; ++i) { ds[i].x *= xf[i].x * (1.f - xf[i].x); ds[i].y *= xf[i].y * (1.f - xf[i].y); ds[i].z *= xf[i].z * (1.f - xf[i].z); ds[i].w *= xf[i].w * (1.f - xf[i].w); }
     // ---- f branch: t1 = LN_f(f); h = tanh(v t1); dt1 = ds (1-h^2) v; dv = ds (1-h^2) t1
-    row_load<NV, TPR>(G, p.f, row, p.N, xf);
+    row_load<NV, TPR, F32>(G, p.f, row, p.N, xf);
     normalize<NV, TPR>(G, xf, st.x, st.y, p.N);
-    row_load<NV, TPR>(G, p.v, row, p.N, v);
+    row_load<NV, TPR, F32>(G, p.v, row, p.N, v);
     row_load_param<NV, TPR>(G, p.gamma_f, p.N, pr);
     row_load_param<NV, TPR>(G, p.beta_f, p.N, pb);
     float4 dt1[NV];
@@ -463,20 +466,20 @@ __device__ __forceinline__ void meta_bwd_body(const MetaArgs& p, const int bid, 
     if (p.dv.p) {
       if (p.dv_accumulate) {
         float4 o[NV];
-        row_load<NV, TPR>(G, p.dv, row, p.N, o);
+        row_load<NV, TPR, F32>(G, p.dv, row, p.N, o);
 #pragma unroll
         for (int i = 0; i < NV; ++i) { v[i].x += o[i].x; v[i].y += o[i].y; v[i].z += o[i].z; v[i].w += o[i].w; }
       }
-      row_store<NV, TPR>(G, p.dv, row, p.N, v);
+      row_store<NV, TPR, F32>(G, p.dv, row, p.N, v);
     }
     ln_bwd_row<NV, TPR>(G, scratch, xf, dt1, pr, st.y, p.N, dgf, dbf);
-    row_store<NV, TPR>(G, p.df, row, p.N, dt1);
+    row_store<NV, TPR, F32>(G, p.df, row, p.N, dt1);
     // ---- g branch: dt2 = ds
-    row_load<NV, TPR>(G, p.g, row, p.N, xf);
+    row_load<NV, TPR, F32>(G, p.g, row, p.N, xf);
     normalize<NV, TPR>(G, xf, st.z, st.w, p.N);
     row_load_param<NV, TPR>(G, p.gamma_g, p.N, pr);
     ln_bwd_row<NV, TPR>(G, scratch, xf, ds, pr, st.w, p.N, dgg, dbg);
-    row_store<NV, TPR>(G, p.dg, row, p.N, ds);
+    row_store<NV, TPR, F32>(G, p.dg, row, p.N, ds);
   }
   cta_colsum_atomic<NV, TPR>(G, dgf, p.N, p.dgamma_f, red);
   cta_colsum_atomic<NV, TPR>(G, dbf, p.N, p.dbeta_f, red);
