@@ -246,14 +246,19 @@ __device__ __forceinline__ void mega_gemm_nn(const MGemm& g, int tile, float* sm
 // outputs.  The two operand tiles (A[:, m0..+31], B[:, n0..+127]) are staged in shared memory with one round trip to L2,
 // then warp = 4 rows m, lane = 4 columns n, the batch is the reduction loop over shared memory.
 constexpr int MEGA_TN_LDA = 36, MEGA_TN_LDB = 132;               // padded rows: conflict-free 128-bit reads
+constexpr int MEGA_TN_CPT = 4;                                   // 128-column chunks per task (vector path): the next chunk is prefetched under the current one
 template <bool VEC>
 __device__ __forceinline__ void mega_gemm_tn(const MGemm& g, int tile, float* smem) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = (g.N + 127) >> 7;
-  const int n_idx = tile % nt, m_idx = tile / nt;
-  const int m0 = m_idx * 32, n0 = n_idx * 128;
+  const int cpt = VEC ? g.splits : 1;                             // the builder sets splits = chunks per task for TN ops
+  const int ntask_n = (nt + cpt - 1) / cpt;
+  const int n_task = tile % ntask_n, m_idx = tile / ntask_n;
+  const int m0 = m_idx * 32;
+  const int ch0 = n_task * cpt, ch1 = min(nt, ch0 + cpt);
   float* As = smem;                                               // [K][36]
   float* Bs = smem + MEGA_MAX_B * MEGA_TN_LDA;                    // [K][132]
+  const int mw = warp * 4, nl = lane * 4;
   __syncthreads();
   if (VEC) {                                                      // M % 4 == 0, N % 4 == 0, aligned: whole float4s are in or out
     for (int i = threadIdx.x; i < g.K * 8; i += MEGA_THREADS) {
@@ -261,8 +266,8 @@ __device__ __forceinline__ void mega_gemm_tn(const MGemm& g, int tile, float* sm
       *(float4*)(As + k * MEGA_TN_LDA + c) = (m0 + c < g.M) ? __ldcg((const float4*)(g.A.p + (int64_t)k * g.A.ld + m0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int i = threadIdx.x; i < g.K * 32; i += MEGA_THREADS) {
-      const int k = i >> 5, c = (i & 31) * 4;
-      *(float4*)(Bs + k * MEGA_TN_LDB + c) = (n0 + c < g.N) ? __ldcg((const float4*)(g.B.p + (int64_t)k * g.B.ld + n0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = i >> 5, c = (i & 31) * 4, n = ch0 * 128 + c;
+      *(float4*)(Bs + k * MEGA_TN_LDB + c) = (n < g.N) ? __ldcg((const float4*)(g.B.p + (int64_t)k * g.B.ld + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else {
     for (int i = threadIdx.x; i < g.K * 32; i += MEGA_THREADS) {
@@ -270,44 +275,67 @@ __device__ __forceinline__ void mega_gemm_tn(const MGemm& g, int tile, float* sm
       As[k * MEGA_TN_LDA + c] = (m0 + c < g.M) ? __ldcg(g.A.p + (int64_t)k * g.A.ld + m0 + c) : 0.f;
     }
     for (int i = threadIdx.x; i < g.K * 128; i += MEGA_THREADS) {
-      const int k = i >> 7, c = i & 127;
-      Bs[k * MEGA_TN_LDB + c] = (n0 + c < g.N) ? __ldcg(g.B.p + (int64_t)k * g.B.ld + n0 + c) : 0.f;
+      const int k = i >> 7, c = i & 127, n = ch0 * 128 + c;
+      Bs[k * MEGA_TN_LDB + c] = (n < g.N) ? __ldcg(g.B.p + (int64_t)k * g.B.ld + n) : 0.f;
     }
   }
   __syncthreads();
-  const int mw = warp * 4, nl = lane * 4;
-  float acc[4][4], cs[4];
+  for (int ch = ch0; ch < ch1; ++ch) {
+    const int n0 = ch * 128;
+    // prefetch the next chunk's B tile into registers while this one is consumed from shared memory (K <= 64: <= 8 vectors per thread)
+    float4 pre[MEGA_MAX_B / 8];
+    const bool more = VEC && ch + 1 < ch1;
+    if (more) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { cs[i] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f; }
-#pragma unroll 4
-  for (int k = 0; k < g.K; ++k) {
-    const float4 a = *(const float4*)(As + k * MEGA_TN_LDA + mw);
-    const float4 b = *(const float4*)(Bs + k * MEGA_TN_LDB + nl);
-    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { cs[i] += av[i];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(av[i], bv[c], acc[i][c]); }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + mw + i, n = n0 + nl;
-    if (m >= g.M) break;
-    float* dst = g.C.p + (int64_t)m * g.C.ld + n;
-    if (VEC) {
-      if (n < g.N) {
-        float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        if (g.accumulate) { const float4 p = __ldcg((const float4*)dst); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-        *(float4*)dst = o;
+      for (int q = 0; q < MEGA_MAX_B / 8; ++q) {
+        const int i = threadIdx.x + q * MEGA_THREADS;
+        const int k = i >> 5, n = (ch + 1) * 128 + (i & 31) * 4;
+        pre[q] = (k < g.K && n < g.N) ? __ldcg((const float4*)(g.B.p + (int64_t)k * g.B.ld + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (n + c < g.N) { float o = acc[i][c]; if (g.accumulate) o += __ldcg(dst + c); dst[c] = o; }
     }
-    if (g.colsum && n_idx == 0 && lane == 0) atomicAdd(g.colsum + m, cs[i]);
+    float acc[4][4], cs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { cs[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.f; }
+#pragma unroll 4
+    for (int k = 0; k < g.K; ++k) {
+      const float4 a = *(const float4*)(As + k * MEGA_TN_LDA + mw);
+      const float4 b = *(const float4*)(Bs + k * MEGA_TN_LDB + nl);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { cs[i] += av[i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(av[i], bv[c], acc[i][c]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + mw + i, n = n0 + nl;
+      if (m >= g.M) break;
+      float* dst = g.C.p + (int64_t)m * g.C.ld + n;
+      if (VEC) {
+        if (n < g.N) {
+          float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          if (g.accumulate) { const float4 p = __ldcg((const float4*)dst); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+          *(float4*)dst = o;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (n + c < g.N) { float o = acc[i][c]; if (g.accumulate) o += __ldcg(dst + c); dst[c] = o; }
+      }
+      if (g.colsum && ch == 0 && lane == 0) atomicAdd(g.colsum + m, cs[i]);
+    }
+    if (more) {
+      __syncthreads();                                            // every warp is done reading the current B tile
+#pragma unroll
+      for (int q = 0; q < MEGA_MAX_B / 8; ++q) {
+        const int i = threadIdx.x + q * MEGA_THREADS;
+        const int k = i >> 5;
+        if (k < g.K) *(float4*)(Bs + k * MEGA_TN_LDB + (i & 31) * 4) = pre[q];
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -696,7 +724,11 @@ struct MegaBuilder {
     } else if (a.a_kc && !a.b_kc) {
       m.layout = MG_NN; m.tiles = rgs * ((a.N + MEGA_CT - 1) / MEGA_CT);
     } else if (!a.a_kc && !a.b_kc) {
-      m.layout = MG_TN; m.tiles = ((a.M + 31) / 32) * ((a.N + 127) / 128);
+      // vector path (same test as mega_run_gemm): several 128-column chunks per task, the next one prefetched under the current
+      const bool vec = ((((uintptr_t)a.A.p) | ((uintptr_t)a.B.p) | ((uintptr_t)a.C.p)) & 15) == 0 && a.A.ld % 4 == 0 && a.B.ld % 4 == 0 &&
+                       a.C.ld % 4 == 0 && a.M % 4 == 0 && a.N % 4 == 0;
+      const int nt = (a.N + 127) / 128, cpt = vec ? std::min(MEGA_TN_CPT, nt) : 1;
+      m.layout = MG_TN; m.splits = (short)cpt; m.tiles = ((a.M + 31) / 32) * ((nt + cpt - 1) / cpt);
     } else { overflow = true; return stage; }
     g.push_back(m);
     return stage;
