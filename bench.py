@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying one CUDA graph per step")
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"], help="GEMM engine policy (auto: tcgen05 from B > 32 in fp32, always in bf16)")
     ap.add_argument("--sweep", default="32,256,1024", help="comma-separated extra per-GPU batch sizes reported under 'sweep' ('' disables)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the token-attention and backbone end-to-end extras (profiling runs)")
     ap.add_argument("--no-incumbent", action="store_true", help="skip the GPU-eager reference (torch.nn on cuda) and the eager drop-in route")
     return ap.parse_args()
 
@@ -482,7 +483,7 @@ def main():
 
     # ---- the token-sequence attention kernel, timed alone: image tokens attending to metadata tokens
     extras = None
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         try:
             extras = {"mha_tokens": time_token_attention(torch, fb, dev)}
         except Exception as exc:                                    # never lose the headline line to an extra
@@ -589,11 +590,13 @@ def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype, model):
     bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     hbm = peaks.get("hbm_gbs", 6650.0)
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    traffic = None
-    try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    traffic, traffic_src = None, None
+    try:   # per-launch DRAM bytes of the dominant kernel: a profiler counter, so it comes from the committed ncu --set full
+           # capture of this round (tools/final_r02.sh), not from this run - the file name says which capture
+        traffic_src = "profiles/r02_dominant_kernel_traffic.json"
+        traffic = json.load(open(os.path.join(ROOT, traffic_src))).get("dram_bytes_per_launch")
     except Exception:
-        pass
+        traffic_src = None
     if dtype == "fp32":
         # fp32-strict GEMMs run as 3 TF32 MMAs per product: peak = cuBLAS TF32 8192^3, measured here, / 3
         tf32 = measure_tf32_peak(torch, dev)
@@ -603,7 +606,7 @@ def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype, model):
     else:
         peak, peak_note = bf16_peak, f"dense bf16 sustained, {src}"
     return {"bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05 GEMM family: forward NT, dX NN, dW TN of one train step)", "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_note": peak_note, "bf16_peak_tflops": bf16_peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_note": peak_note, "bf16_peak_tflops": bf16_peak,
             "hbm_gbs": hbm, "step_peak_tflops": peak, "gemm_ms_per_step": tot_ms, "gemm_launches_per_step": sum(shapes.values()),
             "how": "all GEMM launches of one train step replayed alone (fb200_debug_gemm_replay), CUDA events on the launch stream, eager launches",
             "top_shapes_single_launch": per[:6]}

@@ -40,6 +40,19 @@ struct Grp {
     for (int w = 0; w < ROW_WARPS; ++w) { float2 v = scratch[w]; r.x += v.x; r.y += v.y; }
     return r;
   }
+  // four sums in ONE group reduction (scratch: >= ROW_WARPS float4 = the same 128 bytes viewed as float2[16])
+  __device__ __forceinline__ float4 sum4(float a, float b, float c, float d, float2* scratch) const {
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+    if (TPR == 32) return make_float4(a, b, c, d);
+    float4* s4 = (float4*)scratch;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s4[threadIdx.x >> 5] = make_float4(a, b, c, d);
+    __syncthreads();
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < ROW_WARPS; ++w) { float4 v = s4[w]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+    return r;
+  }
 };
 #define COL(i) (((i) * TPR + G.t) * 4)
 
@@ -154,7 +167,7 @@ __device__ __forceinline__ void lnrd_fwd_body(const LnrdArgs& a, const int bid, 
 }
 template <int NV, int TPR>
 __global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_fwd_kernel(const LnrdArgs a) { pdl_sync();
-  __shared__ float2 scratch[ROW_WARPS];
+  __shared__ __align__(16) float2 scratch[2 * ROW_WARPS];
   lnrd_fwd_body<NV, TPR>(a, blockIdx.x, gridDim.x, scratch, nullptr);
 }
 
@@ -227,7 +240,7 @@ __device__ __forceinline__ void lnrd_bwd_body(const LnrdArgs& a, const int bid, 
 }
 template <int NV, int TPR>
 __global__ void __launch_bounds__(ROW_WARPS * 32) lnrd_bwd_kernel(const LnrdArgs a) { pdl_sync();
-  __shared__ float2 scratch[ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
+  __shared__ __align__(16) float2 scratch[2 * ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
   lnrd_bwd_body<NV, TPR>(a, blockIdx.x, gridDim.x, scratch, red);
 }
 
@@ -254,7 +267,7 @@ __device__ __forceinline__ void gate_fwd_body(const GateArgs& a, const int bid, 
 }
 template <int NV, int TPR>
 __global__ void __launch_bounds__(ROW_WARPS * 32) gate_fwd_kernel(const GateArgs a) { pdl_sync();
-  __shared__ float2 scratch[ROW_WARPS];
+  __shared__ __align__(16) float2 scratch[2 * ROW_WARPS];
   gate_fwd_body<NV, TPR>(a, blockIdx.x, gridDim.x, scratch, nullptr);
 }
 template <int NV, int TPR, bool F32 = false>
@@ -281,7 +294,7 @@ __device__ __forceinline__ void gate_bwd_body(const GateArgs& a, const int bid, 
 }
 template <int NV, int TPR>
 __global__ void __launch_bounds__(ROW_WARPS * 32) gate_bwd_kernel(const GateArgs a) { pdl_sync();
-  __shared__ float2 scratch[ROW_WARPS];
+  __shared__ __align__(16) float2 scratch[2 * ROW_WARPS];
   gate_bwd_body<NV, TPR>(a, blockIdx.x, gridDim.x, scratch, nullptr);
 }
 
@@ -329,7 +342,7 @@ __device__ __forceinline__ void grb_fwd_body(const GrbArgs& p, const int bid, co
 }
 template <int NV, int TPR>
 __global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p) { pdl_sync();
-  __shared__ float2 scratch[ROW_WARPS];
+  __shared__ __align__(16) float2 scratch[2 * ROW_WARPS];
   grb_fwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, nullptr);
 }
 template <int NV, int TPR, bool F32 = false>
@@ -382,7 +395,7 @@ __device__ __forceinline__ void grb_bwd_body(const GrbArgs& p, const int bid, co
 }
 template <int NV, int TPR>
 __global__ void __launch_bounds__(ROW_WARPS * 32) grb_bwd_kernel(const GrbArgs p) { pdl_sync();
-  __shared__ float2 scratch[ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
+  __shared__ __align__(16) float2 scratch[2 * ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
   grb_bwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, red);
 }
 
@@ -399,41 +412,54 @@ struct MetaArgs {
 template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void meta_fwd_body(const MetaArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
+  // r02: the four LayerNorm parameter vectors are loaded ONCE per CTA (r01 re-read them for every row), the three row
+  // operands are requested together, and the statistics of the two LayerNorms share their group reductions (2 instead of 4
+  // rounds of __syncthreads per row for rows wider than 512): at F = 1664, B = 4096 the r01 body ran at 2.3 TB/s.
+  float4 gf[NV], bf[NV], gg[NV], bg[NV];
+  row_load_param<NV, TPR>(G, p.gamma_f, p.N, gf); row_load_param<NV, TPR>(G, p.beta_f, p.N, bf);
+  row_load_param<NV, TPR>(G, p.gamma_g, p.N, gg); row_load_param<NV, TPR>(G, p.beta_g, p.N, bg);
+  const float invN = 1.f / (float)p.N;
   for (int64_t row = G.row0; row < p.B; row += G.rstep) {
-    float4 f[NV], g[NV], v[NV], pr[NV];
+    float4 f[NV], g[NV], v[NV];
     row_load<NV, TPR, F32>(G, p.f, row, p.N, f);
     row_load<NV, TPR, F32>(G, p.g, row, p.N, g);
-    float mf, rf, mg, rg;
-    row_stats<NV, TPR>(G, f, p.N, mf, rf, scratch);
-    row_stats<NV, TPR>(G, g, p.N, mg, rg, scratch);
-    if (G.t == 0) { float4 s = make_float4(mf, rf, mg, rg); *(float4*)(p.stats + row * 4) = s; }
     row_load<NV, TPR, F32>(G, p.v, row, p.N, v);
-    row_load_param<NV, TPR>(G, p.gamma_f, p.N, pr);
+    float sf = 0.f, sg = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) { f[i].x = (f[i].x - mf) * rf * pr[i].x; f[i].y = (f[i].y - mf) * rf * pr[i].y; f[i].z = (f[i].z - mf) * rf * pr[i].z; f[i].w = (f[i].w - mf) * rf * pr[i].w; }
-    row_load_param<NV, TPR>(G, p.beta_f, p.N, pr);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { f[i].x = tanhf(v[i].x * (f[i].x + pr[i].x)); f[i].y = tanhf(v[i].y * (f[i].y + pr[i].y)); f[i].z = tanhf(v[i].z * (f[i].z + pr[i].z)); f[i].w = tanhf(v[i].w * (f[i].w + pr[i].w)); }
-    row_load_param<NV, TPR>(G, p.gamma_g, p.N, pr);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { g[i].x = (g[i].x - mg) * rg * pr[i].x; g[i].y = (g[i].y - mg) * rg * pr[i].y; g[i].z = (g[i].z - mg) * rg * pr[i].z; g[i].w = (g[i].w - mg) * rg * pr[i].w; }
-    row_load_param<NV, TPR>(G, p.beta_g, p.N, pr);
+    for (int i = 0; i < NV; ++i) { sf += (f[i].x + f[i].y) + (f[i].z + f[i].w); sg += (g[i].x + g[i].y) + (g[i].z + g[i].w); }
+    const float2 m = G.sum2(sf, sg, scratch);
+    const float mf = m.x * invN, mg = m.y * invN;
+    float qf = 0.f, qg = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      f[i].x = 1.f / (1.f + expf(-(f[i].x + g[i].x + pr[i].x))); f[i].y = 1.f / (1.f + expf(-(f[i].y + g[i].y + pr[i].y)));
-      f[i].z = 1.f / (1.f + expf(-(f[i].z + g[i].z + pr[i].z))); f[i].w = 1.f / (1.f + expf(-(f[i].w + g[i].w + pr[i].w)));
+      if (COL(i) < p.N) {
+        float a = f[i].x - mf, b = f[i].y - mf, c = f[i].z - mf, d = f[i].w - mf; qf += (a * a + b * b) + (c * c + d * d);
+        a = g[i].x - mg; b = g[i].y - mg; c = g[i].z - mg; d = g[i].w - mg; qg += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    const float2 q = G.sum2(qf, qg, scratch);
+    const float rf = rsqrtf(q.x * invN + LN_EPS), rg = rsqrtf(q.y * invN + LN_EPS);
+    if (G.t == 0) *(float4*)(p.stats + row * 4) = make_float4(mf, rf, mg, rg);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#define MBF(c)                                                                         \
+      { const float t1 = (f[i].c - mf) * rf * gf[i].c + bf[i].c;                       \
+        const float t2 = (g[i].c - mg) * rg * gg[i].c + bg[i].c;                       \
+        f[i].c = 1.f / (1.f + expf(-(tanhf(v[i].c * t1) + t2))); }
+      MBF(x) MBF(y) MBF(z) MBF(w)
+#undef MBF
     }
     row_store<NV, TPR, F32>(G, p.y, row, p.N, f);
   }
 }
 template <int NV, int TPR>
 __global__ void __launch_bounds__(ROW_WARPS * 32) meta_fwd_kernel(const MetaArgs p) { pdl_sync();
-  __shared__ float2 scratch[ROW_WARPS];
+  __shared__ __align__(16) float2 scratch[2 * ROW_WARPS];
   meta_fwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, nullptr);
 }
 // Backward in two sweeps per row so that at most ~6 row-vectors are live (F up to 4096).
 template <int NV, int TPR, bool F32 = false>
-__device__ __forceinline__ void meta_bwd_body(const MetaArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
+__device__ __forceinline__ void meta_bwd_body_wide(const MetaArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
   float4 dgf[NV], dbf[NV], dgg[NV], dbg[NV];
   zero4<NV>(dgf); zero4<NV>(dbf); zero4<NV>(dgg); zero4<NV>(dbg);
@@ -486,9 +512,69 @@ __device__ __forceinline__ void meta_bwd_body(const MetaArgs& p, const int bid, 
   cta_colsum_atomic<NV, TPR>(G, dgg, p.N, p.dgamma_g, red);
   cta_colsum_atomic<NV, TPR>(G, dbg, p.N, p.dbeta_g, red);
 }
+// r02 body for rows up to 2048 wide (NV <= 2): parameters hoisted out of the row loop, every operand of the row requested up
+// front, and the two LayerNorm backward passes share ONE four-value group reduction (r01: two sweeps, two reductions, the
+// parameters re-read per row - 1.3 TB/s at F = 1664, B = 4096).  Wider rows keep the two-sweep body (register budget).
+template <int NV, int TPR, bool F32 = false>
+__device__ __forceinline__ void meta_bwd_body(const MetaArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
+  if (NV > 2) { meta_bwd_body_wide<NV, TPR, F32>(p, bid, nblk, scratch, red); return; }
+  const Grp<TPR> G(bid, nblk);
+  float4 gf[NV], bf[NV], gg[NV];
+  row_load_param<NV, TPR>(G, p.gamma_f, p.N, gf); row_load_param<NV, TPR>(G, p.beta_f, p.N, bf); row_load_param<NV, TPR>(G, p.gamma_g, p.N, gg);
+  float4 dgf[NV], dbf[NV], dgg[NV], dbg[NV];
+  zero4<NV>(dgf); zero4<NV>(dbf); zero4<NV>(dgg); zero4<NV>(dbg);
+  const float invN = 1.f / (float)p.N;
+  for (int64_t row = G.row0; row < p.B; row += G.rstep) {
+    const float4 st = *(const float4*)(p.stats + row * 4);
+    float4 xf[NV], xg[NV], ds[NV], v[NV], y[NV];
+    row_load<NV, TPR, F32>(G, p.y, row, p.N, y);
+    row_load<NV, TPR, F32>(G, p.dy, row, p.N, ds);
+    row_load<NV, TPR, F32>(G, p.f, row, p.N, xf);
+    row_load<NV, TPR, F32>(G, p.g, row, p.N, xg);
+    row_load<NV, TPR, F32>(G, p.v, row, p.N, v);
+    float4 o[NV];
+    if (p.dv.p && p.dv_accumulate) row_load<NV, TPR, F32>(G, p.dv, row, p.N, o); else zero4<NV>(o);
+    normalize<NV, TPR>(G, xf, st.x, st.y, p.N);
+    normalize<NV, TPR>(G, xg, st.z, st.w, p.N);
+    float s1f = 0.f, s2f = 0.f, s1g = 0.f, s2g = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      // ds = dy y (1 - y); t1 = LN_f(f); h = tanh(v t1); dt1 = ds (1 - h^2) v; dv = ds (1 - h^2) t1; dt2 = ds
+#define MBB(c)                                                                                   \
+      { const float dsv = ds[i].c * y[i].c * (1.f - y[i].c);                                     \
+        const float t1 = xf[i].c * gf[i].c + bf[i].c;                                            \
+        const float h = tanhf(v[i].c * t1);                                                      \
+        const float dh = dsv * (1.f - h * h);                                                    \
+        const float d1 = dh * v[i].c;                                                            \
+        o[i].c += dh * t1;                                                                       \
+        dgf[i].c += d1 * xf[i].c; dbf[i].c += d1; dgg[i].c += dsv * xg[i].c; dbg[i].c += dsv;    \
+        const float a1 = d1 * gf[i].c, a2 = dsv * gg[i].c;                                       \
+        s1f += a1; s2f += a1 * xf[i].c; s1g += a2; s2g += a2 * xg[i].c;                          \
+        y[i].c = a1; ds[i].c = a2; }
+      MBB(x) MBB(y) MBB(z) MBB(w)
+#undef MBB
+    }
+    if (p.dv.p) row_store<NV, TPR, F32>(G, p.dv, row, p.N, o);
+    float4 t = G.sum4(s1f, s2f, s1g, s2g, scratch);
+    t.x *= invN; t.y *= invN; t.z *= invN; t.w *= invN;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#define MBC(c)                                                                                   \
+      { y[i].c = st.y * (y[i].c - t.x - xf[i].c * t.y); ds[i].c = st.w * (ds[i].c - t.z - xg[i].c * t.w); }
+      MBC(x) MBC(y) MBC(z) MBC(w)
+#undef MBC
+    }
+    row_store<NV, TPR, F32>(G, p.df, row, p.N, y);
+    row_store<NV, TPR, F32>(G, p.dg, row, p.N, ds);
+  }
+  cta_colsum_atomic<NV, TPR>(G, dgf, p.N, p.dgamma_f, red);
+  cta_colsum_atomic<NV, TPR>(G, dbf, p.N, p.dbeta_f, red);
+  cta_colsum_atomic<NV, TPR>(G, dgg, p.N, p.dgamma_g, red);
+  cta_colsum_atomic<NV, TPR>(G, dbg, p.N, p.dbeta_g, red);
+}
 template <int NV, int TPR>
 __global__ void __launch_bounds__(ROW_WARPS * 32) meta_bwd_kernel(const MetaArgs p) { pdl_sync();
-  __shared__ float2 scratch[ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
+  __shared__ __align__(16) float2 scratch[2 * ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
   meta_bwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, red);
 }
 
