@@ -71,6 +71,7 @@ struct Ctx {
   cudaStream_t st;
   DeviceInfo dev;
   bool gemm_only = false;     // debug replay: launch only the GEMM kernels of the step (bench.py times them with CUDA events)
+  bool dry_run = false;       // host only: build the step-kernel program without touching CUDA (fb200_mega_program_info)
   // two-lane execution (Plan::two_lanes): lane 0 = the caller's stream, lane 1 = a side stream for the metadata chain
   cudaStream_t lane_st[2] = {nullptr, nullptr};
   void* mid_event = nullptr;  // fb200_head_train_step_dp: recorded once every gradient below Plan::dp_split is final
@@ -324,7 +325,7 @@ static int run_forward(Ctx& c) {
       } break;
       default: return FB200_EBADARG;
     }
-    CUDA_OK(cudaGetLastError());
+    if (!c.dry_run) CUDA_OK(cudaGetLastError());
     if (c.mega) c.vready[o.out.buf] = std::max(c.vready[o.out.buf], mout);
     { int rc = ls.touched(o.lane, {o.out.buf}); if (rc != FB200_OK) return rc; }
   }
@@ -339,7 +340,7 @@ static int run_backward(Ctx& c) {
     if (c.vready.empty()) c.vready.assign(p.acts.size(), 0);
     if (c.gready.empty()) c.gready.assign(p.acts.size(), 0);
   }
-  if (!c.gemm_only) CUDA_OK(cudaMemsetAsync(c.grads, 0, (size_t)p.grad_elems * sizeof(float), c.st));
+  if (!c.gemm_only && !c.dry_run) CUDA_OK(cudaMemsetAsync(c.grads, 0, (size_t)p.grad_elems * sizeof(float), c.st));
   std::vector<char> gwritten(p.acts.size(), 0);       // has the gradient buffer been written yet?
   std::vector<char> pwritten(NUM_SLOTS, 0);           // has this weight gradient been written yet?
   gwritten[p.logits.buf] = 1;
@@ -552,7 +553,7 @@ static int run_backward(Ctx& c) {
       } break;
       default: return FB200_EBADARG;
     }
-    CUDA_OK(cudaGetLastError());
+    if (!c.dry_run) CUDA_OK(cudaGetLastError());
     { int rc = ls.touched(o.lane, {o.out.buf, o.in0.buf, o.in1.buf, o.in2.buf, o.dx_view.buf, wslot_ev}); if (rc != FB200_OK) return rc; }
   }
   c.st = main_st;
@@ -613,6 +614,7 @@ static int run_backward(Ctx& c) {
     { int rc = ls.join(c); if (rc != FB200_OK) return rc; }
     { int rc = record_mid(); if (rc != FB200_OK) return rc; }
   }
+  if (c.dry_run) return FB200_OK;
   // inputs nobody differentiated through still owe the caller a defined gradient
   if (c.d_img && !gwritten[0]) CUDA_OK(cudaMemsetAsync(c.d_img, 0, (size_t)B * p.d.F * sizeof(float), c.st));
   if (c.d_txt && !gwritten[1]) CUDA_OK(cudaMemsetAsync(c.d_txt, 0, (size_t)B * p.acts[1].cols * sizeof(float), c.st));
@@ -822,6 +824,34 @@ int fb200_debug_set_pdl(int on) { const int prev = pdl_enabled() ? 1 : 0; pdl_fl
 int fb200_debug_tc_trace(void* device_buf) { tc_trace_buffer() = (long long*)device_buf; return FB200_OK; }
 /* debug: device buffer of >= 2 + 2 * stages int64 receiving clock64 stamps of CTA 0 of the persistent step kernel
  * ([0] entry, [1 + 2s] own tasks of stage s done, [2 + 2s] barrier after stage s passed); NULL disables */
+/* host only (no CUDA call): the program the persistent step kernel would run for `d` - pass 0 forward, 1 backward, 2 fused train
+ * step.  out[0] stages, out[1] GEMM ops, out[2] row ops, out[3] tile tasks; FB200_EUNSUPPORTED when `d` does not take that path. */
+int fb200_mega_program_info(const fb200_desc* d, int pass, int* out) {
+  if (!d || !out || pass < 0 || pass > 2) return FB200_EBADARG;
+  Plan plan; int rc = build_plan(*d, plan); if (rc != FB200_OK) return rc;
+  if (!plan.use_mega) return FB200_EUNSUPPORTED;
+  // fake, never dereferenced on the host: distinct 256-byte aligned addresses
+  std::vector<const void*> params(NUM_SLOTS, nullptr);
+  for (int s = 0; s < NUM_SLOTS; ++s) if (plan.live[s]) params[s] = (const void*)(uintptr_t)(0x100000000ull + (uint64_t)s * 0x4000000ull);
+  char* base = (char*)(uintptr_t)0x4000000000ull;
+  DeviceInfo dev; dev.num_sms = 148; dev.cc_major = 10;
+  const bool nd = d->flags & FB200_FLAG_NEED_DIMG, nt = d->flags & FB200_FLAG_NEED_DTEXT;
+  Ctx c{plan, params.data(), base + 0x1000000000ull, base + 0x1100000000ull, base + 0x1200000000ull, base + 0x1300000000ull,
+        nd ? base + 0x1400000000ull : nullptr, nt ? base + 0x1500000000ull : nullptr, (float*)(base + 0x1600000000ull), nullptr, 0, 0, nullptr,
+        base, nullptr, dev};
+  c.dry_run = true;
+  MegaBuilder mb; mb.scratch = c.ws + plan.splitk_off; mb.scratch_bytes = plan.splitk_bytes; c.mega = &mb;
+  if (pass != 1) { rc = run_forward(c); if (rc != FB200_OK) return rc; }
+  if (pass == 2) mega_emit_ce(c, c.logits, (const int64_t*)(base + 0x1700000000ull), nullptr, nullptr, (float*)(base + 0x1800000000ull), (void*)c.dlogits);
+  if (pass != 0) { rc = run_backward(c); if (rc != FB200_OK) return rc; }
+  static thread_local MegaProg prog;
+  rc = mb.finalize(prog, (unsigned*)(c.ws + plan.mega_bar_off)); if (rc != FB200_OK) return rc;
+  int tasks = 0;
+  for (int i = 0; i < prog.ngemm; ++i) tasks += prog.g[i].tiles;
+  for (int i = 0; i < prog.nrow; ++i) tasks += prog.r[i].chain ? 0 : prog.r[i].tiles;
+  out[0] = prog.nstages; out[1] = prog.ngemm; out[2] = prog.nrow; out[3] = tasks;
+  return FB200_OK;
+}
 int fb200_debug_mega_trace(void* device_buf) { mega_trace_buffer() = (long long*)device_buf; return FB200_OK; }
 /* debug: the step kernel with `nstages` EMPTY stages - the cost of the launch and of the grid barriers alone */
 int fb200_debug_mega_barriers(int nstages, void* ws256, void* stream) {

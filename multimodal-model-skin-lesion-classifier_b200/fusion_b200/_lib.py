@@ -85,6 +85,7 @@ def lib():
     sig("fb200_debug_tc_trace", i32, vp)
     sig("fb200_debug_set_pdl", i32, i32)
     sig("fb200_debug_mega_trace", i32, vp)
+    sig("fb200_mega_program_info", i32, dp, i32, C.POINTER(i32))
     sig("fb200_debug_mega_barriers", i32, i32, vp, vp)
     mp = C.POINTER(MhaDesc)
     sig("fb200_mha_workspace_bytes", i32, mp, C.POINTER(sz))
@@ -184,6 +185,17 @@ def launch_count(desc: Desc):
     f, b = C.c_int(), C.c_int()
     check(lib().fb200_launch_count(C.byref(desc), C.byref(f), C.byref(b)), "fb200_launch_count")
     return f.value, b.value
+
+
+def mega_program_info(desc: Desc, which=2):
+    """(stages, gemm ops, row ops, tile tasks) of the persistent step kernel's program for `desc` (host only), or None when
+    the descriptor takes the per-op kernels.  which: 0 forward, 1 backward, 2 fused train step."""
+    out = (C.c_int * 4)()
+    st = lib().fb200_mega_program_info(C.byref(desc), which, out)
+    if st == -2:
+        return None
+    check(st, "fb200_mega_program_info")
+    return tuple(out)
 
 
 def dropout_sites(desc: Desc):

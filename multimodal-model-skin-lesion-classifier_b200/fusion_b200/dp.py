@@ -90,6 +90,24 @@ class SymmetricGradBucket:
         self._channel = 0
         self._ranges = {}
 
+    @staticmethod
+    def normalize_ranges(ranges, numel):
+        """128-bit vectors: widen every [begin, end) to multiples of 4 elements (the flat buffer pads every slice to 4 and the
+        padding is zero-filled with the rest of the buffer), sort, and merge what then touches or overlaps."""
+        norm = []
+        for b, e in sorted((int(b) & ~3, (int(e) + 3) & ~3) for b, e in ranges):
+            if e <= b:
+                continue
+            if norm and b <= norm[-1][1]:
+                norm[-1][1] = max(norm[-1][1], e)
+            else:
+                norm.append([b, e])
+        if not norm:
+            raise ValueError("no gradient range to reduce")
+        if norm[0][0] < 0 or norm[-1][1] > numel:
+            raise ValueError("gradient range outside the symmetric bucket")
+        return [tuple(be) for be in norm]
+
     def all_reduce(self, ranges, max_ctas=0, channel=0):
         """SUM over all ranks, in place, of the [begin, end) element ranges of `self.tensor`, on the current stream.
         `max_ctas` > 0 caps the grid (overlap with a GEMM); `channel` selects the pair of barrier channels (two all-reduces
@@ -98,16 +116,7 @@ class SymmetricGradBucket:
         key = tuple(ranges)
         hit = self._ranges.get(key)
         if hit is None:
-            # 128-bit vectors: widen every range to multiples of 4 elements (the flat buffer pads every slice to 4 and the
-            # padding is zero-filled with the rest of the buffer) and merge what then touches
-            norm = []
-            for b, e in sorted((int(b) & ~3, (int(e) + 3) & ~3) for b, e in ranges):
-                if norm and b <= norm[-1][1]:
-                    norm[-1][1] = max(norm[-1][1], e)
-                else:
-                    norm.append([b, e])
-            if norm[-1][1] > self.tensor.numel():
-                raise ValueError("gradient range exceeds the symmetric bucket")
+            norm = self.normalize_ranges(ranges, self.tensor.numel())
             flat = [v for be in norm for v in be]
             hit = self._ranges[key] = ((C.c_int64 * len(flat))(*flat), len(norm))
         arr, nr = hit

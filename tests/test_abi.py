@@ -205,3 +205,29 @@ def test_engine_policy_and_launch_counts_on_host():
     # forward NT, weight-gradient TN for every Linear; input-gradient NN only where something upstream needs it
     nt = [x for x in g if x[0] == 0]; tn = [x for x in g if x[0] == 2]; nn = [x for x in g if x[0] == 1]
     assert len(nt) == len(tn) == 15 and len(nn) == 13      # image_projector and text_fc.0 have no dX (inputs need no gradient)
+
+
+def test_step_kernel_program_fits_for_every_fusion_string():
+    """Host only: the persistent step kernel's program (csrc/mega.cuh) for all 18 fusion strings, edge batches and both input-gradient
+    flags stays inside the kernel-parameter capacity (128 GEMM ops, 26 row ops, 80 stages), chains the classifier tail into one
+    task, and batches above 64 rows / bf16 / forced engines take the per-op kernels."""
+    from oracle import head_oracle as ho
+    worst = [0, 0, 0]
+    for mech in ho.MECHANISMS:
+        for B in (1, 32, 33, 64):
+            for flags in (0, _lib.FLAG_NEED_DIMG | _lib.FLAG_NEED_DTEXT):
+                d = make_desc(mech, B, 2048, 85, 512, 512, 8, 6, n=2, train=True, flags=flags)
+                for which in (0, 1, 2):
+                    info = _lib.mega_program_info(d, which)
+                    assert info is not None, (mech, B, which)
+                    stages, ng, nr, tasks = info
+                    assert 1 <= stages <= 80 and ng <= 128 and nr <= 26 and tasks >= 1, (mech, B, which, info)
+                    worst = [max(a, b) for a, b in zip(worst, info[:3])]
+    print("largest program: stages, gemm ops, row ops =", worst)
+    d = make_desc("crossattention", 32, 2048, 85, 512, 512, 8, 6, train=True)
+    fwd, bwd, step = (_lib.mega_program_info(d, w) for w in (0, 1, 2))
+    assert step[0] < fwd[0] + bwd[0]                     # the tail (LayerNorm -> head -> CE -> their backward) shares one stage
+    assert step[1] == fwd[1] + bwd[1]
+    for kw in (dict(B=65), dict(B=32, dtype="bf16"), dict(B=32, flags=_lib.FLAG_FORCE_SIMT), dict(B=32, flags=_lib.FLAG_NO_MEGA)):
+        B = kw.pop("B")
+        assert _lib.mega_program_info(make_desc("crossattention", B, 2048, 85, 512, 512, 8, 6, **kw)) is None

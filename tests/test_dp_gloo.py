@@ -102,3 +102,30 @@ def test_bucket_split_of_live_ranges():
     lo, hi = BucketedAllReduce.split_ranges(ranges, 150)
     assert lo == [(0, 100)] and hi == [(150, 300), (300, 420)]
     assert sum(e - b for b, e in lo) + sum(e - b for b, e in hi) == sum(e - b for b, e in ranges)
+
+
+def test_symmetric_bucket_range_normalisation_and_numa_binding():
+    """Host logic of the hand-written all-reduce path: live ranges become 4-element aligned, sorted, merged vectors inside the
+    bucket; the NUMA binding helper degrades to None without a GPU."""
+    from fusion_b200.dp import SymmetricGradBucket, bind_to_gpu_numa_node
+    nr = SymmetricGradBucket.normalize_ranges
+    assert nr([(0, 6), (8, 12)], 16) == [(0, 12)]                      # 6 -> 8 touches the next range
+    assert nr([(100, 110), (0, 4), (20, 22)], 128) == [(0, 4), (20, 24), (100, 112)]
+    assert nr([(5, 7)], 8) == [(4, 8)]
+    with pytest.raises(ValueError):
+        nr([(0, 10)], 8)
+    with pytest.raises(ValueError):
+        nr([], 8)
+    # the live ranges of every fusion string normalise inside their own flat buffer
+    from fusion_b200 import _lib
+    from fusion_b200.head import make_desc
+    from oracle import head_oracle as ho
+    for mech in ho.MECHANISMS:
+        d = make_desc(mech, 32, 2048, 85, 512, 512, 8, 6)
+        total, _ = _lib.grad_layout(d)
+        if total:
+            out = nr(_lib.grad_live_ranges(d), total)
+            assert all(b % 4 == 0 and e % 4 == 0 and 0 <= b < e <= total for b, e in out) and out == sorted(out)
+    import torch
+    if not torch.cuda.is_available():
+        assert bind_to_gpu_numa_node(0) is None
