@@ -289,6 +289,8 @@ int fb200_gemm_workspace_bytes(int layout, int engine, int M, int N, int K, size
  * ws: fb200_mha_workspace_bytes() bytes, 256-byte aligned; forward leaves Q, K, V, the head outputs and the row
  * log-sum-exps there for backward (the probabilities are recomputed, never stored).  dquery / dkey / dvalue may be
  * NULL (not needed).  When query, key and value are one tensor the caller adds the three input gradients. */
+#define FB200_MHA_POOL_MEAN 1   /* out / dout are [B, D]: the mean over the S_q query tokens (models/multimodalGated.py:200-205:
+                                 * cross_att.permute(1,0,2).mean(dim=1)), folded in front of the output projection it commutes with */
 typedef struct { int32_t Sq, Skv, B, D, H, flags; } fb200_mha_desc;
 int fb200_mha_workspace_bytes(const fb200_mha_desc* d, size_t* bytes);
 int fb200_mha_forward(const fb200_mha_desc* d, const float* query, const float* key, const float* value,

@@ -350,4 +350,32 @@ inline cudaError_t launch_attn_bwd(const AttnArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// ---- mean over the query tokens, folded IN FRONT of the output projection ---------------------------------------------
+// The reference's sequence variants pool the attention output over its tokens right after the module
+// (models/multimodalGated.py:200-205: cross_att.permute(1, 0, 2).mean(dim=1)).  The output projection is linear, so
+// mean_s(O_s W_o^T + b_o) = (mean_s O_s) W_o^T + b_o: pooling first turns the S_q*B-row projection (and its two backward
+// GEMMs) into B-row ones.  O is [S_q*B, D] with row = s*B + b.
+__global__ void __launch_bounds__(256) attn_mean_pool_kernel(const float* __restrict__ O, int Sq, int B, int D, float* __restrict__ pooled) { pdl_sync();
+  const int n4 = B * D / 4;
+  const float inv = 1.f / (float)Sq;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < Sq; ++s) {                               // token order: bit-reproducible
+      const float4 v = __ldg((const float4*)O + (size_t)s * n4 + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    ((float4*)pooled)[i] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  }
+}
+// backward of the pooling: every token row of a batch element receives dPooled / S_q
+__global__ void __launch_bounds__(256) attn_mean_pool_bwd_kernel(const float* __restrict__ dpooled, int Sq, int B, int D, float* __restrict__ dO) { pdl_sync();
+  const int n4 = B * D / 4;
+  const float inv = 1.f / (float)Sq;
+  const size_t total = (size_t)Sq * n4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg((const float4*)dpooled + (i % n4));
+    ((float4*)dO)[i] = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+  }
+}
+
 }  // namespace fb200

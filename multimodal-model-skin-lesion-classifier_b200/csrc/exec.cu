@@ -1126,7 +1126,7 @@ int fb200_gemm(int layout, int engine, int M, int N, int K, const float* A, int 
 
 // ---- multi-head attention on token sequences -------------------------------------------------------
 namespace {
-struct MhaLayout { size_t q, k, v, o, lse, delta, dO, dq, dk, dv, total; };
+struct MhaLayout { size_t q, k, v, o, lse, delta, dO, dq, dk, dv, pool, dpool, total; };
 MhaLayout mha_layout(const fb200_mha_desc& d) {
   auto al = [](size_t v) { return (v + 255) & ~size_t(255); };
   const size_t nq = (size_t)d.Sq * d.B * d.D * sizeof(float), nk = (size_t)d.Skv * d.B * d.D * sizeof(float);
@@ -1135,6 +1135,8 @@ MhaLayout mha_layout(const fb200_mha_desc& d) {
   L.q = c; c = al(c + nq); L.k = c; c = al(c + nk); L.v = c; c = al(c + nk); L.o = c; c = al(c + nq);
   L.lse = c; c = al(c + ns); L.delta = c; c = al(c + ns);
   L.dO = c; c = al(c + nq); L.dq = c; c = al(c + nq); L.dk = c; c = al(c + nk); L.dv = c; c = al(c + nk);
+  const size_t np = (size_t)d.B * d.D * sizeof(float);
+  L.pool = c; c = al(c + np); L.dpool = c; c = al(c + np);
   L.total = c + 256;
   return L;
 }
@@ -1187,6 +1189,13 @@ int fb200_mha_forward(const fb200_mha_desc* d, const float* query, const float* 
   a.Q = Qp; a.K = Kp; a.V = Vp; a.ldq = a.ldk = a.ldv = D; a.O = Oc; a.ldo = D; a.lse = (float*)(w + L.lse);
   a.Sq = d->Sq; a.Sk = d->Skv; a.B = d->B; a.H = d->H; a.hd = D / d->H; a.scale = 1.0f / sqrtf((float)a.hd);
   CUDA_OK(launch_attn_fwd(a, (cudaStream_t)stream));
+  if (d->flags & FB200_MHA_POOL_MEAN) {          // out [B, D] = out_proj(mean over the query tokens): the pooling commutes with the projection
+    float* pooled = (float*)(w + L.pool);
+    int grid = (d->B * D / 4 + 255) / 256; if (grid > 1184) grid = 1184;
+    pdl_launch(attn_mean_pool_kernel, grid, 256, 0, (cudaStream_t)stream, (const float*)Oc, d->Sq, d->B, D, pooled);
+    CUDA_OK(cudaGetLastError());
+    return gemm_auto(0, d->B, D, D, pooled, D, out_proj_weight, D, out, D, out_proj_bias, 0, stream);
+  }
   return gemm_auto(0, Mq, D, D, Oc, D, out_proj_weight, D, out, D, out_proj_bias, 0, stream);
 }
 
@@ -1205,9 +1214,19 @@ int fb200_mha_backward(const fb200_mha_desc* d, const float* query, const float*
   const int D = d->D, Mq = d->Sq * d->B, Mk = d->Skv * d->B;
   float* Qp = (float*)(w + L.q); float* Kp = (float*)(w + L.k); float* Vp = (float*)(w + L.v); float* Oc = (float*)(w + L.o);
   float* dOc = (float*)(w + L.dO); float* dQp = (float*)(w + L.dq); float* dKp = (float*)(w + L.dk); float* dVp = (float*)(w + L.dv);
+  const bool pool = d->flags & FB200_MHA_POOL_MEAN;
+  if (pool) {
+    // dout is [B, D]: dW_o = dout^T pooled, dPooled = dout W_o, then every token row of O receives dPooled / S_q
+    float* pooled = (float*)(w + L.pool); float* dpooled = (float*)(w + L.dpool);
+    rc = gemm_auto(2, D, D, d->B, dout, D, pooled, D, d_out_proj_weight, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
+    rc = gemm_auto(1, d->B, D, D, dout, D, out_proj_weight, D, dpooled, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
+    pdl_launch(attn_mean_pool_bwd_kernel, 1184, 256, 0, st, (const float*)dpooled, d->Sq, d->B, D, dOc);
+    CUDA_OK(cudaGetLastError());
+  } else {
   // out_proj: dW_o = dout^T O, db_o = colsum(dout), dO = dout W_o
   rc = gemm_auto(2, D, D, Mq, dout, D, Oc, D, d_out_proj_weight, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
   rc = gemm_auto(1, Mq, D, D, dout, D, out_proj_weight, D, dOc, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
+  }
   AttnArgs a{};
   a.Q = Qp; a.K = Kp; a.V = Vp; a.ldq = a.ldk = a.ldv = D; a.O = Oc; a.ldo = D; a.lse = (float*)(w + L.lse); a.delta = (float*)(w + L.delta);
   a.dO = dOc; a.lddo = D; a.dQ = dQp; a.dK = dKp; a.dV = dVp; a.lddq = a.lddk = a.lddv = D;
@@ -1219,8 +1238,13 @@ int fb200_mha_backward(const fb200_mha_desc* d, const float* query, const float*
   rc = gemm_auto(2, D, D, Mk, dVp, D, value, D, d_in_proj_weight + (size_t)2 * D * D, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
   CUDA_OK(cudaMemsetAsync(d_in_proj_bias, 0, (size_t)3 * D * sizeof(float), st));
   CUDA_OK(cudaMemsetAsync(d_out_proj_bias, 0, (size_t)D * sizeof(float), st));
-  { const float* xs[2] = {dout, dQp}; float* ds[2] = {d_out_proj_bias, d_in_proj_bias};
-    rc = colsum_rows(xs, ds, 2, Mq, D, dev.num_sms, st); if (rc != FB200_OK) return rc; }
+  if (pool) {
+    { const float* xs[1] = {dout}; float* ds[1] = {d_out_proj_bias}; rc = colsum_rows(xs, ds, 1, d->B, D, dev.num_sms, st); if (rc != FB200_OK) return rc; }
+    { const float* xs[1] = {dQp}; float* ds[1] = {d_in_proj_bias}; rc = colsum_rows(xs, ds, 1, Mq, D, dev.num_sms, st); if (rc != FB200_OK) return rc; }
+  } else {
+    const float* xs[2] = {dout, dQp}; float* ds[2] = {d_out_proj_bias, d_in_proj_bias};
+    rc = colsum_rows(xs, ds, 2, Mq, D, dev.num_sms, st); if (rc != FB200_OK) return rc;
+  }
   { const float* xs[2] = {dKp, dVp}; float* ds[2] = {d_in_proj_bias + D, d_in_proj_bias + 2 * D};
     rc = colsum_rows(xs, ds, 2, Mk, D, dev.num_sms, st); if (rc != FB200_OK) return rc; }
   if (dquery) { rc = gemm_auto(1, Mq, D, D, dQp, D, in_proj_weight, D, dquery, D, nullptr, 0, stream); if (rc != FB200_OK) return rc; }

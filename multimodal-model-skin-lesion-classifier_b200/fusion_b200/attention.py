@@ -29,7 +29,7 @@ def _f32c(t, name):
 
 class FusedMHAFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, query, key, value, in_w, in_b, out_w, out_b, num_heads):
+    def forward(ctx, query, key, value, in_w, in_b, out_w, out_b, num_heads, pool_mean=False):
         L = _lib.lib()
         q, k, v = _f32c(query, "query"), _f32c(key, "key"), _f32c(value, "value")
         if q.dim() != 3 or k.dim() != 3 or v.shape != k.shape or q.shape[1:] != k.shape[1:]:
@@ -37,11 +37,11 @@ class FusedMHAFunction(torch.autograd.Function):
         Sq, B, D = q.shape
         if D % num_heads != 0:
             raise AssertionError("embed_dim must be divisible by num_heads")       # torch's own check, same exception type
-        desc = _lib.MhaDesc(Sq=Sq, Skv=k.shape[0], B=B, D=D, H=num_heads, flags=0)
+        desc = _lib.MhaDesc(Sq=Sq, Skv=k.shape[0], B=B, D=D, H=num_heads, flags=1 if pool_mean else 0)     # FB200_MHA_POOL_MEAN
         nbytes = C.c_size_t(0)
         _lib.check(L.fb200_mha_workspace_bytes(C.byref(desc), C.byref(nbytes)), "fb200_mha_workspace_bytes")
         ws = torch.empty(nbytes.value, dtype=torch.uint8, device=q.device)
-        out = torch.empty_like(q)
+        out = torch.empty(B, D, dtype=torch.float32, device=q.device) if pool_mean else torch.empty_like(q)
         w = [_f32c(t, n) for t, n in ((in_w, "in_proj_weight"), (in_b, "in_proj_bias"), (out_w, "out_proj.weight"), (out_b, "out_proj.bias"))]
         with torch.cuda.device(q.device):
             _lib.check(L.fb200_mha_forward(C.byref(desc), _ptr(q), _ptr(k), _ptr(v), _ptr(w[0]), _ptr(w[1]), _ptr(w[2]), _ptr(w[3]),
@@ -66,14 +66,20 @@ class FusedMHAFunction(torch.autograd.Function):
                                             _ptr(dq), _ptr(dk), _ptr(dv), _ptr(d_in_w), _ptr(d_in_b), _ptr(d_out_w), _ptr(d_out_b),
                                             _ptr(ctx.ws), _stream()), "fb200_mha_backward")
         ctx.ws = None
-        return dq, dk, dv, d_in_w, d_in_b, d_out_w, d_out_b, None
+        return dq, dk, dv, d_in_w, d_in_b, d_out_w, d_out_b, None, None
 
 
 class MultiheadAttention(nn.Module):
     """``nn.MultiheadAttention(embed_dim, num_heads)`` with the fused CUDA path (sequence-first tensors)."""
 
-    def __init__(self, embed_dim, num_heads, dropout=0.0, bias=True, batch_first=False):
+    def __init__(self, embed_dim, num_heads, dropout=0.0, bias=True, batch_first=False, pool=None):
+        """``pool="mean"``: forward returns the mean of the attention output over the query tokens, [B, D] - what the
+        reference's sequence models compute right after the module (multimodalGated.py:200-205).  The pooling is folded in
+        front of the output projection (it commutes with it), so that projection runs on B rows instead of S_q * B."""
         super().__init__()
+        if pool not in (None, "mean"):
+            raise ValueError("pool must be None or 'mean'")
+        self.pool = pool
         if dropout != 0.0 or not bias or batch_first:
             raise ValueError("the fused attention implements the reference's configuration: dropout=0, bias=True, batch_first=False")
         if embed_dim % num_heads != 0:
@@ -94,5 +100,5 @@ class MultiheadAttention(nn.Module):
         if key_padding_mask is not None or attn_mask is not None:
             raise ValueError("masks are not supported by the fused attention (the reference never passes one)")
         out = FusedMHAFunction.apply(query, key, value, self.in_proj_weight, self.in_proj_bias,
-                                     self.out_proj.weight, self.out_proj.bias, self.num_heads)
+                                     self.out_proj.weight, self.out_proj.bias, self.num_heads, self.pool == "mean")
         return out, None

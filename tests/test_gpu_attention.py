@@ -99,3 +99,32 @@ def test_rejects_bad_arguments():
     m = fb.MultiheadAttention(64, 8).cuda()
     with pytest.raises(fb.Fb200Error):
         m(torch.randn(2, 1, 64), torch.randn(2, 1, 64), torch.randn(2, 1, 64))      # host tensors: no CPU path
+
+
+@pytest.mark.parametrize("Sq,Sk,B,D,H", [(197, 85, 4, 128, 8), (7, 3, 5, 64, 4), (1, 1, 9, 64, 8)])
+def test_mean_pool_folded_in_front_of_the_output_projection(Sq, Sk, B, D, H):
+    """pool="mean" (multimodalGated.py:200-205: attention output averaged over its tokens) equals out.mean(0) of the plain
+    module, forward and every gradient - the oracle is the float64 attention with the pooled gradient broadcast to the tokens."""
+    c = _fresh(Sq, Sk, B, D, H, False, seed=Sq + B)
+    dpool = np.random.default_rng(5).standard_normal((B, D))
+    c["dy"] = np.broadcast_to(dpool[None] / Sq, (Sq, B, D)).copy()
+    ref = oracle_mha(c, H, False)
+    dev = "cuda"
+    m = fb.MultiheadAttention(D, H, pool="mean").to(dev)
+    with torch.no_grad():
+        m.in_proj_weight.copy_(torch.from_numpy(c["in_w"])); m.in_proj_bias.copy_(torch.from_numpy(c["in_b"]))
+        m.out_proj.weight.copy_(torch.from_numpy(c["out_w"])); m.out_proj.bias.copy_(torch.from_numpy(c["out_b"]))
+    q, k, v = (torch.from_numpy(c[n]).float().to(dev).requires_grad_(True) for n in ("q", "k", "v"))
+    out, _ = m(q, k, v)
+    assert out.shape == (B, D)
+    out.backward(torch.from_numpy(dpool).float().to(dev))
+    torch.cuda.synchronize()
+    got = dict(out=out, dq=q.grad, dk=k.grad, dv=v.grad, d_in_w=m.in_proj_weight.grad, d_in_b=m.in_proj_bias.grad,
+               d_out_w=m.out_proj.weight.grad, d_out_b=m.out_proj.bias.grad)
+    ref = dict(ref, out=ref["out"].mean(axis=0))
+    for n, t in got.items():
+        r = ref[n]
+        if np.abs(r).max() == 0:
+            assert np.all(t.detach().cpu().numpy() == 0), n
+        else:
+            assert parity.rel_err(t.detach().cpu().numpy(), r) < TOL, (n, parity.rel_err(t.detach().cpu().numpy(), r))
