@@ -363,47 +363,37 @@ __device__ __forceinline__ void mega_gemm_ksplit(const MGemm& g, int tile, float
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
-  const int mlast = g.M - 1;                                       // rows past the edge re-read the last valid row; they are never stored
+  const float* arow[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const int r = m0 + rq + 4 * j; arow[j] = g.A.p + (int64_t)(r < g.M ? r : m0) * g.A.ld; }
   const int nchunk = (k1 - k0 + 31) >> 5;
-  // Two chunks per trip, all 32 loads issued before the first FMA: a warp's chunks were two dependent L2 round trips of ~0.9 us
-  // each (the whole task is latency); now they overlap.
-  auto load_a = [&](int k, float4 (&a)[8]) {
+  for (int ch = warp; ch < nchunk; ch += ROW_WARPS) {
+    const int k = k0 + ch * 32 + 4 * kq;
+    if (k < k1) {                                                 // K % 4 == 0: a float4 of k is in or out as a whole
+      float4 a[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = __ldcg((const float4*)(g.A.p + (int64_t)min(m0 + rq + 4 * j, mlast) * g.A.ld + k));
-  };
-  auto load_b = [&](int k, float (&b)[4][8]) {                     // b[i][c] = W element for reduction index k + i and output column n0 + c
-    if (LAYOUT == 0) {
+      for (int j = 0; j < 8; ++j) a[j] = __ldcg((const float4*)(arow[j] + k));
+      float b[4][8];                                              // b[i][c] = W element for reduction index k + i and output column n0 + c
+      if (LAYOUT == 0) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 w = __ldg((const float4*)(g.B.p + (int64_t)(n0 + c < g.N ? n0 + c : n0) * g.B.ld + k));
-        b[0][c] = w.x; b[1][c] = w.y; b[2][c] = w.z; b[3][c] = w.w;
+        for (int c = 0; c < 8; ++c) {
+          const float4 w = __ldg((const float4*)(g.B.p + (int64_t)(n0 + c < g.N ? n0 + c : n0) * g.B.ld + k));
+          b[0][c] = w.x; b[1][c] = w.y; b[2][c] = w.z; b[3][c] = w.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* wr = g.B.p + (int64_t)(k + i) * g.B.ld + n0;
+          const float4 w0 = __ldg((const float4*)wr), w1 = __ldg((const float4*)(wr + 4));
+          b[i][0] = w0.x; b[i][1] = w0.y; b[i][2] = w0.z; b[i][3] = w0.w; b[i][4] = w1.x; b[i][5] = w1.y; b[i][6] = w1.z; b[i][7] = w1.w;
+        }
       }
-    } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float* wr = g.B.p + (int64_t)(k + i) * g.B.ld + n0;
-        const float4 w0 = __ldg((const float4*)wr), w1 = __ldg((const float4*)(wr + 4));
-        b[i][0] = w0.x; b[i][1] = w0.y; b[i][2] = w0.z; b[i][3] = w0.w; b[i][4] = w1.x; b[i][5] = w1.y; b[i][6] = w1.z; b[i][7] = w1.w;
-      }
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          acc[j][c] = fmaf(a[j].x, b[0][c], fmaf(a[j].y, b[1][c], fmaf(a[j].z, b[2][c], fmaf(a[j].w, b[3][c], acc[j][c]))));
     }
-  };
-  auto fma_block = [&](const float4 (&a)[8], const float (&b)[4][8]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        acc[j][c] = fmaf(a[j].x, b[0][c], fmaf(a[j].y, b[1][c], fmaf(a[j].z, b[2][c], fmaf(a[j].w, b[3][c], acc[j][c]))));
-  };
-  for (int ch = warp; ch < nchunk; ch += 2 * ROW_WARPS) {
-    const int ka = k0 + ch * 32 + 4 * kq, kb = ka + ROW_WARPS * 32;
-    const bool va = ka < k1, vb = (ch + ROW_WARPS < nchunk) && kb < k1;        // K % 4 == 0: a float4 of k is in or out as a whole
-    float4 a0[8], a1[8]; float b[4][8];
-    // the activation loads of BOTH chunks (L2 round trips) and the first chunk's weights go out together; the second chunk's
-    // weights (L1 / L2, short) are fetched behind the first FMA block - three operand sets plus 64 accumulators fit the register file
-    if (va) { load_a(ka, a0); load_b(ka, b); }
-    if (vb) load_a(kb, a1);
-    if (va) fma_block(a0, b);
-    if (vb) { load_b(kb, b); fma_block(a1, b); }
   }
   if (tr && threadIdx.x == 0) tr[1] = clock64();
   // transpose-reduce the 64 sums over the 8 k-lanes: lane-bit 1 keeps rows j in {0..3} / {4..7}, bit 2 halves again, bit 4 again:
