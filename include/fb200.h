@@ -301,6 +301,45 @@ int fb200_mha_backward(const fb200_mha_desc* d, const float* query, const float*
                        float* dquery, float* dkey, float* dvalue, float* d_in_proj_weight, float* d_in_proj_bias,
                        float* d_out_proj_weight, float* d_out_proj_bias, void* ws, void* stream);
 
+/* ---- TabTransformer encoder (models/tab_transformer.py:6-60) ------------------------------------------
+ * Replaces, for the whole batch in ONE launch per pass, the embedding lookups + torch.stack (:42-43), the
+ * nn.TransformerEncoder stack (:19-27, :46: post-norm layers, ReLU feed-forward, dropout p on the attention
+ * probabilities, after the attention, inside the feed-forward and after it) and the flatten (:47).
+ *   B samples, T categorical columns (tokens), D = embed_dim, H heads, F = dim_feedforward, L layers.
+ *   codes    [B, T] int64 category codes (x_categorical), emb_base[t] = first row of column t's table inside the
+ *            stacked embedding table (n_emb_rows rows = sum of the cardinalities);
+ *   params   one flat fp32 buffer: L layer blocks, each in nn.TransformerEncoderLayer's state_dict order
+ *            (self_attn.in_proj_weight [3D,D], in_proj_bias [3D], out_proj.weight [D,D], out_proj.bias [D],
+ *            linear1.weight [F,D], linear1.bias [F], linear2.weight [D,F], linear2.bias [D], norm1.weight, norm1.bias,
+ *            norm2.weight, norm2.bias [D each]), then embeddings.0.weight ... embeddings.T-1.weight stacked
+ *            [n_emb_rows, D]; fb200_tabt_param_elems gives the block and total sizes;
+ *   out      [B, T*D] with row stride ldo >= T*D (the caller may hand in the left part of the concatenated feature matrix);
+ *   saved    fb200_tabt_workspace_bytes(saved_bytes): the inputs of layers 1..L-1, written by forward, read by backward
+ *            (everything else is recomputed on chip);
+ *   masks    NULL, or 4 optional uint8 keep-masks {attention [L,B,H,T,T], after-attention [L,B*T,D], feed-forward
+ *            [L,B*T,F], after-feed-forward [L,B*T,D]}; a NULL entry draws from Philox (seed, offset | rng_state) when train = 1;
+ *   dparams  gradient of `params`, same layout, OVERWRITTEN (bit-reproducible: no atomics); ws = bwd_ws_bytes scratch.
+ * 16-byte aligned params / out / saved / dout / dparams / ws.  FB200_EUNSUPPORTED when a sample's working set does not
+ * fit the 227 KB of one SM, D or F is not a multiple of 4, or D / H is not 2, 4, 8, 16 or 32. */
+#define FB200_TABT_MAX_CTAS 160
+typedef struct { int32_t B, T, D, H, F, L, n_emb_rows, train; float p; int32_t flags; } fb200_tabt_desc;
+int fb200_tabt_param_elems(const fb200_tabt_desc* d, int64_t* layer_elems, int64_t* total_elems);
+int fb200_tabt_workspace_bytes(const fb200_tabt_desc* d, size_t* saved_bytes, size_t* bwd_ws_bytes);
+int fb200_tabt_forward(const fb200_tabt_desc* d, const int64_t* codes, const int32_t* emb_base, const float* params,
+                       const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
+                       float* out, int ldo, void* saved, void* stream);
+int fb200_tabt_backward(const fb200_tabt_desc* d, const int64_t* codes, const int32_t* emb_base, const float* params,
+                        const uint8_t* const* masks, uint64_t seed, uint64_t offset, const void* rng_state,
+                        const void* saved, const float* dout, int lddo, float* dparams, void* ws, void* stream);
+
+/* nn.Linear on row-major fp32 tensors with explicit row strides (tab_transformer.py:30 numeric_projection, :33-38 fc):
+ * y[M,N] = x[M,K] W[N,K]^T + bias, optionally followed by ReLU; the engine (tcgen05 3xTF32 / FFMA) is chosen per shape.
+ * backward: dx = dy W (dx may be NULL), dW = dy^T x and db = column sums of dy (both OVERWRITTEN). */
+int fb200_linear_forward(int M, int N, int K, const float* x, int ldx, const float* W, const float* bias, int relu,
+                         float* y, int ldy, void* stream);
+int fb200_linear_backward(int M, int N, int K, const float* x, int ldx, const float* W, const float* dy, int lddy,
+                          float* dx, int lddx, float* dW, float* db, void* stream);
+
 /* y = dropout(relu(LayerNorm(x))), rows of width N (fc_fusion[1:4], [5:8]); stats = [B,2] (mean, rstd) */
 int fb200_ln_relu_dropout_fwd(const float* x, const float* gamma, const float* beta,
                               const uint8_t* mask, float p, int train, uint64_t seed, uint64_t offset, int site,

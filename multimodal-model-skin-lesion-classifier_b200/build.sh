@@ -5,9 +5,9 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 mkdir -p "$HERE/lib" "$HERE/build"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr)
-for f in plan exec; do
+for f in plan exec tabt; do
   "$NVCC" "${FLAGS[@]}" ${FB200_PTXAS_V:+-Xptxas -v} -c "$HERE/csrc/$f.cu" -o "$HERE/build/$f.o" &
 done
 wait
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$HERE/lib/libfb200.so" "$HERE/build/plan.o" "$HERE/build/exec.o" -lcudart_static -ldl -lrt -lpthread
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$HERE/lib/libfb200.so" "$HERE/build/plan.o" "$HERE/build/exec.o" "$HERE/build/tabt.o" -lcudart_static -ldl -lrt -lpthread
 echo "built $HERE/lib/libfb200.so"

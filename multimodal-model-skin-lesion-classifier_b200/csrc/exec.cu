@@ -1148,11 +1148,11 @@ int mha_check(const fb200_mha_desc* d) {
 }
 // fp32 GEMM on the engine that fits: tcgen05 3xTF32 once the row dimension exceeds 32 and the strides are TMA-legal, else FFMA
 int gemm_auto(int layout, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-              const float* bias, int accumulate, void* stream) {
+              const float* bias, int accumulate, void* stream, int relu = 0) {
   const int rows = layout == 2 ? K : M;
   const bool aligned = !((((uintptr_t)A) | ((uintptr_t)B) | ((uintptr_t)C)) & 15) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0;
   const int engine = (rows > 32 && aligned && tc_shape_ok(layout, M, N, K)) ? 1 : 0;
-  return fb200_gemm(layout, engine, M, N, K, A, lda, B, ldb, C, ldc, bias, 0, accumulate, nullptr, 0, stream);
+  return fb200_gemm(layout, engine, M, N, K, A, lda, B, ldb, C, ldc, bias, relu, accumulate, nullptr, 0, stream);
 }
 int colsum_rows(const float* const* xs, float* const* dsts, int n, int rows, int N, int num_sms, cudaStream_t st) {
   ColsumBatch cb{}; cb.B = rows; cb.nseg = n;
@@ -1162,6 +1162,51 @@ int colsum_rows(const float* const* xs, float* const* dsts, int n, int rows, int
   return cudaGetLastError() == cudaSuccess ? FB200_OK : FB200_ECUDA;
 }
 }  // namespace
+
+}  // extern "C" paused: a device kernel
+namespace fb200 {
+// column sums of a row-major matrix of any width / stride (bias gradient of an output layer whose width is not a multiple of 4)
+__global__ void __launch_bounds__(256) colsum_any_kernel(const float* __restrict__ y, int ld, int M, int N, float* __restrict__ out) { pdl_sync();
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5, c = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (c < N) for (int r = rg; r < M; r += 8) s += __ldg(y + (size_t)r * ld + c);
+  red[rg][lane] = s;
+  __syncthreads();
+  if (rg == 0 && c < N) { for (int g = 1; g < 8; ++g) s += red[g][lane]; out[c] = s; }
+}
+}  // namespace fb200
+extern "C" {
+// ---- nn.Linear with row strides (the GEMMs around the TabTransformer encoder: tab_transformer.py:30, :33-38) -----------------
+int fb200_linear_forward(int M, int N, int K, const float* x, int ldx, const float* W, const float* bias, int relu,
+                         float* y, int ldy, void* stream) {
+  if (!x || !W || !y || M < 1 || N < 1 || K < 1 || ldx < K || ldy < N) return FB200_EBADARG;
+  if (!is_device_ptr(W) || (bias && !is_device_ptr(bias))) return FB200_EUNSUPPORTED;          // x and y are checked by fb200_gemm
+  return gemm_auto(0, M, N, K, x, ldx, W, K, y, ldy, bias, 0, stream, relu ? 1 : 0);
+}
+
+int fb200_linear_backward(int M, int N, int K, const float* x, int ldx, const float* W, const float* dy, int lddy,
+                          float* dx, int lddx, float* dW, float* db, void* stream) {
+  if (!x || !W || !dy || !dW || M < 1 || N < 1 || K < 1 || ldx < K || lddy < N || (dx && lddx < K)) return FB200_EBADARG;
+  if (!is_device_ptr(W) || !is_device_ptr(x) || (db && !is_device_ptr(db))) return FB200_EUNSUPPORTED;
+  DeviceInfo dev; int rc = get_device_info(dev); if (rc != FB200_OK) return rc;
+  rc = gemm_auto(2, N, K, M, dy, lddy, x, ldx, dW, K, nullptr, 0, stream); if (rc != FB200_OK) return rc;      // dW = dy^T x
+  if (dx) { rc = gemm_auto(1, M, K, N, dy, lddy, W, K, dx, lddx, nullptr, 0, stream); if (rc != FB200_OK) return rc; }   // dx = dy W
+  if (db) {
+    if (N % 4 == 0 && lddy % 4 == 0 && !(((uintptr_t)dy | (uintptr_t)db) & 15)) {
+      CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), (cudaStream_t)stream));
+      const float* xs[1] = {dy}; float* ds[1] = {db};
+      ColsumBatch cb{}; cb.B = M; cb.nseg = 1; cb.seg[0] = ColsumSeg{make_ref((void*)dy, lddy, FMT_F32), N, db};
+      int gx = (M + 63) / 64; if (gx > 8 * dev.num_sms + 1) gx = 8 * dev.num_sms + 1;
+      (void)xs; (void)ds;
+      pdl_launch(colsum_batch_kernel, dim3(gx, 1), 256, 0, (cudaStream_t)stream, cb);
+    } else {
+      pdl_launch(colsum_any_kernel, (N + 31) / 32, 256, 0, (cudaStream_t)stream, dy, lddy, M, N, db);      // e.g. the 85-wide output layer
+    }
+    CUDA_OK(cudaGetLastError());
+  }
+  return FB200_OK;
+}
 
 int fb200_mha_workspace_bytes(const fb200_mha_desc* d, size_t* bytes) {
   int rc = mha_check(d); if (rc != FB200_OK) return rc;

@@ -15,5 +15,6 @@ from .attention import FusedMHAFunction, MultiheadAttention
 from .model import GraphedTrainStep, MultimodalModel
 from .optim import FusedAdam
 from .metadata import MetadataEncoder
+from .tab_transformer import FusedLinearFunction, FusedTabEncoderFunction, TabTransformer
 
-__all__ = ["MetadataEncoder", "MultimodalModel", "MultiheadAttention", "FusedMHAFunction", "GraphedTrainStep", "FusedAdam", "FusedCrossEntropyLoss", "FusedFocalLoss", "FusedSoftTargetCrossEntropy", "softmax_argmax", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]
+__all__ = ["TabTransformer", "FusedTabEncoderFunction", "FusedLinearFunction", "MetadataEncoder", "MultimodalModel", "MultiheadAttention", "FusedMHAFunction", "GraphedTrainStep", "FusedAdam", "FusedCrossEntropyLoss", "FusedFocalLoss", "FusedSoftTargetCrossEntropy", "softmax_argmax", "FusedHeadFunction", "cross_entropy", "make_desc", "Fb200Error", "_lib"]

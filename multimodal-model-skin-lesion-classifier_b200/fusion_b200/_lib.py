@@ -30,6 +30,11 @@ class MhaDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("Sq", "Skv", "B", "D", "H", "flags")]
 
 
+class TabtDesc(C.Structure):
+    """struct fb200_tabt_desc (include/fb200.h)."""
+    _fields_ = [(n, C.c_int32) for n in ("B", "T", "D", "H", "F", "L", "n_emb_rows", "train")] + [("p", C.c_float), ("flags", C.c_int32)]
+
+
 class Fb200Error(RuntimeError):
     """Non-zero status from libfb200 (kept a RuntimeError so the reference's
     ``try/except ... continue`` around each experiment keeps working: train_pad_20.py:486-488)."""
@@ -104,6 +109,13 @@ def lib():
     sig("fb200_ln_relu_dropout_fwd", i32, vp, vp, vp, vp, f32, i32, u64, u64, i32, i32, i32, vp, vp, vp)
     sig("fb200_ln_relu_dropout_bwd", i32, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp)
     sig("fb200_metablock_fwd", i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp)
+    tp = C.POINTER(TabtDesc)
+    sig("fb200_tabt_param_elems", i32, tp, C.POINTER(i64), C.POINTER(i64))
+    sig("fb200_tabt_workspace_bytes", i32, tp, C.POINTER(sz), C.POINTER(sz))
+    sig("fb200_tabt_forward", i32, tp, vp, vp, vp, pp, u64, u64, vp, vp, i32, vp, vp)
+    sig("fb200_tabt_backward", i32, tp, vp, vp, vp, pp, u64, u64, vp, vp, vp, i32, vp, vp, vp)
+    sig("fb200_linear_forward", i32, i32, i32, i32, vp, i32, vp, vp, i32, vp, i32, vp)
+    sig("fb200_linear_backward", i32, i32, i32, i32, vp, i32, vp, vp, i32, vp, i32, vp, vp, vp)
     _lib = L
     return L
 
