@@ -489,6 +489,10 @@ def main():
         except Exception as exc:                                    # never lose the headline line to an extra
             extras = {"mha_tokens": {"error": repr(exc)}}
         try:
+            extras["tab_transformer"] = time_tab_transformer(torch, fb, dev)
+        except Exception as exc:
+            extras["tab_transformer"] = {"error": repr(exc)}
+        try:
             extras["e2e_backbone"] = time_backbone_e2e(torch, fb, dev, wl)
         except Exception as exc:
             extras["e2e_backbone"] = {"error": repr(exc)}
@@ -793,6 +797,54 @@ def time_token_attention(torch, fb, dev, Sq=197, Skv=85, B=32, D=512, H=8, reps=
     fwd_ms, bwd_ms = statistics.median(tf), statistics.median(tb)
     return {"shape": {"Sq": Sq, "Skv": Skv, "B": B, "D": D, "H": H}, "fwd_us": fwd_ms * 1e3, "bwd_us": bwd_ms * 1e3,
             "fwd_tflops": (core + proj) / (fwd_ms * 1e-3) / 1e12, "note": "eager launches through autograd (host overhead included); fp32, probabilities never stored"}
+
+
+def time_tab_transformer(torch, fb, dev, B=1024, reps=10):
+    """The fused TabTransformer (csrc/tabt.cu: embedding gather + both encoder layers in one kernel per pass, then the fc MLP on the
+    GEMM engines) against the same module composed from stock torch.nn on the same GPU - what models/tab_transformer.py:6-60 runs
+    with device='cuda' - at the reference's dimensions (82 columns x 10 categories, d 32, 4 heads, ff 128, 2 layers, 85 outputs),
+    train mode, forward + backward, fp32 (TF32 off), CUDA events, median of `reps`."""
+    import torch.nn as nn
+    cards = [10] * 82
+
+    class Stock(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embeddings = nn.ModuleList([nn.Embedding(c, 32) for c in cards])
+            layer = nn.TransformerEncoderLayer(d_model=32, nhead=4, dim_feedforward=128, activation="relu", dropout=0.3, batch_first=True)
+            self.transformer_encoder = nn.TransformerEncoder(layer, num_layers=2)
+            self.numeric_projection = nn.Linear(4, 32)
+            self.fc = nn.Sequential(nn.Linear(82 * 32 + 32, 128), nn.ReLU(), nn.Dropout(0.3), nn.Linear(128, 85))
+
+        def forward(self, xc, xn):
+            tok = torch.stack([e(xc[:, i]) for i, e in enumerate(self.embeddings)], dim=1)
+            return self.fc(torch.cat([self.transformer_encoder(tok).flatten(start_dim=1), self.numeric_projection(xn)], dim=1))
+
+    fused = fb.TabTransformer(cards, 4, output_dim=85).to(dev).train()
+    stock = Stock().to(dev).train()
+    xc = torch.randint(0, 10, (B, 82), device=dev); xn = torch.randn(B, 4, device=dev); g = torch.randn(B, 85, device=dev)
+
+    def timed(m):
+        ts = []
+        for i in range(reps + 3):
+            m.zero_grad(set_to_none=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); m(xc, xn).backward(g); e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        f_ms, s_ms = timed(fused), timed(stock)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    flops = 2 * (2 * 82 * 32 * 96 + 4 * 82 * 82 * 32 + 2 * 82 * 32 * 32 + 4 * 82 * 32 * 128) * B      # encoder stack, forward
+    return {"batch": B, "fused_fwd_bwd_ms": f_ms, "torch_nn_cuda_fwd_bwd_ms": s_ms, "speedup": s_ms / f_ms,
+            "samples_per_s": B / (f_ms * 1e-3), "encoder_fwd_gflop": flops / 1e9,
+            "note": "eager launches through autograd; fused = 2 encoder kernels + GEMMs, stock = torch.nn.TransformerEncoder on cuda"}
 
 
 def measure_tf32_peak(torch, dev, n=8192):

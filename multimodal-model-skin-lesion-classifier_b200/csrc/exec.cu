@@ -4,6 +4,7 @@
 #include "rowwise.cuh"
 #include "tc_gemm.cuh"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "mega.cuh"
 #include "dp_comm.cuh"
 #include <cstdio>
@@ -1233,7 +1234,7 @@ int fb200_mha_forward(const fb200_mha_desc* d, const float* query, const float* 
   AttnArgs a{};
   a.Q = Qp; a.K = Kp; a.V = Vp; a.ldq = a.ldk = a.ldv = D; a.O = Oc; a.ldo = D; a.lse = (float*)(w + L.lse);
   a.Sq = d->Sq; a.Sk = d->Skv; a.B = d->B; a.H = d->H; a.hd = D / d->H; a.scale = 1.0f / sqrtf((float)a.hd);
-  CUDA_OK(launch_attn_fwd(a, (cudaStream_t)stream));
+  CUDA_OK(attn_tc_ok(a) ? launch_attn_tc_fwd(a, (cudaStream_t)stream) : launch_attn_fwd(a, (cudaStream_t)stream));   // tensor-core core for hd 16 / 32 / 64
   if (d->flags & FB200_MHA_POOL_MEAN) {          // out [B, D] = out_proj(mean over the query tokens): the pooling commutes with the projection
     float* pooled = (float*)(w + L.pool);
     int grid = (d->B * D / 4 + 255) / 256; if (grid > 1184) grid = 1184;
@@ -1276,7 +1277,7 @@ int fb200_mha_backward(const fb200_mha_desc* d, const float* query, const float*
   a.Q = Qp; a.K = Kp; a.V = Vp; a.ldq = a.ldk = a.ldv = D; a.O = Oc; a.ldo = D; a.lse = (float*)(w + L.lse); a.delta = (float*)(w + L.delta);
   a.dO = dOc; a.lddo = D; a.dQ = dQp; a.dK = dKp; a.dV = dVp; a.lddq = a.lddk = a.lddv = D;
   a.Sq = d->Sq; a.Sk = d->Skv; a.B = d->B; a.H = d->H; a.hd = D / d->H; a.scale = 1.0f / sqrtf((float)a.hd);
-  CUDA_OK(launch_attn_bwd(a, st));
+  CUDA_OK(attn_tc_ok(a) ? launch_attn_tc_bwd(a, st) : launch_attn_bwd(a, st));
   // in_proj: dW = [dQ^T query; dK^T key; dV^T value], db = column sums, and the input gradients
   rc = gemm_auto(2, D, D, Mq, dQp, D, query, D, d_in_proj_weight, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;
   rc = gemm_auto(2, D, D, Mk, dKp, D, key, D, d_in_proj_weight + (size_t)D * D, D, nullptr, 0, stream); if (rc != FB200_OK) return rc;

@@ -233,30 +233,26 @@ __device__ __forceinline__ float4 tabt_mult4(const TabtDrop& d, const uint8_t* m
 }
 
 // ---- attention rows -------------------------------------------------------------------------------------------------------------
-// One (head, query) per thread: softmax over the T keys in two passes (max, then exponentials and the weighted value sum), the
-// way torch computes it.  Dropout acts on the normalised probabilities (F.multi_head_attention_forward / SDPA dropout_p):
+// One (head, query) per thread, ONE pass over the T keys with a running (max, sum, output row) - four keys per trip, the running
+// maximum only moves (and the accumulators are only rescaled) when one of the four beats it.  Scores are kept in base-2 units
+// (q is pre-multiplied by log2(e) / sqrt(hd)), so every exponential is one ex2 and the saved log-sum-exp is in base 2 as well.
+// Dropout acts on the normalised probabilities (F.multi_head_attention_forward / SDPA dropout_p):
 // A_i = sum_j P_ij keep_ij / (1 - p) V_j with the denominator of P taken over ALL keys.  keep bits of row (h, i) go to
 // bits[(h*T + i) * W + j/32] for the backward phases.
+constexpr float TABT_LOG2E = 1.4426950408889634f, TABT_LN2 = 0.6931471805599453f;
 template <int HD>
 __device__ __forceinline__ void tabt_attn_fwd(const float* QKV, int ld3, int T, int H, int D, float scale, float* A, int ldA,
-                                              float* lse, uint32_t* bits, int W, const TabtDrop& dr, const uint8_t* mask /*[H][T][T]*/,
+                                              float* lse2, uint32_t* bits, int W, const TabtDrop& dr, const uint8_t* mask /*[H][T][T]*/,
                                               int site, int64_t b) {
   const int T4 = (T + 3) & ~3;
   for (int it = threadIdx.x; it < H * T; it += TABT_THREADS) {
     const int h = it / T, i = it - h * T;
     float q[HD];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = QKV[i * ld3 + h * HD + d] * scale;
+    for (int d = 0; d < HD; ++d) q[d] = QKV[i * ld3 + h * HD + d] * (scale * TABT_LOG2E);
     const float* Kb = QKV + D + h * HD;
     const float* Vb = QKV + 2 * D + h * HD;
-    float m = -INFINITY;
-    for (int j = 0; j < T; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(q[d], Kb[j * ld3 + d], s);
-      m = fmaxf(m, s);
-    }
-    float l = 0.f, o[HD];
+    float m = -INFINITY, l = 0.f, o[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) o[d] = 0.f;
     uint32_t word = 0;
@@ -269,24 +265,39 @@ __device__ __forceinline__ void tabt_attn_fwd(const float* QKV, int ld3, int T, 
         } else keep = tabt_keep4(dr, (uint64_t)((((int64_t)b * H + h) * T + i) * T4 + j0) >> 2, site);
       }
       word |= keep << (j0 & 31);
-      for (int jj = 0; jj < 4 && j0 + jj < T; ++jj) {
-        const int j = j0 + jj;
-        float s = 0.f;
+      float sc[4];
+      float mx = -INFINITY;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) s = fmaf(q[d], Kb[j * ld3 + d], s);
-        const float e = expf(s - m);
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = min(j0 + jj, T - 1);                       // the tail re-reads the last key; masked below
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) a = fmaf(q[d], Kb[j * ld3 + d], a);
+        sc[jj] = j0 + jj < T ? a : -INFINITY;
+        mx = fmaxf(mx, sc[jj]);
+      }
+      if (mx > m) {                                              // exp2(-inf) = 0 on the first trip
+        const float c = exp2f(m - mx);
+        l *= c;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] *= c;
+        m = mx;
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = min(j0 + jj, T - 1);
+        const float e = exp2f(sc[jj] - m);                       // 0 for the masked tail
         l += e;
-        if (keep & (1u << jj)) {
+        const float ek = (keep >> jj) & 1u ? e : 0.f;
 #pragma unroll
-          for (int d = 0; d < HD; ++d) o[d] = fmaf(e, Vb[j * ld3 + d], o[d]);
-        }
+        for (int d = 0; d < HD; ++d) o[d] = fmaf(ek, Vb[j * ld3 + d], o[d]);
       }
       if (bits && (((j0 + 4) & 31) == 0 || j0 + 4 >= T)) { bits[it * W + (j0 >> 5)] = word; word = 0; }
     }
     const float inv = dr.keep_scale / l;
 #pragma unroll
     for (int d = 0; d < HD; ++d) A[i * ldA + h * HD + d] = o[d] * inv;
-    if (lse) lse[it] = m + logf(l);
+    if (lse2) lse2[it] = m + log2f(l);
   }
 }
 
@@ -300,7 +311,7 @@ __device__ __forceinline__ void tabt_attn_bwd_q(const float* QKV, int ld3, const
     float dl = 0.f;
 #pragma unroll
     for (int d = 0; d < HD; ++d) {
-      q[d] = QKV[i * ld3 + h * HD + d] * scale; g[d] = dA[i * ldA + h * HD + d]; dq[d] = 0.f;
+      q[d] = QKV[i * ld3 + h * HD + d] * (scale * TABT_LOG2E); g[d] = dA[i * ldA + h * HD + d]; dq[d] = 0.f;
       dl = fmaf(g[d], A[i * ldA + h * HD + d], dl);
     }
     const float* Kb = QKV + D + h * HD;
@@ -311,7 +322,7 @@ __device__ __forceinline__ void tabt_attn_bwd_q(const float* QKV, int ld3, const
 #pragma unroll
       for (int d = 0; d < HD; ++d) { s = fmaf(q[d], Kb[j * ld3 + d], s); dp = fmaf(g[d], Vb[j * ld3 + d], dp); }
       const float keep = (bits[it * W + (j >> 5)] >> (j & 31)) & 1u ? keep_scale : 0.f;
-      const float ds = T == 1 ? 0.f : expf(s - ls) * (dp * keep - dl);      // one key: dS == 0 exactly, as in torch
+      const float ds = T == 1 ? 0.f : exp2f(s - ls) * (dp * keep - dl);     // one key: dS == 0 exactly, as in torch
 #pragma unroll
       for (int d = 0; d < HD; ++d) dq[d] = fmaf(ds, Kb[j * ld3 + d], dq[d]);
     }
@@ -336,75 +347,92 @@ __device__ __forceinline__ void tabt_attn_bwd_kv(const float* QKV, int ld3, cons
       float q[HD], g[HD];
 #pragma unroll
       for (int d = 0; d < HD; ++d) {
-        q[d] = QKV[i * ld3 + h * HD + d] * scale; g[d] = dA[i * ldA + h * HD + d];
+        q[d] = QKV[i * ld3 + h * HD + d] * (scale * TABT_LOG2E); g[d] = dA[i * ldA + h * HD + d];   // base-2 score units; dk is rescaled at the end
         s = fmaf(q[d], k[d], s); dp = fmaf(g[d], v[d], dp);
       }
       const int row = h * T + i;
       const float keep = (bits[row * W + (j >> 5)] >> (j & 31)) & 1u ? keep_scale : 0.f;
-      const float pr = expf(s - lse[row]);
+      const float pr = exp2f(s - lse[row]);
       const float pk = pr * keep;
       const float ds = T == 1 ? 0.f : pr * (dp * keep - delta[row]);
 #pragma unroll
       for (int d = 0; d < HD; ++d) { dv[d] = fmaf(pk, g[d], dv[d]); dk[d] = fmaf(ds, q[d], dk[d]); }
     }
 #pragma unroll
-    for (int d = 0; d < HD; ++d) { dQKV[j * ldg + D + h * HD + d] = dk[d]; dQKV[j * ldg + 2 * D + h * HD + d] = dv[d]; }
+    for (int d = 0; d < HD; ++d) { dQKV[j * ldg + D + h * HD + d] = dk[d] * TABT_LN2; dQKV[j * ldg + 2 * D + h * HD + d] = dv[d]; }
   }
 }
 
-// ---- residual + LayerNorm (one token per thread) ---------------------------------------------------------------------------------
+// ---- residual + LayerNorm (four adjacent lanes per token, sums by quad shuffles) -----------------------------------------------------
+__device__ __forceinline__ float tabt_quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
 // v = R[t] + mult * Y[t];  xhat = (v - mean) rstd -> Y (in place);  dst[t] = xhat * gamma + beta (when dst != nullptr)
 __device__ __forceinline__ void tabt_res_ln(const float* R, float* Y, int ld, int T, int D, const float* __restrict__ gamma, const float* __restrict__ beta,
                                             const TabtDrop& dr, const uint8_t* mask, int site, int64_t row0, float* dst, float* rstd_s) {
-  for (int t = threadIdx.x; t < T; t += TABT_THREADS) {
+  const int sub = threadIdx.x & 3;
+  for (int t0 = 0; t0 < T; t0 += TABT_THREADS / 4) {               // uniform trip count: every lane reaches the shuffles
+    const int t = t0 + (threadIdx.x >> 2);
+    const bool ok = t < T;
+    const int tt = ok ? t : T - 1;
     float sum = 0.f;
-    for (int k = 0; k < D; k += 4) {
-      const float4 r = *(const float4*)(R + t * ld + k), y = *(const float4*)(Y + t * ld + k), m = tabt_mult4(dr, mask, site, row0 + t, k, D);
+    for (int k = 4 * sub; k < D; k += 16) {
+      const float4 r = *(const float4*)(R + tt * ld + k), y = *(const float4*)(Y + tt * ld + k), m = tabt_mult4(dr, mask, site, row0 + tt, k, D);
       const float4 v = make_float4(fmaf(y.x, m.x, r.x), fmaf(y.y, m.y, r.y), fmaf(y.z, m.z, r.z), fmaf(y.w, m.w, r.w));
-      *(float4*)(Y + t * ld + k) = v;
+      if (ok) *(float4*)(Y + tt * ld + k) = v;
       sum += (v.x + v.y) + (v.z + v.w);
     }
-    const float mean = sum / (float)D;
+    const float mean = tabt_quad_sum(sum) / (float)D;
+    __syncwarp();                                                    // the quad re-reads only its own writes; kept for clarity of the memory order
     float var = 0.f;
-    for (int k = 0; k < D; k += 4) {
-      const float4 v = *(const float4*)(Y + t * ld + k);
+    for (int k = 4 * sub; k < D; k += 16) {
+      const float4 v = *(const float4*)(Y + tt * ld + k);
       const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
       var += (a * a + b * b) + (c * c + d * d);
     }
-    const float rstd = 1.0f / sqrtf(var / (float)D + 1e-5f);
-    for (int k = 0; k < D; k += 4) {
-      const float4 v = *(const float4*)(Y + t * ld + k);
-      const float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
-      *(float4*)(Y + t * ld + k) = xh;
-      if (dst) {
-        const float4 g = __ldg((const float4*)(gamma + k)), be = __ldg((const float4*)(beta + k));
-        *(float4*)(dst + t * ld + k) = make_float4(fmaf(xh.x, g.x, be.x), fmaf(xh.y, g.y, be.y), fmaf(xh.z, g.z, be.z), fmaf(xh.w, g.w, be.w));
+    const float rstd = 1.0f / sqrtf(tabt_quad_sum(var) / (float)D + 1e-5f);
+    if (ok) {
+      for (int k = 4 * sub; k < D; k += 16) {
+        const float4 v = *(const float4*)(Y + tt * ld + k);
+        const float4 xh = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
+        *(float4*)(Y + tt * ld + k) = xh;
+        if (dst) {
+          const float4 g = __ldg((const float4*)(gamma + k)), be = __ldg((const float4*)(beta + k));
+          *(float4*)(dst + tt * ld + k) = make_float4(fmaf(xh.x, g.x, be.x), fmaf(xh.y, g.y, be.y), fmaf(xh.z, g.z, be.z), fmaf(xh.w, g.w, be.w));
+        }
       }
+      if (sub == 0) rstd_s[tt] = rstd;
     }
-    rstd_s[t] = rstd;
   }
 }
 // G[t] <- dS = rstd (g*gamma - mean(g*gamma) - xhat mean(g*gamma*xhat))  (gradient of the LayerNorm input = of the residual sum);
 // G2[t] <- dS * mult  (gradient of the branch that went through dropout)
 __device__ __forceinline__ void tabt_ln_bwd(float* Gs, const float* Xh, int ld, int T, int D, const float* __restrict__ gamma, const float* rstd_s,
                                             const TabtDrop& dr, const uint8_t* mask, int site, int64_t row0, float* G2) {
-  for (int t = threadIdx.x; t < T; t += TABT_THREADS) {
+  const int sub = threadIdx.x & 3;
+  for (int t0 = 0; t0 < T; t0 += TABT_THREADS / 4) {
+    const int t = t0 + (threadIdx.x >> 2);
+    const bool ok = t < T;
+    const int tt = ok ? t : T - 1;
     float m1 = 0.f, m2 = 0.f;
-    for (int k = 0; k < D; k += 4) {
-      const float4 g = *(const float4*)(Gs + t * ld + k), ga = __ldg((const float4*)(gamma + k)), xh = *(const float4*)(Xh + t * ld + k);
+    for (int k = 4 * sub; k < D; k += 16) {
+      const float4 g = *(const float4*)(Gs + tt * ld + k), ga = __ldg((const float4*)(gamma + k)), xh = *(const float4*)(Xh + tt * ld + k);
       const float a = g.x * ga.x, b = g.y * ga.y, c = g.z * ga.z, d = g.w * ga.w;
       m1 += (a + b) + (c + d);
       m2 += fmaf(a, xh.x, b * xh.y) + fmaf(c, xh.z, d * xh.w);
     }
-    m1 /= (float)D; m2 /= (float)D;
-    const float rstd = rstd_s[t];
-    for (int k = 0; k < D; k += 4) {
-      const float4 g = *(const float4*)(Gs + t * ld + k), ga = __ldg((const float4*)(gamma + k)), xh = *(const float4*)(Xh + t * ld + k);
-      const float4 m = tabt_mult4(dr, mask, site, row0 + t, k, D);
-      const float4 ds = make_float4(rstd * (g.x * ga.x - m1 - xh.x * m2), rstd * (g.y * ga.y - m1 - xh.y * m2),
-                                    rstd * (g.z * ga.z - m1 - xh.z * m2), rstd * (g.w * ga.w - m1 - xh.w * m2));
-      *(float4*)(Gs + t * ld + k) = ds;
-      *(float4*)(G2 + t * ld + k) = make_float4(ds.x * m.x, ds.y * m.y, ds.z * m.z, ds.w * m.w);
+    m1 = tabt_quad_sum(m1) / (float)D; m2 = tabt_quad_sum(m2) / (float)D;
+    if (ok) {
+      const float rstd = rstd_s[tt];
+      for (int k = 4 * sub; k < D; k += 16) {
+        const float4 g = *(const float4*)(Gs + tt * ld + k), ga = __ldg((const float4*)(gamma + k)), xh = *(const float4*)(Xh + tt * ld + k);
+        const float4 m = tabt_mult4(dr, mask, site, row0 + tt, k, D);
+        const float4 ds = make_float4(rstd * (g.x * ga.x - m1 - xh.x * m2), rstd * (g.y * ga.y - m1 - xh.y * m2),
+                                      rstd * (g.z * ga.z - m1 - xh.z * m2), rstd * (g.w * ga.w - m1 - xh.w * m2));
+        *(float4*)(Gs + tt * ld + k) = ds;
+        *(float4*)(G2 + tt * ld + k) = make_float4(ds.x * m.x, ds.y * m.y, ds.z * m.z, ds.w * m.w);
+      }
     }
   }
 }
