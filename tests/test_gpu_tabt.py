@@ -123,3 +123,70 @@ def test_full_batch_is_deterministic_and_philox_dropout_has_the_right_rate():
     # LayerNorm output: every token row of the encoder part is normalised before the affine map (default gamma = 1, beta = 0)
     tok = e1[:, :82 * 32].reshape(B, 82, 32)
     assert tok.mean(-1).abs().max() < 1e-5 and (tok.var(-1, unbiased=False) - 1).abs().max() < 1e-3
+
+
+def test_config4_end_to_end_tab_transformer_feeds_the_fused_head():
+    """BASELINE configs[3]: tab-transformer metadata + GFCAM fusion.  model(img_feat, (x_cat, x_num)) -> weighted CE ->
+    backward through the fused head AND the fused TabTransformer, against the two oracles chained by hand the way SURVEY 8c
+    prescribes (txt_feat = text_encoder(x_cat, x_num), then the reference's own sub-modules from text_projector on)."""
+    from oracle import head_oracle as ho
+    from tests.golden import cases as C
+    B, F, Cn = 48, 768, 2
+    kw = dict(mechanism="gfcam", F=F, V=None, C=Cn, T=85, text_model="tab-transformer")
+    cfg = C.make_cfg(kw)
+    hp = C.gen_params(cfg, 21, np.float32)
+    cards = [10] * 82
+    tp = {k: v.astype(np.float32) for k, v in to.gen_params(to.param_shapes(cards, 4, 32, 128, 2, 85), 22).items()}
+    model = fb.MultimodalModel(Cn, cfg.H, "cuda", f"identity:{F}", "tab-transformer", common_dim=cfg.D, text_encoder_dim_output=85,
+                               attention_mecanism="gfcam")
+    sd = {k: torch.from_numpy(v) for k, v in hp.items()}
+    sd.update({"text_encoder." + k: torch.from_numpy(v) for k, v in tp.items()})
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and not [k for k in res.missing_keys if not k.startswith("image_encoder.")], res
+    model = model.cuda().eval()
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((B, F)).astype(np.float32)
+    x_cat = rng.integers(0, 10, size=(B, 82)).astype(np.int64)
+    x_num = rng.standard_normal((B, 4)).astype(np.float32)
+    labels = rng.integers(0, Cn, size=B).astype(np.int64)
+    cw = np.array([0.7, 1.6], np.float32)
+    # oracles, float64, chained by hand; samples sitting on a ReLU tie of the encoder are redrawn
+    tp64 = {k: v.astype(np.float64) for k, v in tp.items()}
+    hp64 = {k: v.astype(np.float64) for k, v in hp.items()}
+    for _ in range(20):
+        enc = to.forward_backward(tp64, x_cat, x_num.astype(np.float64), 4, 0.3, None, None)
+        tied = np.nonzero(enc["sample_margin"] < 2e-5)[0]
+        if tied.size == 0:
+            break
+        x_cat[tied] = rng.integers(0, 10, size=(tied.size, 82))
+    for _ in range(20):
+        head = ho.head_forward_backward(cfg, hp64, x.astype(np.float64), enc["out"], labels, cw.astype(np.float64), None, need_input_grad=True)
+        if head["relu_margin"] > 2e-5:
+            break
+        x = rng.standard_normal((B, F)).astype(np.float32)
+    assert head["relu_margin"] > 2e-5
+    encb = to.forward_backward(tp64, x_cat, x_num.astype(np.float64), 4, 0.3, None, head["d_text_in"])
+    # CUDA: the drop-in call shape of the training loops
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    logits = model(xt, (torch.from_numpy(x_cat).cuda(), torch.from_numpy(x_num).cuda()))
+    loss = fb.FusedCrossEntropyLoss(weight=torch.from_numpy(cw).cuda())(logits, torch.from_numpy(labels).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert parity.rel_err(logits.detach().cpu().numpy(), head["logits"]) < TOL
+    assert abs(float(loss) - head["loss"]) / abs(head["loss"]) < TOL
+    assert np.array_equal(logits.argmax(1).cpu().numpy(), head["logits"].argmax(1))
+    worst = ("", 0.0)
+    named = dict(model.named_parameters())
+    for k, g in head["grads"].items():
+        if g is None or np.abs(g).max() == 0:
+            continue
+        e = parity.rel_err(named[k].grad.cpu().numpy(), g)
+        worst = max(worst, (k, e), key=lambda kv: kv[1])
+    for k, g in encb["grads"].items():
+        if np.abs(g).max() == 0:
+            continue
+        e = parity.rel_err(named["text_encoder." + k].grad.cpu().numpy(), g)
+        worst = max(worst, ("text_encoder." + k, e), key=lambda kv: kv[1])
+    e = parity.rel_err(xt.grad.cpu().numpy(), head["d_img_feat"])
+    worst = max(worst, ("d_img_feat", e), key=lambda kv: kv[1])
+    assert worst[1] < 2e-5, worst          # two fp32 stages chained: the head's 1e-5 on top of the encoder's

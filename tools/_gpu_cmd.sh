@@ -1,6 +1,12 @@
-set -x
-python -m pytest tests/test_gpu_tabt.py -q -k deterministic 2>&1 | tail -3
-python tools/attn_once.py && ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02c_attn_launches.csv python tools/attn_once.py > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 3 -c 3 -o gpurun_out/r02c_attn_tc -f python tools/attn_once.py > gpurun_out/r02c_attn_tc_ncu.log 2>&1
-python tools/tabt_once.py 1024 && ncu --set full --clock-control none --import-source on -k regex:tabt_ -s 3 -c 3 -o gpurun_out/r02c_tabt -f python tools/tabt_once.py 1024 > gpurun_out/r02c_tabt_ncu.log 2>&1
-ls -la gpurun_out/*.ncu-rep
+O=gpurun_out
+python -m pytest tests/test_gpu_parity.py -q -k "rgatt or cfg5 or cfg4b or small" 2>&1 | tail -3
+for wl in cfg4b cfg5; do
+  python bench.py --workload $wl --no-cpu-baseline --no-incumbent --no-extras --sweep "" --steps 40 > $O/r02c_wide1_$wl.json 2>/dev/null
+  FB200_GRB_WIDE=0 python bench.py --workload $wl --no-cpu-baseline --no-incumbent --no-extras --sweep "" --steps 40 > $O/r02c_wide0_$wl.json 2>/dev/null
+done
+python - <<'PY'
+import json
+for wl in ("cfg4b","cfg5"):
+    for w in (1,0):
+        d=json.load(open(f"gpurun_out/r02c_wide{w}_{wl}.json")); print(wl, "wide",w, d["ms_per_step"], d["dtype"])
+PY
