@@ -249,7 +249,7 @@ __device__ __forceinline__ void tabt_attn_fwd(const float* QKV, int ld3, int T, 
     const int h = it / T, i = it - h * T;
     float q[HD];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = QKV[i * ld3 + h * HD + d] * (scale * TABT_LOG2E);
+    for (int d = 0; d < HD; ++d) q[d] = QKV[i * ld3 + h * HD + d];              // pre-scaled by the in-projection epilogue
     const float* Kb = QKV + D + h * HD;
     const float* Vb = QKV + 2 * D + h * HD;
     float m = -INFINITY, l = 0.f, o[HD];
@@ -311,12 +311,13 @@ __device__ __forceinline__ void tabt_attn_bwd_q(const float* QKV, int ld3, const
     float dl = 0.f;
 #pragma unroll
     for (int d = 0; d < HD; ++d) {
-      q[d] = QKV[i * ld3 + h * HD + d] * (scale * TABT_LOG2E); g[d] = dA[i * ldA + h * HD + d]; dq[d] = 0.f;
+      q[d] = QKV[i * ld3 + h * HD + d]; g[d] = dA[i * ldA + h * HD + d]; dq[d] = 0.f;
       dl = fmaf(g[d], A[i * ldA + h * HD + d], dl);
     }
     const float* Kb = QKV + D + h * HD;
     const float* Vb = QKV + 2 * D + h * HD;
     const float ls = lse[it];
+#pragma unroll 2
     for (int j = 0; j < T; ++j) {
       float s = 0.f, dp = 0.f;
 #pragma unroll
@@ -342,12 +343,13 @@ __device__ __forceinline__ void tabt_attn_bwd_kv(const float* QKV, int ld3, cons
     float k[HD], v[HD], dk[HD], dv[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) { k[d] = QKV[j * ld3 + D + h * HD + d]; v[d] = QKV[j * ld3 + 2 * D + h * HD + d]; dk[d] = 0.f; dv[d] = 0.f; }
+#pragma unroll 2
     for (int i = 0; i < T; ++i) {
       float s = 0.f, dp = 0.f;
       float q[HD], g[HD];
 #pragma unroll
       for (int d = 0; d < HD; ++d) {
-        q[d] = QKV[i * ld3 + h * HD + d] * (scale * TABT_LOG2E); g[d] = dA[i * ldA + h * HD + d];   // base-2 score units; dk is rescaled at the end
+        q[d] = QKV[i * ld3 + h * HD + d]; g[d] = dA[i * ldA + h * HD + d];   // base-2 score units; dk is rescaled at the end
         s = fmaf(q[d], k[d], s); dp = fmaf(g[d], v[d], dp);
       }
       const int row = h * T + i;
@@ -457,7 +459,12 @@ __device__ __forceinline__ void tabt_layer_fwd(const TabtArgs& a, const TabtSmem
   float* X = S + sm.X; float* QKV = S + sm.QKV; float* A = S + sm.A; float* Xh1 = S + sm.Xh1; float* X1 = S + sm.X1;
   float* Hb = S + sm.Hb; float* Xh2 = S + sm.Xh2;
   // packed in-projection: [Q | K | V] = X W_in^T + b_in
-  tabt_lin_nt<4>(X, ldD, P + o.win, P + o.bin, T, 3 * D, D, [&](int t, int n, float4 v) { *(float4*)(QKV + t * ld3 + n) = v; });
+  // (the Q columns are stored pre-multiplied by log2(e) / sqrt(hd): every attention phase reads them in base-2 score units)
+  const float qs = TABT_LOG2E / sqrtf((float)HD);
+  tabt_lin_nt<4>(X, ldD, P + o.win, P + o.bin, T, 3 * D, D, [&](int t, int n, float4 v) {
+    if (n < D) { v.x *= qs; v.y *= qs; v.z *= qs; v.w *= qs; }
+    *(float4*)(QKV + t * ld3 + n) = v;
+  });
   __syncthreads();
   tabt_attn_fwd<HD>(QKV, ld3, T, H, D, 1.0f / sqrtf((float)HD), A, ldD, keep_for_bwd ? S + sm.lse : nullptr,
                     keep_for_bwd ? (uint32_t*)(S + sm.bits) : nullptr, W, dr, m_attn, site + 0, b);

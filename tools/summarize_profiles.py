@@ -73,7 +73,48 @@ def attention():
     return recs
 
 
+def rep_summary(rep, out_name, command, shape, extra_metrics=()):
+    """ncu --set full report -> JSON of the per-kernel counters that explain it (tensor / FMA pipe, issue slots, stalls, DRAM)."""
+    if not os.path.exists(rep):
+        print("missing", rep); return []
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines())); hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+            "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"] + list(extra_metrics)
+    recs = [{w: (r[idx[w]] + " " + units[idx[w]]).strip() for w in want if w in idx} for r in rows[2:]]
+    json.dump({"command": command, "shape": shape, "kernels": recs}, open(os.path.join(P, out_name), "w"), indent=1)
+    return recs
+
+
+def r02c():
+    a = rep_summary(os.path.join(G, "r02c_attn_tc.ncu-rep"), "r02c_attention_tc_ncu_summary.json",
+                    "ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 3 -c 3 python tools/attn_once.py",
+                    "Sq=197 image tokens, Skv=85 metadata tokens, B=32, D=512, H=8 (hd=64), fp32 via 3xTF32 mma.sync")
+    t = rep_summary(os.path.join(G, "r02c_tabt.ncu-rep"), "r02c_tabt_ncu_summary.json",
+                    "ncu --set full --clock-control none --import-source on -k regex:tabt_ -s 3 -c 3 python tools/tabt_once.py 4096",
+                    "TabTransformer encoder, B=4096 samples x 82 tokens x d=32, 4 heads, ff=128, 2 layers, train mode (Philox dropout), fp32")
+    for r in a + t:
+        print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                                                   "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")})
+    for src, dst in (("r02c_bench_head.json", "r02c_bench_head.json"), ("r02c_tabt_bench.log", "r02c_tabt_bench.txt"),
+                     ("r02c_attn_bench.log", "r02c_attn_bench.txt"), ("r02c_gputest.log", "r02c_gputest.txt")):
+        if os.path.exists(os.path.join(G, src)):
+            open(os.path.join(P, dst), "w").write(open(os.path.join(G, src)).read())
+
+
 if __name__ == "__main__":
+    if tag == "r02c":
+        r02c(); sys.exit(0)
     tot, agg = launch_list(); print("launch list total", tot)
     for r in attention(): print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum")})
     for r in full(): print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed")})
