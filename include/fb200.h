@@ -175,6 +175,8 @@ int fb200_debug_tc_trace(void* device_buf);
 /* debug: clock64 stamps of CTA 0 of the persistent step kernel (>= 2 + 2 * stages int64; NULL disables), and that kernel
  * with `nstages` empty stages (launch + grid-barrier cost alone; ws256: 256 bytes of device memory) */
 int fb200_debug_mega_trace(void* device_buf);
+/* debug: clock64 stamps of CTA 0 of the TabTransformer kernels after every phase of its first sample (int64[32]; NULL disables) */
+int fb200_debug_tabt_trace(void* device_buf);
 /* host only: shape of the program the persistent step kernel (fp32, B <= 64) runs for `d`; pass 0 forward, 1 backward, 2 fused
  * train step; out[4] = stages, GEMM ops, row ops, tile tasks.  FB200_EUNSUPPORTED when `d` takes the per-op kernels. */
 int fb200_mega_program_info(const fb200_desc* d, int pass, int* out);

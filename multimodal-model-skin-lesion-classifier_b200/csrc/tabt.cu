@@ -69,7 +69,10 @@ struct TabtArgs {
   const uint8_t* mask_res1;      //                               [L][B*T][D]
   const uint8_t* mask_ff;        //                               [L][B*T][F]
   const uint8_t* mask_res2;      //                               [L][B*T][D]
+  long long* trace;              // debug: clock64 stamps of CTA 0 after every phase (fb200_debug_tabt_trace), else nullptr
 };
+
+#define TABT_STAMP(a, k) do { if ((a).trace && blockIdx.x == 0 && threadIdx.x == 0) (a).trace[k] = clock64(); } while (0)
 
 __device__ __forceinline__ float dot4(const float4 a, const float4 b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
@@ -444,7 +447,8 @@ __device__ __forceinline__ void tabt_ln_bwd(float* Gs, const float* Xh, int ld, 
 // keep bits stay in shared memory for the backward phases.
 template <int HD>
 __device__ __forceinline__ void tabt_layer_fwd(const TabtArgs& a, const TabtSmem& sm, float* S, const float* P, int layer, int64_t b,
-                                               const TabtDrop& dr, float* dst, bool keep_for_bwd) {
+                                               const TabtDrop& dr, float* dst, bool keep_for_bwd, int tb = -1) {
+  if (tb >= 0) TABT_STAMP(a, tb);
   const int T = a.T, D = a.D, F = a.F, H = a.H;
   const int ldD = tabt_ld(D), ld3 = tabt_ld(3 * D), ldF = tabt_ld(F);
   const int W = (((T + 3) & ~3) + 31) / 32;
@@ -466,24 +470,31 @@ __device__ __forceinline__ void tabt_layer_fwd(const TabtArgs& a, const TabtSmem
     *(float4*)(QKV + t * ld3 + n) = v;
   });
   __syncthreads();
+  if (tb >= 0) TABT_STAMP(a, tb + 1);
   tabt_attn_fwd<HD>(QKV, ld3, T, H, D, 1.0f / sqrtf((float)HD), A, ldD, keep_for_bwd ? S + sm.lse : nullptr,
                     keep_for_bwd ? (uint32_t*)(S + sm.bits) : nullptr, W, dr, m_attn, site + 0, b);
   __syncthreads();
+  if (tb >= 0) TABT_STAMP(a, tb + 2);
   // output projection -> Xh1 (temporary), then X1 = LayerNorm1(X + dropout1(.))
   tabt_lin_nt<2>(A, ldD, P + o.wo, P + o.bo, T, D, D, [&](int t, int n, float4 v) { *(float4*)(Xh1 + t * ldD + n) = v; });
   __syncthreads();
+  if (tb >= 0) TABT_STAMP(a, tb + 3);
   tabt_res_ln(X, Xh1, ldD, T, D, P + o.g1, P + o.be1, dr, m_res1, site + 1, row0, X1, S + sm.rstd1);
   __syncthreads();
+  if (tb >= 0) TABT_STAMP(a, tb + 4);
   // feed-forward: Hb = dropout(relu(X1 W1^T + b1)),  Z = Hb W2^T + b2 -> Xh2 (temporary),  out = LayerNorm2(X1 + dropout2(Z))
   tabt_lin_nt<4>(X1, ldD, P + o.w1, P + o.b1, T, F, D, [&](int t, int n, float4 v) {
     const float4 m = tabt_mult4(dr, m_ff, site + 2, row0 + t, n, F);
     *(float4*)(Hb + t * ldF + n) = make_float4(fmaxf(v.x, 0.f) * m.x, fmaxf(v.y, 0.f) * m.y, fmaxf(v.z, 0.f) * m.z, fmaxf(v.w, 0.f) * m.w);
   });
   __syncthreads();
+  if (tb >= 0) TABT_STAMP(a, tb + 5);
   tabt_lin_nt<2>(Hb, ldF, P + o.w2, P + o.b2, T, D, F, [&](int t, int n, float4 v) { *(float4*)(Xh2 + t * ldD + n) = v; });
   __syncthreads();
+  if (tb >= 0) TABT_STAMP(a, tb + 6);
   tabt_res_ln(X1, Xh2, ldD, T, D, P + o.g2, P + o.be2, dr, m_res2, site + 3, row0, dst, S + sm.rstd2);
   __syncthreads();
+  if (tb >= 0) TABT_STAMP(a, tb + 7);
 }
 
 __device__ __forceinline__ void tabt_gather(const TabtArgs& a, int64_t b, float* X, int ldD) {
@@ -511,7 +522,7 @@ __global__ void __launch_bounds__(TABT_THREADS, 1) tabt_fwd_kernel(const TabtArg
     tabt_gather(a, b, S + sm.X, ldD);
     __syncthreads();
     for (int l = 0; l < a.L; ++l) {
-      tabt_layer_fwd<HD>(a, sm, S, a.params + (size_t)l * lsize, l, b, dr, S + sm.X, false);    // the output becomes the next layer's input
+      tabt_layer_fwd<HD>(a, sm, S, a.params + (size_t)l * lsize, l, b, dr, S + sm.X, false, (b == blockIdx.x && l == 0) ? 0 : -1);    // the output becomes the next layer's input
       const bool last = l == a.L - 1;
       float* dstg = last ? a.out + b * a.ldo : a.saved + ((size_t)l * a.B + b) * a.T * a.D;
       for (int idx = threadIdx.x; idx < a.T * g; idx += TABT_THREADS) {
@@ -564,12 +575,15 @@ __global__ void __launch_bounds__(TABT_THREADS, 1) tabt_bwd_kernel(const TabtArg
         }
       }
       __syncthreads();
-      tabt_layer_fwd<HD>(a, sm, S, P, l, b, dr, nullptr, true);        // recompute: Xh1, X1, Hb, Xh2, rstd, lse, keep bits
+      const int tb = (b == blockIdx.x && l == a.L - 1) ? 0 : -1;          // phase timeline of CTA 0 (tools/tabt_trace.py)
+      tabt_layer_fwd<HD>(a, sm, S, P, l, b, dr, nullptr, true, tb);        // recompute: Xh1, X1, Hb, Xh2, rstd, lse, keep bits
       // LayerNorm2: parameter gradients, then G <- dS2 (residual path), G2 <- dZ = dS2 * dropout2
       tabt_ln_param_grads(G, Xh2, ldD, T, D, gs + o.g2, gs + o.be2);
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 8);
       tabt_ln_bwd(G, Xh2, ldD, T, D, P + o.g2, S + sm.rstd2, dr, m_res2, site + 3, row0, G2);
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 9);
       // linear2: dW2 += dZ^T Hb, db2 += colsum(dZ); dHpre = (dZ W2) * [Hb > 0] / (1 - p)  (Hb > 0 <=> ReLU active AND kept)
       tabt_grad_tn<2>(G2, ldD, Hb, ldF, T, D, F, gs + o.w2);
       tabt_colsum(G2, ldD, T, D, gs + o.b2);
@@ -579,6 +593,7 @@ __global__ void __launch_bounds__(TABT_THREADS, 1) tabt_bwd_kernel(const TabtArg
         *(float4*)(dH + t * ldg + k) = make_float4(h.x > 0.f ? v.x * s : 0.f, h.y > 0.f ? v.y * s : 0.f, h.z > 0.f ? v.z * s : 0.f, h.w > 0.f ? v.w * s : 0.f);
       });
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 10);
       // linear1: dW1 += dHpre^T X1, db1 += colsum(dHpre); G += dHpre W1  (G = gradient of X1)
       tabt_grad_tn<2>(dH, ldg, X1, ldD, T, F, D, gs + o.w1);
       tabt_colsum(dH, ldg, T, F, gs + o.b1);
@@ -588,22 +603,28 @@ __global__ void __launch_bounds__(TABT_THREADS, 1) tabt_bwd_kernel(const TabtArg
         *(float4*)(G + t * ldD + k) = c;
       });
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 11);
       // LayerNorm1
       tabt_ln_param_grads(G, Xh1, ldD, T, D, gs + o.g1, gs + o.be1);
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 12);
       tabt_ln_bwd(G, Xh1, ldD, T, D, P + o.g1, S + sm.rstd1, dr, m_res1, site + 1, row0, G2);
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 13);
       // output projection: dWo += dY^T A, dbo += colsum(dY); dA = dY Wo -> Xh2 (free now)
       float* dA = Xh2;
       tabt_grad_tn<8>(G2, ldD, A, ldD, T, D, D, gs + o.wo);
       tabt_colsum(G2, ldD, T, D, gs + o.bo);
       tabt_lin_nn<2>(G2, ldD, P + o.wo, T, D, D, [&](int t, int k, float4 v) { *(float4*)(dA + t * ldD + k) = v; });
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 14);
       // attention: dQ (+ delta), then dK and dV, into dH reused as dQKV [T][3D]
       tabt_attn_bwd_q<HD>(QKV, ld3, A, dA, ldD, T, H, D, scale, S + sm.lse, (const uint32_t*)(S + sm.bits), W, dr.keep_scale, S + sm.delta, dH, ldg);
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 15);
       tabt_attn_bwd_kv<HD>(QKV, ld3, dA, ldD, T, H, D, scale, S + sm.lse, S + sm.delta, (const uint32_t*)(S + sm.bits), W, dr.keep_scale, dH, ldg);
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 16);
       // in-projection: dW_in += dQKV^T X, db_in += colsum(dQKV); G += dQKV W_in  (G = gradient of the layer input)
       tabt_grad_tn<2>(dH, ldg, X, ldD, T, 3 * D, D, gs + o.win);
       tabt_colsum(dH, ldg, T, 3 * D, gs + o.bin);
@@ -613,6 +634,7 @@ __global__ void __launch_bounds__(TABT_THREADS, 1) tabt_bwd_kernel(const TabtArg
         *(float4*)(G + t * ldD + k) = c;
       });
       __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 17);
     }
     // embedding rows: every token of a sample hits its own table, so the rows of one sample are distinct
     float* ge = slab + (size_t)a.L * o.size;
@@ -643,6 +665,7 @@ __global__ void __launch_bounds__(256) tabt_reduce_kernel(const float* __restric
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------------
 namespace {
+long long* g_tabt_trace = nullptr;
 bool tabt_dev_ptr(const void* p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -673,6 +696,7 @@ TabtArgs tabt_args(const fb200_tabt_desc& d, const int64_t* codes, const int32_t
   a.p_total = (long long)d.L * tabt_off(d.D, d.F).size + (long long)d.n_emb_rows * d.D;
   a.train = d.train; a.p = d.p; a.seed = seed; a.offset = offset; a.rng_state = (const uint64_t*)rng_state;
   if (masks) { a.mask_attn = masks[0]; a.mask_res1 = masks[1]; a.mask_ff = masks[2]; a.mask_res2 = masks[3]; }
+  a.trace = g_tabt_trace;
   return a;
 }
 #define TABT_CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; } } while (0)
@@ -699,6 +723,9 @@ int tabt_launch_bwd(int hd, int grid, size_t smem, cudaStream_t st, const TabtAr
 using namespace fb200;
 
 extern "C" {
+
+/* debug: device int64[32] that CTA 0 fills with clock64 stamps after every phase of its first sample (nullptr: off) */
+int fb200_debug_tabt_trace(void* buf) { g_tabt_trace = (long long*)buf; return FB200_OK; }
 
 int fb200_tabt_param_elems(const fb200_tabt_desc* d, int64_t* layer_elems, int64_t* total_elems) {
   int rc = tabt_check(d); if (rc != FB200_OK) return rc;

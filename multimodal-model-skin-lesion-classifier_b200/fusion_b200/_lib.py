@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libfb200.so")
+LIB_PATH = os.environ.get("FB200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libfb200.so")   # FB200_LIB: A/B builds of the same library
 
 F32, BF16 = 0, 1
 FLAG_NEED_DIMG, FLAG_NEED_DTEXT, FLAG_FORCE_SIMT, FLAG_FORCE_TC, FLAG_ONE_STREAM, FLAG_NO_MEGA = 1, 2, 4, 8, 16, 32
@@ -114,6 +114,7 @@ def lib():
     sig("fb200_tabt_workspace_bytes", i32, tp, C.POINTER(sz), C.POINTER(sz))
     sig("fb200_tabt_forward", i32, tp, vp, vp, vp, pp, u64, u64, vp, vp, i32, vp, vp)
     sig("fb200_tabt_backward", i32, tp, vp, vp, vp, pp, u64, u64, vp, vp, vp, i32, vp, vp, vp)
+    sig("fb200_debug_tabt_trace", i32, vp)
     sig("fb200_linear_forward", i32, i32, i32, i32, vp, i32, vp, vp, i32, vp, i32, vp)
     sig("fb200_linear_backward", i32, i32, i32, i32, vp, i32, vp, vp, i32, vp, i32, vp, vp, vp)
     _lib = L
