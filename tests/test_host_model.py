@@ -73,8 +73,11 @@ def test_no_cpu_fallback():
 def test_tab_transformer_text_mode():
     m = fb.MultimodalModel(2, 8, "cpu", "identity:768", "tab-transformer", attention_mecanism="gfcam")
     assert m.text_fc is None and m.text_projector.weight.shape == (512, 85)
+    # the encoder is the fused TabTransformer (reference constructor and state_dict); like the head it has no CPU path
+    assert isinstance(m.text_encoder, fb.TabTransformer) and len(m.text_encoder.state_dict()) == 112
     x_cat = torch.randint(0, 10, (3, 82)); x_num = torch.randn(3, 4)
-    assert m.text_encoder(x_cat, x_num).shape == (3, 85)
+    with pytest.raises(fb.Fb200Error):
+        m.text_encoder(x_cat, x_num)
 
 
 def test_backbone_modes():
