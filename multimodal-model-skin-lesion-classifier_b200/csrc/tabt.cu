@@ -44,11 +44,14 @@ __host__ __device__ inline TabtSmem tabt_smem(int T, int D, int F, int H, bool b
   const int W = (((T + 3) & ~3) + 31) / 32;
   TabtSmem s; int c = 0;
   auto take = [&](int n) { int at = c; c += (n + 3) & ~3; return at; };
+  // Backward keeps its shared memory under 164 KB so that the SM's L1 keeps 92 KB for the layer's weights (50 KB, read by
+  // every phase through L1): the feed-forward gradient dH overwrites Hb in place, dQKV later reuses the same region, dZ / dY
+  // (G2) live in the buffer of the layer input X, which is re-read from global memory into the dead X1 buffer for the last phase.
   s.X = take(T * ldD); s.QKV = take(T * ld3); s.A = take(T * ldD); s.Xh1 = take(T * ldD); s.X1 = take(T * ldD);
-  s.Hb = take(T * ldF); s.Xh2 = take(T * ldD);
+  s.Hb = take(T * (bwd && ld3 > ldF ? ld3 : ldF)); s.Xh2 = take(T * ldD);
   s.rstd1 = take(T); s.rstd2 = take(T); s.lse = take(H * T); s.delta = take(H * T); s.bits = take(H * T * W);
-  s.G = s.G2 = s.dH = 0;
-  if (bwd) { s.G = take(T * ldD); s.G2 = take(T * ldD); s.dH = take(T * (ldF > ld3 ? ldF : ld3)); }
+  s.G = 0; s.G2 = s.X; s.dH = s.Hb;
+  if (bwd) s.G = take(T * ldD);
   s.total = c;
   return s;
 }
@@ -508,6 +511,17 @@ __device__ __forceinline__ void tabt_gather(const TabtArgs& a, int64_t b, float*
   }
 }
 
+// the input of layer l of sample b: the embedding gather (layer 0) or the tensor the forward kernel saved (layers >= 1)
+__device__ __forceinline__ void tabt_load_input(const TabtArgs& a, int64_t b, int l, float* X, int ldD) {
+  if (l == 0) { tabt_gather(a, b, X, ldD); return; }
+  const int g4 = a.D >> 2;
+  const float* src = a.saved + ((size_t)(l - 1) * a.B + b) * a.T * a.D;
+  for (int idx = threadIdx.x; idx < a.T * g4; idx += TABT_THREADS) {
+    const int t = idx / g4, k = (idx - t * g4) << 2;
+    *(float4*)(X + t * ldD + k) = __ldg((const float4*)(src + t * a.D + k));
+  }
+}
+
 // ---- forward kernel ---------------------------------------------------------------------------------------------------------------
 template <int HD>
 __global__ void __launch_bounds__(TABT_THREADS, 1) tabt_fwd_kernel(const TabtArgs a) {
@@ -544,13 +558,12 @@ __global__ void __launch_bounds__(TABT_THREADS, 1) tabt_bwd_kernel(const TabtArg
   const int T = a.T, D = a.D, F = a.F, H = a.H;
   const TabtSmem sm = tabt_smem(T, D, F, H, true);
   const int ldD = tabt_ld(D), ld3 = tabt_ld(3 * D), ldF = tabt_ld(F), g4 = D >> 2;
-  const int ldg = ldF > ld3 ? ldF : ld3;
   const int W = (((T + 3) & ~3) + 31) / 32;
   const TabtOff o = tabt_off(D, F);
   const TabtDrop dr = tabt_drop(a);
   float* slab = a.slab + (size_t)blockIdx.x * a.p_total;
   float* X = S + sm.X; float* QKV = S + sm.QKV; float* A = S + sm.A; float* Xh1 = S + sm.Xh1; float* X1 = S + sm.X1;
-  float* Hb = S + sm.Hb; float* Xh2 = S + sm.Xh2; float* G = S + sm.G; float* G2 = S + sm.G2; float* dH = S + sm.dH;
+  float* Hb = S + sm.Hb; float* Xh2 = S + sm.Xh2; float* G = S + sm.G; float* G2 = S + sm.G2;      // G2 aliases X (see tabt_smem)
   const float scale = 1.0f / sqrtf((float)HD);
   for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
     const int64_t row0 = b * T;
@@ -565,15 +578,7 @@ __global__ void __launch_bounds__(TABT_THREADS, 1) tabt_bwd_kernel(const TabtArg
       const size_t lb = (size_t)l * a.B;
       const uint8_t* m_res1 = a.mask_res1 ? a.mask_res1 + lb * T * D : nullptr;
       const uint8_t* m_res2 = a.mask_res2 ? a.mask_res2 + lb * T * D : nullptr;
-      // the layer's input: saved by the forward kernel (layers >= 1) or the embedding gather (layer 0)
-      if (l == 0) tabt_gather(a, b, X, ldD);
-      else {
-        const float* src = a.saved + ((size_t)(l - 1) * a.B + b) * T * D;
-        for (int idx = threadIdx.x; idx < T * g4; idx += TABT_THREADS) {
-          const int t = idx / g4, k = (idx - t * g4) << 2;
-          *(float4*)(X + t * ldD + k) = __ldg((const float4*)(src + t * D + k));
-        }
-      }
+      tabt_load_input(a, b, l, X, ldD);
       __syncthreads();
       const int tb = (b == blockIdx.x && l == a.L - 1) ? 0 : -1;          // phase timeline of CTA 0 (tools/tabt_trace.py)
       tabt_layer_fwd<HD>(a, sm, S, P, l, b, dr, nullptr, true, tb);        // recompute: Xh1, X1, Hb, Xh2, rstd, lse, keep bits
@@ -584,57 +589,64 @@ __global__ void __launch_bounds__(TABT_THREADS, 1) tabt_bwd_kernel(const TabtArg
       tabt_ln_bwd(G, Xh2, ldD, T, D, P + o.g2, S + sm.rstd2, dr, m_res2, site + 3, row0, G2);
       __syncthreads();
       if (tb >= 0) TABT_STAMP(a, 9);
-      // linear2: dW2 += dZ^T Hb, db2 += colsum(dZ); dHpre = (dZ W2) * [Hb > 0] / (1 - p)  (Hb > 0 <=> ReLU active AND kept)
+      // linear2: dW2 += dZ^T Hb, db2 += colsum(dZ); then, IN PLACE over Hb, dHpre = (dZ W2) * [Hb > 0] / (1 - p)
+      // (Hb > 0 <=> ReLU active AND kept; every element is read and overwritten by the same thread, after all of dW2 is done)
       tabt_grad_tn<2>(G2, ldD, Hb, ldF, T, D, F, gs + o.w2);
       tabt_colsum(G2, ldD, T, D, gs + o.b2);
+      __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 10);
       tabt_lin_nn<4>(G2, ldD, P + o.w2, T, D, F, [&](int t, int k, float4 v) {
         const float4 h = *(const float4*)(Hb + t * ldF + k);
         const float s = dr.keep_scale;
-        *(float4*)(dH + t * ldg + k) = make_float4(h.x > 0.f ? v.x * s : 0.f, h.y > 0.f ? v.y * s : 0.f, h.z > 0.f ? v.z * s : 0.f, h.w > 0.f ? v.w * s : 0.f);
+        *(float4*)(Hb + t * ldF + k) = make_float4(h.x > 0.f ? v.x * s : 0.f, h.y > 0.f ? v.y * s : 0.f, h.z > 0.f ? v.z * s : 0.f, h.w > 0.f ? v.w * s : 0.f);
       });
       __syncthreads();
-      if (tb >= 0) TABT_STAMP(a, 10);
+      if (tb >= 0) TABT_STAMP(a, 11);
       // linear1: dW1 += dHpre^T X1, db1 += colsum(dHpre); G += dHpre W1  (G = gradient of X1)
-      tabt_grad_tn<2>(dH, ldg, X1, ldD, T, F, D, gs + o.w1);
-      tabt_colsum(dH, ldg, T, F, gs + o.b1);
-      tabt_lin_nn<2>(dH, ldg, P + o.w1, T, F, D, [&](int t, int k, float4 v) {
+      tabt_grad_tn<2>(Hb, ldF, X1, ldD, T, F, D, gs + o.w1);
+      tabt_colsum(Hb, ldF, T, F, gs + o.b1);
+      tabt_lin_nn<2>(Hb, ldF, P + o.w1, T, F, D, [&](int t, int k, float4 v) {
         float4 c = *(const float4*)(G + t * ldD + k);
         c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
         *(float4*)(G + t * ldD + k) = c;
       });
       __syncthreads();
-      if (tb >= 0) TABT_STAMP(a, 11);
+      if (tb >= 0) TABT_STAMP(a, 12);
       // LayerNorm1
       tabt_ln_param_grads(G, Xh1, ldD, T, D, gs + o.g1, gs + o.be1);
       __syncthreads();
-      if (tb >= 0) TABT_STAMP(a, 12);
+      if (tb >= 0) TABT_STAMP(a, 13);
       tabt_ln_bwd(G, Xh1, ldD, T, D, P + o.g1, S + sm.rstd1, dr, m_res1, site + 1, row0, G2);
       __syncthreads();
-      if (tb >= 0) TABT_STAMP(a, 13);
-      // output projection: dWo += dY^T A, dbo += colsum(dY); dA = dY Wo -> Xh2 (free now)
+      if (tb >= 0) TABT_STAMP(a, 14);
+      // output projection: dWo += dY^T A, dbo += colsum(dY); dA = dY Wo -> Xh2 (free now).  The layer input comes back from
+      // global memory into the X1 buffer (dead since linear1) for the in-projection gradients at the end.
       float* dA = Xh2;
+      float* Xr = X1;
+      tabt_load_input(a, b, l, Xr, ldD);
       tabt_grad_tn<8>(G2, ldD, A, ldD, T, D, D, gs + o.wo);
       tabt_colsum(G2, ldD, T, D, gs + o.bo);
       tabt_lin_nn<2>(G2, ldD, P + o.wo, T, D, D, [&](int t, int k, float4 v) { *(float4*)(dA + t * ldD + k) = v; });
       __syncthreads();
-      if (tb >= 0) TABT_STAMP(a, 14);
-      // attention: dQ (+ delta), then dK and dV, into dH reused as dQKV [T][3D]
-      tabt_attn_bwd_q<HD>(QKV, ld3, A, dA, ldD, T, H, D, scale, S + sm.lse, (const uint32_t*)(S + sm.bits), W, dr.keep_scale, S + sm.delta, dH, ldg);
-      __syncthreads();
       if (tb >= 0) TABT_STAMP(a, 15);
-      tabt_attn_bwd_kv<HD>(QKV, ld3, dA, ldD, T, H, D, scale, S + sm.lse, S + sm.delta, (const uint32_t*)(S + sm.bits), W, dr.keep_scale, dH, ldg);
+      // attention: dQ (+ delta), then dK and dV, into the Hb region reused as dQKV [T][3D]
+      float* dQKV = Hb;
+      tabt_attn_bwd_q<HD>(QKV, ld3, A, dA, ldD, T, H, D, scale, S + sm.lse, (const uint32_t*)(S + sm.bits), W, dr.keep_scale, S + sm.delta, dQKV, ld3);
       __syncthreads();
       if (tb >= 0) TABT_STAMP(a, 16);
+      tabt_attn_bwd_kv<HD>(QKV, ld3, dA, ldD, T, H, D, scale, S + sm.lse, S + sm.delta, (const uint32_t*)(S + sm.bits), W, dr.keep_scale, dQKV, ld3);
+      __syncthreads();
+      if (tb >= 0) TABT_STAMP(a, 17);
       // in-projection: dW_in += dQKV^T X, db_in += colsum(dQKV); G += dQKV W_in  (G = gradient of the layer input)
-      tabt_grad_tn<2>(dH, ldg, X, ldD, T, 3 * D, D, gs + o.win);
-      tabt_colsum(dH, ldg, T, 3 * D, gs + o.bin);
-      tabt_lin_nn<2>(dH, ldg, P + o.win, T, 3 * D, D, [&](int t, int k, float4 v) {
+      tabt_grad_tn<2>(dQKV, ld3, Xr, ldD, T, 3 * D, D, gs + o.win);
+      tabt_colsum(dQKV, ld3, T, 3 * D, gs + o.bin);
+      tabt_lin_nn<2>(dQKV, ld3, P + o.win, T, 3 * D, D, [&](int t, int k, float4 v) {
         float4 c = *(const float4*)(G + t * ldD + k);
         c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
         *(float4*)(G + t * ldD + k) = c;
       });
       __syncthreads();
-      if (tb >= 0) TABT_STAMP(a, 17);
+      if (tb >= 0) TABT_STAMP(a, 18);
     }
     // embedding rows: every token of a sample hits its own table, so the rows of one sample are distinct
     float* ge = slab + (size_t)a.L * o.size;
@@ -703,6 +715,9 @@ TabtArgs tabt_args(const fb200_tabt_desc& d, const int64_t* codes, const int32_t
 template <typename K>
 int tabt_launch(K kern, int grid, size_t smem, cudaStream_t st, const TabtArgs& a) {
   TABT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // leave the rest of the unified 256 KB array to L1: the layer weights are read through it by every phase
+  int carve = (int)(((smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024)); if (carve > 100) carve = 100;
+  TABT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   TABT_CUDA_OK(pdl_launch(kern, grid, TABT_THREADS, smem, st, a));
   return FB200_OK;
 }

@@ -17,7 +17,7 @@ torch.cuda.synchronize()
 tr = torch.zeros(32, dtype=torch.int64, device="cuda")
 L = _lib.lib()
 FWD = ["in-proj (QKV)", "attention rows", "out-proj", "residual+LN1", "ff linear1+relu+drop", "ff linear2", "residual+LN2"]
-BWD = ["LN2 param grads", "LN2 bwd", "dW2 + db2 + dH", "dW1 + db1 + dX1", "LN1 param grads", "LN1 bwd", "dWo + dbo + dA", "attention dQ", "attention dK dV", "dWin + dbin + dX"]
+BWD = ["LN2 param grads", "LN2 bwd", "dW2 + db2", "dH (in place over H)", "dW1 + db1 + dX1", "LN1 param grads", "LN1 bwd", "dWo + dbo + dA", "attention dQ", "attention dK dV", "dWin + dbin + dX"]
 L.fb200_debug_tabt_trace(tr.data_ptr())
 with torch.no_grad():
     m.eval(); m.encode(xc, xn); m.train()
@@ -38,4 +38,4 @@ for i, n in enumerate(FWD):
     print(f"  recompute {n:24s} {t[i + 1] - t[i]:8d}")
 for i, n in enumerate(BWD):
     print(f"  {n:34s} {t[8 + i] - t[7 + i]:8d}")
-print(f"  {'layer total':34s} {t[17] - t[0]:8d}")
+print(f"  {'layer total':34s} {t[18] - t[0]:8d}")
