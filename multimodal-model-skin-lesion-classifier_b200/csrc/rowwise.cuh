@@ -345,56 +345,85 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) grb_fwd_kernel(const GrbArgs p
   __shared__ __align__(16) float2 scratch[2 * ROW_WARPS];
   grb_fwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, nullptr);
 }
+// LayerNorm backward for one row with gamma read where it is used (L1-resident) instead of held in registers across the row loop
+template <int NV, int TPR>
+__device__ __forceinline__ void ln_bwd_row_g(const Grp<TPR>& G, float2* scratch, const float4 (&xh)[NV], float4 (&g)[NV], const float* __restrict__ gamma,
+                                             float rstd, int N, float4 (&dgam)[NV], float4 (&dbet)[NV]) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = COL(i);
+    const float4 gm = (c < N) ? __ldg((const float4*)(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    dgam[i].x += g[i].x * xh[i].x; dgam[i].y += g[i].y * xh[i].y; dgam[i].z += g[i].z * xh[i].z; dgam[i].w += g[i].w * xh[i].w;
+    dbet[i].x += g[i].x; dbet[i].y += g[i].y; dbet[i].z += g[i].z; dbet[i].w += g[i].w;
+    g[i].x *= gm.x; g[i].y *= gm.y; g[i].z *= gm.z; g[i].w *= gm.w;
+    s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+    s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+  }
+  const float2 tot = G.sum2(s1, s2, scratch);
+  s1 = tot.x / (float)N;
+  s2 = tot.y / (float)N;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g[i].x = rstd * (g[i].x - s1 - xh[i].x * s2);
+    g[i].y = rstd * (g[i].y - s1 - xh[i].y * s2);
+    g[i].z = rstd * (g[i].z - s1 - xh[i].z * s2);
+    g[i].w = rstd * (g[i].w - s1 - xh[i].w * s2);
+  }
+}
+// r02d: the row needs q, a, z, dy, the recomputed u and dq - with gamma and both parameter-gradient accumulators that was
+// ~150 live registers per thread, one 8-warp CTA per SM (ncu: 12 % of the warp slots, 1.0 TB/s).  Only the difference
+// w = a*m - q and the gate g are needed after u is formed, gamma is re-read from L1 where it is used: four row vectors live at
+// a time, two CTAs per SM.
 template <int NV, int TPR, bool F32 = false>
 __device__ __forceinline__ void grb_bwd_body(const GrbArgs& p, const int bid, const int nblk, float2* scratch, float* red) {
   const Grp<TPR> G(bid, nblk);
-  float4 gam[NV], dgam[NV], dbet[NV];
-  row_load_param<NV, TPR>(G, p.gamma, p.N, gam);
+  float4 dgam[NV], dbet[NV];
   zero4<NV>(dgam); zero4<NV>(dbet);
   for (int64_t row = G.row0; row < p.B; row += G.rstep) {
-    float4 q[NV], a[NV], z[NV], u[NV], du[NV];
-    row_load<NV, TPR, F32>(G, p.q, row, p.N, q);
-    row_load<NV, TPR, F32>(G, p.a, row, p.N, a);
-    row_load<NV, TPR, F32>(G, p.z, row, p.N, z);
+    float4 u[NV], w[NV], g[NV], du[NV];
+    row_load<NV, TPR, F32>(G, p.q, row, p.N, u);          // q, becomes u
+    row_load<NV, TPR, F32>(G, p.a, row, p.N, w);          // a, becomes a*m - q
+    row_load<NV, TPR, F32>(G, p.z, row, p.N, g);          // z, becomes the gate
     row_load<NV, TPR, F32>(G, p.dy, row, p.N, du);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       int c = COL(i);
       float4 m = (c < p.N) ? drop_mult4(p.drop, row, c, p.N) : make_float4(0.f, 0.f, 0.f, 0.f);
 #define GRB2(f)                                               \
-      { float g = 1.f / (1.f + expf(-z[i].f));               \
-        z[i].f = g; a[i].f *= m.f;                            \
-        u[i].f = g * a[i].f + (1.f - g) * q[i].f; }
+      { const float gg = 1.f / (1.f + expf(-g[i].f));        \
+        const float am = w[i].f * m.f, qq = u[i].f;           \
+        g[i].f = gg; w[i].f = am - qq;                        \
+        u[i].f = gg * am + (1.f - gg) * qq; }
       GRB2(x) GRB2(y) GRB2(z) GRB2(w)
 #undef GRB2
-      // keep the dropout multiplier for da in place of nothing: recomputed below
     }
     const float mean = p.stats[row * 2], rstd = p.stats[row * 2 + 1];
     normalize<NV, TPR>(G, u, mean, rstd, p.N);
-    ln_bwd_row<NV, TPR>(G, scratch, u, du, gam, rstd, p.N, dgam, dbet);     // du now holds d(u)
-    float4 dq[NV];
+    ln_bwd_row_g<NV, TPR>(G, scratch, u, du, p.gamma, rstd, p.N, dgam, dbet);     // du now holds d(u)
+    float4 (&dq)[NV] = u;                                                          // u is dead: its registers take dq
     if (p.dq_accumulate) row_load<NV, TPR, F32>(G, p.dq, row, p.N, dq); else zero4<NV>(dq);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       int c = COL(i);
       float4 m = (c < p.N) ? drop_mult4(p.drop, row, c, p.N) : make_float4(0.f, 0.f, 0.f, 0.f);
 #define GRB3(f)                                               \
-      { float g = z[i].f;                                     \
-        dq[i].f += du[i].f * (1.f - g);                       \
-        z[i].f = du[i].f * (a[i].f - q[i].f) * g * (1.f - g); \
-        a[i].f = du[i].f * g * m.f; }
+      { const float gg = g[i].f, d = du[i].f;                 \
+        dq[i].f += d * (1.f - gg);                            \
+        g[i].f = d * w[i].f * gg * (1.f - gg);                \
+        w[i].f = d * gg * m.f; }
       GRB3(x) GRB3(y) GRB3(z) GRB3(w)
 #undef GRB3
     }
-    row_store<NV, TPR, F32>(G, p.da, row, p.N, a);
-    row_store<NV, TPR, F32>(G, p.dz, row, p.N, z);
+    row_store<NV, TPR, F32>(G, p.da, row, p.N, w);
+    row_store<NV, TPR, F32>(G, p.dz, row, p.N, g);
     row_store<NV, TPR, F32>(G, p.dq, row, p.N, dq);
   }
   cta_colsum_atomic<NV, TPR>(G, dgam, p.N, p.dgamma, red);
   cta_colsum_atomic<NV, TPR>(G, dbet, p.N, p.dbeta, red);
 }
 template <int NV, int TPR>
-__global__ void __launch_bounds__(ROW_WARPS * 32) grb_bwd_kernel(const GrbArgs p) { pdl_sync();
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2) grb_bwd_kernel(const GrbArgs p) { pdl_sync();
   __shared__ __align__(16) float2 scratch[2 * ROW_WARPS]; __shared__ __align__(16) float red[ROW_WARPS * 512];
   grb_bwd_body<NV, TPR>(p, blockIdx.x, gridDim.x, scratch, red);
 }

@@ -41,6 +41,8 @@ struct TcEpilogue {
   int accumulate;         // C += result
   int atomic;             // split-K: fp32 atomic add into C (FMT_F32 only)
   float* colsum;          // optional: colsum[n] += sum_m result(m,n)  (unused by the head; reserved)
+  int csplit;             // set by the launcher: CTAs of one thread-block cluster (1,1,csplit) that share an output tile, each
+                          // reducing a slice of K; the partial tiles meet through distributed shared memory (0 / 1 = none)
   int dbg;                // debug (timing experiments only, results are wrong): 1 skip B split, 2 skip A split, 16 no tcgen05.st, 32 no A TMA, 64 no B TMA
   long long* trace;       // debug: per-k-block clock64 stamps of CTA (0,0,0): [i*8 + {issue, full, mma_issued, empty_seen, split_done}]
 };
@@ -93,6 +95,29 @@ __device__ __forceinline__ bool elect_one_sync() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// thread-block cluster: rank of this CTA, barrier over every thread of the cluster, peer shared-memory addresses
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");   // (not .aligned: callable after divergent code)
+}
+__device__ __forceinline__ uint32_t cluster_map_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
+  float4 v; asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory"); return v;
+}
+// sum of the float4 at the same shared-memory offset in the S CTAs of the cluster, in rank order (bit-reproducible); the S
+// loads are issued back to back so that one remote latency covers them all
+template <int S>
+__device__ __forceinline__ float4 dsmem_sum_v4(uint32_t addr) {
+  float4 w[S];
+#pragma unroll
+  for (int p = 0; p < S; ++p) w[p] = ld_dsmem_v4(cluster_map_shared(addr, (uint32_t)p));
+  float4 v = w[0];
+#pragma unroll
+  for (int p = 1; p < S; ++p) { v.x += w[p].x; v.y += w[p].y; v.z += w[p].z; v.w += w[p].w; }
+  return v;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -324,6 +349,8 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         if (ATM && i + 1 < num_kb) load_a(i + 1);
       }
     }
+    __syncwarp();
+    if (ep.csplit > 1) { cluster_sync_all(); cluster_sync_all(); }                 // the two barriers of the workers' cluster epilogue
   } else if (warp == 1) {
     // ===== MMA issuer: the WHOLE warp walks the k-blocks in lock step, one ELECTED lane issues.  Uniform control flow keeps
     //       the descriptor arithmetic on the uniform datapath; under a plain `if (lane == 0)` the compiler wraps every
@@ -350,7 +377,10 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         tc_fence_after();
         if (tr && lane == 0) tr[i * 8 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
-        const uint32_t a_hi = smem_u32(ring_b + s * Cfg::STAGE_BYTES);                  // (A in smem: the non-ATM kinds)
+        // & 0x3FFFF: in a cluster launch the shared-window address of a CTA of rank > 0 carries the rank above bit 24; added
+        // unmasked to a descriptor it spills out of the 14-bit start-address field into the LBO field (the chunk stride of
+        // MN-major operands: every 32-column chunk but the first read garbage - found with cluster split-K, r02d)
+        const uint32_t a_hi = smem_u32(ring_b + s * Cfg::STAGE_BYTES) & 0x3FFFFu;       // (A in smem: the non-ATM kinds)
         const uint32_t b_hi = a_hi + Cfg::B_OFF;
         // descriptors differ only in the 14-bit start-address field (>> 4): add to the low word
         const uint64_t da0 = a_desc_base + (uint64_t)(a_hi >> 4), db0 = b_desc_base + (uint64_t)(b_hi >> 4);
@@ -377,6 +407,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         if (tr && lane == 0) tr[i * 8 + 2] = clock64();
       }
     }
+    if (ep.csplit > 1) { cluster_sync_all(); cluster_sync_all(); }
   } else {
     // ===== workers: warps 2..17.  A warp may only touch TMEM lanes [32 (warp % 4), +32); the TC_NH warps that share a
     //       lane quarter split the columns between them (h = which part).  Four warps per scheduler: the operand split is
@@ -508,6 +539,14 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wbase + (uint32_t)((lane * LDS_ROW + h * HN + g * 4) * 4)),
                      "f"(acc[g * 4]), "f"(acc[g * 4 + 1]), "f"(acc[g * 4 + 2]), "f"(acc[g * 4 + 3]) : "memory");
       asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * TC_NH) : "memory");     // the TC_NH warps of this lane quarter
+      // Cluster split-K (ep.csplit = S > 1): the S CTAs of the cluster hold partial sums of the SAME tile, parked at the same
+      // shared-memory offsets.  After a cluster-wide barrier CTA `crank` finishes the rows r with (r / RPI) % S == crank: it reads
+      // the S partial rows through distributed shared memory, adds them in rank order and runs the ordinary epilogue (bias, ReLU,
+      // mask, accumulate, any output format) on the sum - no atomics, no zeroed output, bit-reproducible; a second barrier keeps
+      // every CTA's shared memory alive until its peers have read it.
+      const int S = ep.csplit > 1 ? ep.csplit : 1;
+      uint32_t crank = 0;
+      if (S > 1) { cluster_sync_all(); crank = cluster_ctarank(); }
       if (tr && threadIdx.x == 64) tr[37] = clock64();                               // trace: tile parked in smem
       const int64_t row_base = (int64_t)m0 + q * 32;
       const int rows_valid = (int)((M - row_base) < 32 ? (M - row_base) : 32);
@@ -521,12 +560,21 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       static_assert(BN == 128 || BN == 64, "the epilogue maps BN/4 lanes to one row");
       const int c4 = lane % CPR, rsub = lane / CPR;
       const int n = n0 + c4 * 4;
+      auto ld_tile = [&](uint32_t a) -> float4 {
+        if (S == 2) return dsmem_sum_v4<2>(a);
+        if (S == 4) return dsmem_sum_v4<4>(a);
+        if (S == 8) return dsmem_sum_v4<8>(a);
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+        return v;
+      };
+      auto mine = [&](int r) -> bool { return S == 1 || (uint32_t)((r / RPI) % S) == crank; };
       if (n < N && r_end > r_begin) {
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.bias) bv = __ldg((const float4*)(ep.bias + n));
         const uint32_t rbase = wbase + (uint32_t)(c4 * 16);
         const float floor_v = ep.relu ? 0.f : -INFINITY;
-        if (plain) {
+        if (plain && S == 1) {
           // hot path: all loads of the warp's rows first, then the stores (every data-dependent branch costs its full latency:
           // measured 280 cycles per row in a generic loop, 9 k cycles per tile)
           float* cp = (float*)ep.C.p + row_base * ep.C.ld + n;
@@ -559,8 +607,8 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
             atomicAdd(c, v.x); atomicAdd(c + 1, v.y); atomicAdd(c + 2, v.z); atomicAdd(c + 3, v.w);
           }
         } else {
-          // any output format, ReLU-backward mask, accumulate-into-gradient: every global load of the trip issued before
-          // the first use (the flags are warp-uniform: predicated, no divergence)
+          // any output format, ReLU-backward mask, accumulate-into-gradient, cluster split-K: every load of the trip issued
+          // before the first use (the flags are warp-uniform: predicated, no divergence)
           const bool has_mask = ep.mask_src.p != nullptr, acc_c = ep.accumulate != 0;
           constexpr int U2 = UNR < 4 ? UNR : 4;
           for (int r0 = r_begin; r0 < r_end; r0 += U2 * RPI) {
@@ -568,17 +616,18 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
 #pragma unroll
             for (int u = 0; u < U2; ++u) {
               const int r = r0 + u * RPI + rsub;
-              const bool ok = r < r_end;
+              const bool ok = r < r_end && mine(r);
+              if (S > 1 && !ok) { v[u] = mk[u] = o[u] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
               const int rr = ok ? r : r_begin;
               const int64_t row = row_base + rr;
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(rbase + (uint32_t)(rr * LDS_ROW * 4)));
+              v[u] = ld_tile(rbase + (uint32_t)(rr * LDS_ROW * 4));
               mk[u] = has_mask ? ld4(ep.mask_src, row, n) : make_float4(1.f, 1.f, 1.f, 1.f);
               o[u] = acc_c ? ld4(ep.C, row, n) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < U2; ++u) {
               const int r = r0 + u * RPI + rsub;
-              if (r >= r_end) continue;
+              if (r >= r_end || !mine(r)) continue;
               float4 w;
               w.x = fmaxf(v[u].x + bv.x, floor_v); w.y = fmaxf(v[u].y + bv.y, floor_v);
               w.z = fmaxf(v[u].z + bv.z, floor_v); w.w = fmaxf(v[u].w + bv.w, floor_v);
@@ -589,6 +638,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
           }
         }
       }
+      if (S > 1) cluster_sync_all();                                                  // peers may still be reading this CTA's tile
     }
     tc_fence_before();
     if (tr && threadIdx.x == 64) tr[29] = clock64();                                 // trace: tile stored
@@ -628,7 +678,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_grouped_tn_kernel(const
   const int tiles_n = (g.N[p] + BN - 1) / BN;
   TcEpilogue ep;
   ep.C = make_ref(g.C[p], g.ldc[p], FMT_F32); ep.bias = nullptr; ep.relu = 0; ep.mask_src.p = nullptr; ep.accumulate = g.accumulate[p];
-  ep.atomic = 0; ep.colsum = nullptr; ep.trace = nullptr; ep.dbg = 0;
+  ep.atomic = 0; ep.colsum = nullptr; ep.trace = nullptr; ep.dbg = 0; ep.csplit = 0;
   tc_gemm_tile<KIND, 1, 1, BN>(&g.maps[2 * p], &g.maps[2 * p + 1], ep, g.M[p], g.N[p], (t / tiles_n) * TC_BM, (t % tiles_n) * BN, 0,
                                (g.K + Cfg::BK - 1) / Cfg::BK, nullptr);
 }
@@ -738,10 +788,29 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   int kb_per = (total_kb + split - 1) / split;
   split = (total_kb + kb_per - 1) / kb_per;                       // no empty slices
   ep.atomic = split > 1 ? 1 : 0;
+  // Cluster split-K: when the tiles of this GEMM leave most of the chip idle (batches up to ~512 rows against the 512-wide
+  // layers) the k-loop - the only part of a latency-bound launch that parallelises - is cut across the CTAs of a cluster
+  // (1, 1, S) and the partial tiles are summed through distributed shared memory in the epilogue (tc_gemm_tile).
+  // S = the largest power of two that keeps the launch within HALF the chip (the other lane's GEMM runs beside it; measured:
+  // 64 CTAs win 19-22 %, 128 CTAs are a wash in fp32 and lose 20 % in bf16), leaves every slice >= 2 k-blocks and divides the
+  // epilogue's rows; and only when it removes enough of the k-loop to pay for two cluster barriers and the remote reads
+  // (a bf16 k-block is ~0.2 us: K = 512 is not worth splitting, K = 2048 is).
+  int csplit = 1;
+  if (split == 1) {
+    static const int cap = [] { const char* e = getenv("FB200_TC_CSPLIT"); return e ? atoi(e) : 8; }();       // 0 / 1: off (A/B runs)
+    const int tiles = tiles_m * tiles_n, max_s = BN == 128 ? 8 : 4, min_saved = KIND == 1 ? 4 : 16;
+    int s = 1;
+    while (s * 2 <= max_s && s * 2 <= cap && tiles * s * 2 <= num_sms / 2 && total_kb / (s * 2) >= 2) s *= 2;
+    for (; s > 1; s >>= 1) { const int per = (total_kb + s - 1) / s; if ((total_kb + per - 1) / per == s) break; }   // no empty slices
+    if (s > 1 && total_kb - (total_kb + s - 1) / s >= min_saved) { csplit = s; kb_per = (total_kb + s - 1) / s; }
+  }
+  ep.csplit = csplit;
   ep.trace = tc_trace_buffer();
   { static const int dbg = [] { const char* e = getenv("FB200_TC_DBG"); return e ? atoi(e) : 0; }(); ep.dbg = dbg; }
-  dim3 grid(tiles_n, tiles_m, split);
-  if (pdl_launch(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, ma, mb, ep, g.M, g.N, g.K, kb_per) != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
+  dim3 grid(tiles_n, tiles_m, csplit > 1 ? csplit : split);
+  const cudaError_t lrc = csplit > 1 ? pdl_launch_cluster(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, dim3(1, 1, csplit), ma, mb, ep, g.M, g.N, g.K, kb_per)
+                                     : pdl_launch(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, ma, mb, ep, g.M, g.N, g.K, kb_per);
+  if (lrc != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
   return FB200_OK;
 }
 
