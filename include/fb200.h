@@ -78,6 +78,8 @@ enum fb200_mechanism {
 #define FB200_FLAG_FORCE_SIMT  4   /* never use the tcgen05 GEMM (exact-fp32 FFMA everywhere) */
 #define FB200_FLAG_FORCE_TC    8   /* use the tcgen05 GEMM wherever its shape rules allow     */
 #define FB200_FLAG_NO_MEGA    32   /* small fp32 batches: keep the per-op kernels instead of the persistent step kernel */
+#define FB200_FLAG_FORCE_MEGA 64   /* fp32: use the persistent step kernel up to its capacity of 64 rows (default: up to 32 rows;
+                                      from 33 rows the tcgen05 GEMMs with cluster split-K are faster - measured) */
 #define FB200_FLAG_ONE_STREAM 16   /* launch everything on the caller's stream (default: the metadata chain of large
                                       batches runs on an internal side stream, forked from and joined back into the
                                       caller's stream inside the call - graph-capturable, invisible to the caller) */

@@ -437,6 +437,9 @@ static int run_backward(Ctx& c) {
             pwritten[o.w_slot] = 1;
             break;
           }
+          // (r02d, measured and removed: running only dX here and leaving dW / db to a deferred FFMA GEMM beside the grouped weight
+          // gradients made the step SLOWER - B = 256: 0.267 vs 0.254 ms, B = 1024: 0.403 vs 0.389, B = 4096: no change - the
+          // 6-row TN GEMM is a worse reduction kernel than this one and lengthens the side lane)
           CUDA_OK(launch_smalln_bwd(a, c.dev.num_sms, c.st));
           pwritten[o.w_slot] = 1;
           if (a.dx.p) set_written(o.dx_view);

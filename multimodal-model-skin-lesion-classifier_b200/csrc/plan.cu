@@ -200,7 +200,10 @@ int build_plan(const fb200_desc& d, Plan& p) {
   // walks the whole op program (mega.cuh) - exact FFMA arithmetic, one launch per pass.  FB200_MEGA=0 / FB200_FLAG_NO_MEGA
   // keep the per-op kernels (A/B measurements, and the FFMA / tcgen05 engines stay covered by the tests through FORCE_*).
   static const bool mega_env_off = [] { const char* e = getenv("FB200_MEGA"); return e && e[0] == '0'; }();
-  p.use_mega = d.dtype == FB200_F32 && d.B <= 64 && !(d.flags & (FB200_FLAG_FORCE_SIMT | FB200_FLAG_FORCE_TC | FB200_FLAG_NO_MEGA)) && !mega_env_off;
+  // r02d: with cluster split-K the tcgen05 path takes 33 .. 64 rows in 0.21 ms against 0.25 - 0.26 ms for the step kernel (which
+  // walks two 32-row groups there), so the step kernel keeps batches up to 32 rows; FB200_FLAG_FORCE_MEGA restores its full range.
+  const int mega_rows = (d.flags & FB200_FLAG_FORCE_MEGA) ? 64 : 32;
+  p.use_mega = d.dtype == FB200_F32 && d.B <= mega_rows && !(d.flags & (FB200_FLAG_FORCE_SIMT | FB200_FLAG_FORCE_TC | FB200_FLAG_NO_MEGA)) && !mega_env_off;
   p.use_tc = !p.use_mega && !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B > 32);
   p.fmt = d.dtype == FB200_BF16 ? FMT_BF16 : FMT_F32;    // fp32-strict keeps everything fp32 in memory (hi/lo split happens in smem)
 

@@ -553,7 +553,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       constexpr int RPW = 32 / TC_NH;                                                // rows each warp of the quarter stores
       const int r_begin = h * RPW;
       const int r_end = rows_valid < r_begin + RPW ? rows_valid : r_begin + RPW;
-      const bool plain = !ep.atomic && !ep.mask_src.p && !ep.accumulate && ep.C.fmt == FMT_F32;
+      const bool plain = !ep.atomic && !ep.mask_src.p && !ep.accumulate && (ep.C.fmt == FMT_F32 || ep.C.fmt == FMT_BF16);
       // BN / 4 lanes cover one row with four columns each: a 128-wide tile is one row per warp store (512 contiguous
       // bytes), a 64-wide tile two rows of 256 bytes
       constexpr int CPR = BN / 4, RPI = 32 / CPR, UNR = RPW / RPI;
@@ -578,6 +578,8 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
           // hot path: all loads of the warp's rows first, then the stores (every data-dependent branch costs its full latency:
           // measured 280 cycles per row in a generic loop, 9 k cycles per tile)
           float* cp = (float*)ep.C.p + row_base * ep.C.ld + n;
+          __nv_bfloat16* cb = (__nv_bfloat16*)ep.C.p + row_base * ep.C.ld + n;      // (bf16 outputs: r02d, 8-byte stores, same shape)
+          const bool f32_out = ep.C.fmt == FMT_F32;
           float4 v[UNR];
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
@@ -589,7 +591,14 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
             const int r = r_begin + u * RPI + rsub;
             v[u].x = fmaxf(v[u].x + bv.x, floor_v); v[u].y = fmaxf(v[u].y + bv.y, floor_v);
             v[u].z = fmaxf(v[u].z + bv.z, floor_v); v[u].w = fmaxf(v[u].w + bv.w, floor_v);
-            if (r < r_end) *(float4*)(cp + (int64_t)r * ep.C.ld) = v[u];
+            if (r < r_end) {
+              if (f32_out) *(float4*)(cp + (int64_t)r * ep.C.ld) = v[u];
+              else {
+                const __nv_bfloat162 lo2 = __floats2bfloat162_rn(v[u].x, v[u].y), hi2 = __floats2bfloat162_rn(v[u].z, v[u].w);
+                uint2 raw; raw.x = *reinterpret_cast<const uint32_t*>(&lo2); raw.y = *reinterpret_cast<const uint32_t*>(&hi2);
+                *(uint2*)(cb + (int64_t)r * ep.C.ld) = raw;
+              }
+            }
           }
         } else if (ep.atomic) {
           // split-K slice: fp32 atomic add into the (pre-zeroed or accumulated-into) output; the bias rides on slice 0, a

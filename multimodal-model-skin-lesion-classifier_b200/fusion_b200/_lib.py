@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FB200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libfb200.so")   # FB200_LIB: A/B builds of the same library
 
 F32, BF16 = 0, 1
-FLAG_NEED_DIMG, FLAG_NEED_DTEXT, FLAG_FORCE_SIMT, FLAG_FORCE_TC, FLAG_ONE_STREAM, FLAG_NO_MEGA = 1, 2, 4, 8, 16, 32
+FLAG_NEED_DIMG, FLAG_NEED_DTEXT, FLAG_FORCE_SIMT, FLAG_FORCE_TC, FLAG_ONE_STREAM, FLAG_NO_MEGA, FLAG_FORCE_MEGA = 1, 2, 4, 8, 16, 32, 64
 NUM_DROPOUT_SITES = 6
 DROP_SITES = ("img_res", "txt_res", "img_res2", "txt_res2", "fc1", "fc2")
 

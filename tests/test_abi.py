@@ -189,7 +189,8 @@ def test_engine_policy_and_launch_counts_on_host():
 
     g32, _ = gemms(32)
     assert {e for _, e, *_ in g32} == {0}                                          # FFMA everywhere
-    assert {e for _, e, *_ in gemms(64)[0]} == {0}                                # up to 64 rows: persistent step kernel, FFMA arithmetic
+    assert {e for _, e, *_ in gemms(64, flags=_lib.FLAG_FORCE_MEGA)[0]} == {0}    # persistent step kernel (up to 64 rows when forced): FFMA arithmetic
+    assert gemms(64)[0] == gemms(64, flags=_lib.FLAG_NO_MEGA)[0]                  # default above 32 rows: tcgen05 with cluster split-K
     g64, _ = gemms(64, flags=_lib.FLAG_NO_MEGA)
     assert {e for _, e, *_ in g64} == {0, 1}
     assert all(e == 0 for lay, e, M, N, K in g64 if 85 in (N, K))                  # text_fc.0: K = 85 is not TMA-legal
@@ -216,7 +217,7 @@ def test_step_kernel_program_fits_for_every_fusion_string():
     for mech in ho.MECHANISMS:
         for B in (1, 32, 33, 64):
             for flags in (0, _lib.FLAG_NEED_DIMG | _lib.FLAG_NEED_DTEXT):
-                d = make_desc(mech, B, 2048, 85, 512, 512, 8, 6, n=2, train=True, flags=flags)
+                d = make_desc(mech, B, 2048, 85, 512, 512, 8, 6, n=2, train=True, flags=flags | _lib.FLAG_FORCE_MEGA)
                 for which in (0, 1, 2):
                     info = _lib.mega_program_info(d, which)
                     assert info is not None, (mech, B, which)
@@ -228,6 +229,7 @@ def test_step_kernel_program_fits_for_every_fusion_string():
     fwd, bwd, step = (_lib.mega_program_info(d, w) for w in (0, 1, 2))
     assert step[0] < fwd[0] + bwd[0]                     # the tail (LayerNorm -> head -> CE -> their backward) shares one stage
     assert step[1] == fwd[1] + bwd[1]
-    for kw in (dict(B=65), dict(B=32, dtype="bf16"), dict(B=32, flags=_lib.FLAG_FORCE_SIMT), dict(B=32, flags=_lib.FLAG_NO_MEGA)):
+    assert _lib.mega_program_info(make_desc("crossattention", 33, 2048, 85, 512, 512, 8, 6, train=True)) is None       # default: up to 32 rows
+    for kw in (dict(B=65, flags=_lib.FLAG_FORCE_MEGA), dict(B=32, dtype="bf16"), dict(B=32, flags=_lib.FLAG_FORCE_SIMT), dict(B=32, flags=_lib.FLAG_NO_MEGA)):
         B = kw.pop("B")
         assert _lib.mega_program_info(make_desc("crossattention", B, 2048, 85, 512, 512, 8, 6, **kw)) is None

@@ -23,7 +23,7 @@ def test_fp32_matches_reference_golden(name, engine):
     """Every fixture (B = 32 / 5 / 1 / 33) through the persistent step kernel (the default up to 64 rows: one
     cooperative launch per pass, csrc/mega.cuh) and through the per-op FFMA kernels (FB200_FLAG_FORCE_SIMT)."""
     case = CASES[name]
-    cfg, model = build_model(case, "fp32", flags=0 if engine == "mega" else _lib.FLAG_FORCE_SIMT)
+    cfg, model = build_model(case, "fp32", flags=_lib.FLAG_FORCE_MEGA if engine == "mega" else _lib.FLAG_FORCE_SIMT)
     logits, loss, grads, dx = run_autograd(model, cfg, case)
     worst = parity.check_against_golden(name, case, logits, loss, grads, dx, tol=parity.FP32_TOL)
     print(f"{name} [{engine}]: worst rel err {worst:.2e}")

@@ -86,7 +86,7 @@ def test_two_lane_execution_equals_one_stream(mech, B):
     case = dict(cfg=dict(dims, mechanism=mech), B=B, seed=11, train=False, full_grads=False)
     cfg, one = build_model(case, "fp32", flags=_lib.FLAG_ONE_STREAM | _lib.FLAG_NO_MEGA)
     _, two = build_model(case, "fp32", flags=_lib.FLAG_NO_MEGA)
-    _, mega = build_model(case, "fp32")            # B = 32: the persistent step kernel (repeated steps: its grid barrier and stage order)
+    _, mega = build_model(case, "fp32", flags=_lib.FLAG_FORCE_MEGA)            # B = 32: the persistent step kernel (repeated steps: its grid barrier and stage order)
     x, tin, y, cw, _ = case_inputs(cfg, case)
     one.eval(); two.eval(); mega.eval()
     l_ref, g_ref = _grads_once(one, x, tin, y, cw, True)
