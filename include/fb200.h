@@ -179,7 +179,7 @@ int fb200_debug_tc_trace(void* device_buf);
 int fb200_debug_mega_trace(void* device_buf);
 /* debug: clock64 stamps of CTA 0 of the TabTransformer kernels after every phase of its first sample (int64[32]; NULL disables) */
 int fb200_debug_tabt_trace(void* device_buf);
-/* host only: shape of the program the persistent step kernel (fp32, B <= 64) runs for `d`; pass 0 forward, 1 backward, 2 fused
+/* host only: shape of the program the persistent step kernel (fp32, B <= 32; B <= 64 with FB200_FLAG_FORCE_MEGA) runs for `d`; pass 0 forward, 1 backward, 2 fused
  * train step; out[4] = stages, GEMM ops, row ops, tile tasks.  FB200_EUNSUPPORTED when `d` takes the per-op kernels. */
 int fb200_mega_program_info(const fb200_desc* d, int pass, int* out);
 int fb200_debug_mega_barriers(int nstages, void* ws256, void* stream);

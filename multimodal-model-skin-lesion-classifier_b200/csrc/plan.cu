@@ -202,9 +202,11 @@ int build_plan(const fb200_desc& d, Plan& p) {
   static const bool mega_env_off = [] { const char* e = getenv("FB200_MEGA"); return e && e[0] == '0'; }();
   // r02d: with cluster split-K the tcgen05 path takes 33 .. 64 rows in 0.21 ms against 0.25 - 0.26 ms for the step kernel (which
   // walks two 32-row groups there), so the step kernel keeps batches up to 32 rows; FB200_FLAG_FORCE_MEGA restores its full range.
-  const int mega_rows = (d.flags & FB200_FLAG_FORCE_MEGA) ? 64 : 32;
+  static const int mega_rows_env = [] { const char* e = getenv("FB200_MEGA_ROWS"); return e ? atoi(e) : 32; }();   // A/B: largest batch of the step kernel
+  static const int tc_min_env = [] { const char* e = getenv("FB200_TC_MIN"); return e ? atoi(e) : 32; }();         // A/B: tcgen05 above this many rows
+  const int mega_rows = (d.flags & FB200_FLAG_FORCE_MEGA) ? 64 : mega_rows_env;
   p.use_mega = d.dtype == FB200_F32 && d.B <= mega_rows && !(d.flags & (FB200_FLAG_FORCE_SIMT | FB200_FLAG_FORCE_TC | FB200_FLAG_NO_MEGA)) && !mega_env_off;
-  p.use_tc = !p.use_mega && !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B > 32);
+  p.use_tc = !p.use_mega && !(d.flags & FB200_FLAG_FORCE_SIMT) && ((d.flags & FB200_FLAG_FORCE_TC) || d.dtype == FB200_BF16 || d.B > tc_min_env);
   p.fmt = d.dtype == FB200_BF16 ? FMT_BF16 : FMT_F32;    // fp32-strict keeps everything fp32 in memory (hi/lo split happens in smem)
 
   Builder b(p);

@@ -100,6 +100,8 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");   // (not .aligned: callable after divergent code)
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t addr, uint32_t rank) {
   uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
 }
@@ -255,7 +257,9 @@ struct TcCfg {
 };
 
 // One 128 x BN output tile: the whole pipeline described at the top of this file.
-template <int KIND, int A_MN, int B_MN, int BN>
+// CL: the cluster split-K variant (r02d).  It is a separate instantiation because merely carrying the runtime branches cost the
+// ordinary kernels 2.9 % at the headline batch (same-box A/B against the r02c build: 0.736 -> 0.758 ms per step).
+template <int KIND, int A_MN, int B_MN, int BN, bool CL = false>
 __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pmap_a, const CUtensorMap* __restrict__ pmap_b, const TcEpilogue& ep,
                                              const int M, const int N, const int m0, const int n0, const int kb_begin, const int num_kb,
                                              long long* tr) {
@@ -349,8 +353,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         if (ATM && i + 1 < num_kb) load_a(i + 1);
       }
     }
-    __syncwarp();
-    if (ep.csplit > 1) { cluster_sync_all(); cluster_sync_all(); }                 // the two barriers of the workers' cluster epilogue
+    if constexpr (CL) { __syncwarp(); cluster_sync_all(); cluster_sync_all(); }    // the two barriers of the workers' cluster epilogue
   } else if (warp == 1) {
     // ===== MMA issuer: the WHOLE warp walks the k-blocks in lock step, one ELECTED lane issues.  Uniform control flow keeps
     //       the descriptor arithmetic on the uniform datapath; under a plain `if (lane == 0)` the compiler wraps every
@@ -407,7 +410,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         if (tr && lane == 0) tr[i * 8 + 2] = clock64();
       }
     }
-    if (ep.csplit > 1) { cluster_sync_all(); cluster_sync_all(); }
+    if constexpr (CL) { cluster_sync_all(); cluster_sync_all(); }
   } else {
     // ===== workers: warps 2..17.  A warp may only touch TMEM lanes [32 (warp % 4), +32); the TC_NH warps that share a
     //       lane quarter split the columns between them (h = which part).  Four warps per scheduler: the operand split is
@@ -544,16 +547,17 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       // the S partial rows through distributed shared memory, adds them in rank order and runs the ordinary epilogue (bias, ReLU,
       // mask, accumulate, any output format) on the sum - no atomics, no zeroed output, bit-reproducible; a second barrier keeps
       // every CTA's shared memory alive until its peers have read it.
-      const int S = ep.csplit > 1 ? ep.csplit : 1;
+      const int S = CL ? ep.csplit : 1;                                              // CL kernels are only launched with csplit >= 2
       uint32_t crank = 0;
-      if (S > 1) { cluster_sync_all(); crank = cluster_ctarank(); }
+      if (CL && tr && threadIdx.x == 64) tr[45] = clock64();                         // trace: own partial tile parked, before the cluster barrier
+      if constexpr (CL) { cluster_sync_all(); crank = cluster_ctarank(); }
       if (tr && threadIdx.x == 64) tr[37] = clock64();                               // trace: tile parked in smem
       const int64_t row_base = (int64_t)m0 + q * 32;
       const int rows_valid = (int)((M - row_base) < 32 ? (M - row_base) : 32);
       constexpr int RPW = 32 / TC_NH;                                                // rows each warp of the quarter stores
       const int r_begin = h * RPW;
       const int r_end = rows_valid < r_begin + RPW ? rows_valid : r_begin + RPW;
-      const bool plain = !ep.atomic && !ep.mask_src.p && !ep.accumulate && (ep.C.fmt == FMT_F32 || ep.C.fmt == FMT_BF16);
+      const bool plain = !CL && !ep.atomic && !ep.mask_src.p && !ep.accumulate && (ep.C.fmt == FMT_F32 || (KIND == 0 && ep.C.fmt == FMT_BF16));
       // BN / 4 lanes cover one row with four columns each: a 128-wide tile is one row per warp store (512 contiguous
       // bytes), a 64-wide tile two rows of 256 bytes
       constexpr int CPR = BN / 4, RPI = 32 / CPR, UNR = RPW / RPI;
@@ -561,25 +565,53 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       const int c4 = lane % CPR, rsub = lane / CPR;
       const int n = n0 + c4 * 4;
       auto ld_tile = [&](uint32_t a) -> float4 {
-        if (S == 2) return dsmem_sum_v4<2>(a);
-        if (S == 4) return dsmem_sum_v4<4>(a);
-        if (S == 8) return dsmem_sum_v4<8>(a);
+        if constexpr (CL) {
+          if (S == 2) return dsmem_sum_v4<2>(a);
+          if (S == 4) return dsmem_sum_v4<4>(a);
+          return dsmem_sum_v4<8>(a);
+        }
         float4 v;
         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
         return v;
       };
-      auto mine = [&](int r) -> bool { return S == 1 || (uint32_t)((r / RPI) % S) == crank; };
+      auto mine = [&](int r) -> bool { return !CL || (uint32_t)((r / RPI) % S) == crank; };
       if (n < N && r_end > r_begin) {
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ep.bias) bv = __ldg((const float4*)(ep.bias + n));
         const uint32_t rbase = wbase + (uint32_t)(c4 * 16);
         const float floor_v = ep.relu ? 0.f : -INFINITY;
-        if (plain && S == 1) {
+        if constexpr (CL) {
+          // cluster split-K: gather the sums of the rows this CTA owns (u = crank, crank + S, ...: at most UNR / 2 of the warp's
+          // rows) with every remote load in flight at once, tell the cluster that this CTA is done reading (arrive - the wait
+          // comes after the stores, so a slow peer costs nothing here), then the ordinary epilogue on registers
+          constexpr int OWN = UNR / 2;
+          float4 v[OWN];
+#pragma unroll
+          for (int k = 0; k < OWN; ++k) {
+            const int u = (int)crank + k * S, r = r_begin + u * RPI + rsub;
+            v[k] = (u < UNR && r < r_end) ? ld_tile(rbase + (uint32_t)(r * LDS_ROW * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          cluster_arrive();
+          if (tr && threadIdx.x == 64) tr[53] = clock64();                             // trace: partial sums gathered
+          const bool has_mask = ep.mask_src.p != nullptr, acc_c = ep.accumulate != 0;
+#pragma unroll
+          for (int k = 0; k < OWN; ++k) {
+            const int u = (int)crank + k * S, r = r_begin + u * RPI + rsub;
+            if (u >= UNR || r >= r_end) continue;
+            const int64_t row = row_base + r;
+            float4 w;
+            w.x = fmaxf(v[k].x + bv.x, floor_v); w.y = fmaxf(v[k].y + bv.y, floor_v);
+            w.z = fmaxf(v[k].z + bv.z, floor_v); w.w = fmaxf(v[k].w + bv.w, floor_v);
+            if (has_mask) { const float4 mk = ld4(ep.mask_src, row, n); w.x = mk.x > 0.f ? w.x : 0.f; w.y = mk.y > 0.f ? w.y : 0.f; w.z = mk.z > 0.f ? w.z : 0.f; w.w = mk.w > 0.f ? w.w : 0.f; }
+            if (acc_c) { const float4 o = ld4(ep.C, row, n); w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
+            st4(ep.C, row, n, w);
+          }
+        } else if (plain) {
           // hot path: all loads of the warp's rows first, then the stores (every data-dependent branch costs its full latency:
           // measured 280 cycles per row in a generic loop, 9 k cycles per tile)
           float* cp = (float*)ep.C.p + row_base * ep.C.ld + n;
           __nv_bfloat16* cb = (__nv_bfloat16*)ep.C.p + row_base * ep.C.ld + n;      // (bf16 outputs: r02d, 8-byte stores, same shape)
-          const bool f32_out = ep.C.fmt == FMT_F32;
+          const bool f32_out = KIND == 1 || ep.C.fmt == FMT_F32;                    // fp32-strict never stores bf16: the branch below folds away
           float4 v[UNR];
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
@@ -626,7 +658,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
             for (int u = 0; u < U2; ++u) {
               const int r = r0 + u * RPI + rsub;
               const bool ok = r < r_end && mine(r);
-              if (S > 1 && !ok) { v[u] = mk[u] = o[u] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+              if (CL && !ok) { v[u] = mk[u] = o[u] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
               const int rr = ok ? r : r_begin;
               const int64_t row = row_base + rr;
               v[u] = ld_tile(rbase + (uint32_t)(rr * LDS_ROW * 4));
@@ -647,7 +679,10 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
           }
         }
       }
-      if (S > 1) cluster_sync_all();                                                  // peers may still be reading this CTA's tile
+      if constexpr (CL) {                                                             // peers may still be reading this CTA's tile
+        if (!(n < N && r_end > r_begin)) cluster_arrive();                              // (threads with nothing to gather arrive here)
+        cluster_wait();
+      }
     }
     tc_fence_before();
     if (tr && threadIdx.x == 64) tr[29] = clock64();                                 // trace: tile stored
@@ -656,7 +691,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
-template <int KIND, int A_MN, int B_MN, int BN>
+template <int KIND, int A_MN, int B_MN, int BN, bool CL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcEpilogue ep, const int M, const int N, const int K, const int kb_per_split) {
@@ -665,7 +700,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int kb_begin = blockIdx.z * kb_per_split;
   const int num_kb = min(total_kb, kb_begin + kb_per_split) - kb_begin;             // >= 1 by construction of the grid
   long long* tr = (ep.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? ep.trace : nullptr;
-  tc_gemm_tile<KIND, A_MN, B_MN, BN>(&map_a, &map_b, ep, M, N, blockIdx.y * TC_BM, blockIdx.x * BN, kb_begin, num_kb, tr);
+  tc_gemm_tile<KIND, A_MN, B_MN, BN, CL>(&map_a, &map_b, ep, M, N, blockIdx.y * TC_BM, blockIdx.x * BN, kb_begin, num_kb, tr);
 }
 
 // All weight gradients of one backward pass in ONE launch: problem p is dW_p[M_p, N_p] = dY_p^T X_p with the
@@ -777,10 +812,14 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   if (rc != FB200_OK) return rc;
   rc = make_operand_map(&mb, KIND, g.B, B_MN ? Cfg::EPC : Cfg::BK, B_MN ? Cfg::BK : BN, B_MN);
   if (rc != FB200_OK) return rc;
-  auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN>;
+  auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN, false>;
+  constexpr bool HAS_CL = KIND == 1 && !A_MN;      // cluster split-K variants exist for the fp32-strict forward / dX layouts (the only users)
   {                                                // forward runs on the caller's thread, backward on autograd's worker
     static std::once_flag once; static cudaError_t attr_rc = cudaSuccess;
-    std::call_once(once, [&] { attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+    std::call_once(once, [&] {
+      attr_rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+      if constexpr (HAS_CL) { if (attr_rc == cudaSuccess) attr_rc = cudaFuncSetAttribute(tc_gemm_kernel<KIND, A_MN, B_MN, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); }
+    });
     if (attr_rc != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
   }
   const int tiles_m = (g.M + TC_BM - 1) / TC_BM, tiles_n = (g.N + BN - 1) / BN;
@@ -802,12 +841,12 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   // (1, 1, S) and the partial tiles are summed through distributed shared memory in the epilogue (tc_gemm_tile).
   // S = the largest power of two that keeps the launch within HALF the chip (the other lane's GEMM runs beside it; measured:
   // 64 CTAs win 19-22 %, 128 CTAs are a wash in fp32 and lose 20 % in bf16), leaves every slice >= 2 k-blocks and divides the
-  // epilogue's rows; and only when it removes enough of the k-loop to pay for two cluster barriers and the remote reads
-  // (a bf16 k-block is ~0.2 us: K = 512 is not worth splitting, K = 2048 is).
+  // epilogue's rows; and only when it removes enough of the k-loop to pay for two cluster barriers and the remote reads.
+  // fp32-strict only: a bf16 k-block is ~0.2 us, splitting K = 512 measured no gain (cfg5, B = 32 .. 256: +-1 %).
   int csplit = 1;
-  if (split == 1) {
+  if (HAS_CL && split == 1) {
     static const int cap = [] { const char* e = getenv("FB200_TC_CSPLIT"); return e ? atoi(e) : 8; }();       // 0 / 1: off (A/B runs)
-    const int tiles = tiles_m * tiles_n, max_s = BN == 128 ? 8 : 4, min_saved = KIND == 1 ? 4 : 16;
+    const int tiles = tiles_m * tiles_n, max_s = BN == 128 ? 8 : 4, min_saved = 4;
     int s = 1;
     while (s * 2 <= max_s && s * 2 <= cap && tiles * s * 2 <= num_sms / 2 && total_kb / (s * 2) >= 2) s *= 2;
     for (; s > 1; s >>= 1) { const int per = (total_kb + s - 1) / s; if ((total_kb + per - 1) / per == s) break; }   // no empty slices
@@ -817,8 +856,11 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   ep.trace = tc_trace_buffer();
   { static const int dbg = [] { const char* e = getenv("FB200_TC_DBG"); return e ? atoi(e) : 0; }(); ep.dbg = dbg; }
   dim3 grid(tiles_n, tiles_m, csplit > 1 ? csplit : split);
-  const cudaError_t lrc = csplit > 1 ? pdl_launch_cluster(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, dim3(1, 1, csplit), ma, mb, ep, g.M, g.N, g.K, kb_per)
-                                     : pdl_launch(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, ma, mb, ep, g.M, g.N, g.K, kb_per);
+  cudaError_t lrc;
+  if constexpr (HAS_CL) {
+    lrc = csplit > 1 ? pdl_launch_cluster(tc_gemm_kernel<KIND, A_MN, B_MN, BN, true>, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, dim3(1, 1, csplit), ma, mb, ep, g.M, g.N, g.K, kb_per)
+                     : pdl_launch(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, ma, mb, ep, g.M, g.N, g.K, kb_per);
+  } else lrc = pdl_launch(kern, grid, dim3(TC_THREADS), Cfg::SMEM_BYTES, st, ma, mb, ep, g.M, g.N, g.K, kb_per);
   if (lrc != cudaSuccess) { cudaGetLastError(); return FB200_ECUDA; }
   return FB200_OK;
 }

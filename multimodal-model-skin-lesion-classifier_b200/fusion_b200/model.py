@@ -11,6 +11,7 @@ called; ``forward`` hands raw device pointers of their weights to the C ABI.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -279,19 +280,30 @@ class GraphedTrainStep:
             raise ValueError("GraphedTrainStep captures the head only: use a frozen backbone (or feed features)")
         self.model, self.args = model, (image, text_metadata, label, class_weights, denom, True, mid_event, flat_out)
         self.mid_event = mid_event
-        side = torch.cuda.Stream(device=image.device)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                model.forward_loss(*self.args)
+        # Engine for the captured step.  Eager calls of small fp32 batches (<= 32 rows) run the persistent step kernel: ONE launch
+        # per pass is what a host-bound loop wants (B = 32, eager forward_loss: 0.29 ms against 0.44 ms with per-op launches).
+        # Inside a graph launches are free, and the per-op tcgen05 kernels with cluster split-K are faster (0.178 against 0.194 ms,
+        # cfg3a 0.162 against 0.184): capture those unless the caller chose an engine.
+        chosen = _lib.FLAG_FORCE_SIMT | _lib.FLAG_FORCE_TC | _lib.FLAG_NO_MEGA | _lib.FLAG_FORCE_MEGA
+        saved_flags = model.engine_flags
+        if model.compute_dtype == "fp32" and not (saved_flags & chosen) and os.environ.get("FB200_GRAPH_ENGINE", "tc") == "tc":
+            model.engine_flags = saved_flags | _lib.FLAG_FORCE_TC
+        try:
+            side = torch.cuda.Stream(device=image.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    model.forward_loss(*self.args)
+                    if after_step is not None:
+                        after_step(model.flat_grad)
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss, self.logits = model.forward_loss(*self.args)
                 if after_step is not None:
                     after_step(model.flat_grad)
-        torch.cuda.current_stream().wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss, self.logits = model.forward_loss(*self.args)
-            if after_step is not None:
-                after_step(model.flat_grad)
+        finally:
+            model.engine_flags = saved_flags
         self.flat_grad = model.flat_grad
         self.desc = model.last_desc
 

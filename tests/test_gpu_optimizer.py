@@ -5,6 +5,7 @@ import pytest
 import torch
 
 import fusion_b200 as fb
+from fusion_b200 import _lib
 from oracle import head_oracle as ho
 from oracle.adam_oracle import AdamOracle
 from tests import parity
@@ -87,3 +88,24 @@ def test_graphed_train_step_equals_eager():
     assert parity.rel_err(step.flat_grad.cpu().numpy(), g0.cpu().numpy()) < 1e-5
     a = float(step.run()); b = float(step.run())
     assert a != b                                            # fresh dropout masks on every replay (device-side Philox offset)
+
+
+def test_graphed_small_batch_captures_the_tensor_core_engine():
+    """B = 32 (the reference's BATCH_SIZE): an eager call is ONE launch of the persistent step kernel, a captured step takes the
+    per-op tcgen05 kernels with cluster split-K (faster inside a graph) - same loss and gradients within the fp32 bar, and the
+    model's own engine flags are left as they were."""
+    case = dict(cfg=dict(mechanism="crossattention", F=2048, V=85, C=6), B=32, seed=4, train=False, full_grads=False)
+    cfg, model = build_model(case, "fp32")
+    x, tin, y, cw, _ = case_inputs(cfg, case)
+    model.eval()
+    loss0, _ = model.forward_loss(x, tin, y, cw)
+    assert _lib.mega_program_info(model.last_desc) is not None          # eager: the step kernel
+    g0 = model.flat_grad.clone(); l0 = float(loss0)
+    step = fb.GraphedTrainStep(model, x, tin, y, cw, warmup=1)
+    assert model.engine_flags == 0 and (step.desc.flags & _lib.FLAG_FORCE_TC)
+    assert _lib.mega_program_info(step.desc) is None                    # captured: per-op kernels
+    step.run(); torch.cuda.synchronize()
+    assert abs(float(step.loss) - l0) < 1e-5 * abs(l0)
+    assert parity.rel_err(step.flat_grad.cpu().numpy(), g0.cpu().numpy()) < 1e-5
+    forced = fb.GraphedTrainStep(build_model(case, "fp32", flags=_lib.FLAG_FORCE_MEGA)[1].eval(), x, tin, y, cw, warmup=1)
+    assert _lib.mega_program_info(forced.desc) is not None              # an engine the caller chose is kept

@@ -4,8 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
-def launch_list():
-    with open(os.path.join(G, f"launches_{tag}.csv")) as f:
+def launch_list(src=None, dst=None, title="one train step (forward + CE + backward), cfg2 crossattention, B=4096, fp32-strict"):
+    with open(os.path.join(G, src or f"launches_{tag}.csv")) as f:
         lines = [l for l in f if l.startswith('"')]
     r = csv.reader(lines); hdr = next(r)
     ki, vi, ui, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Grid Size")
@@ -18,8 +18,8 @@ def launch_list():
         name = re.sub(r"\(.*", "", row[ki]).replace("fb200::", "").replace("void ", "")
         out.append(f"{v:9.1f} us  grid {row[gi]:>14s}  {name}")
         a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v; tot += v
-    with open(os.path.join(P, f"{tag}_launch_list_cfg2_B4096.txt"), "w") as f:
-        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none; one train step (forward + CE + backward), cfg2 crossattention, B=4096, fp32-strict\n")
+    with open(os.path.join(P, dst or f"{tag}_launch_list_cfg2_B4096.txt"), "w") as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none; {title}\n")
         f.write(f"# cold-cache, serialised durations: compare SHARES, not absolutes.  step total {tot:.1f} us over {e - s} launches\n")
         f.write("# --- per kernel ---\n")
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -112,9 +112,31 @@ def r02c():
             open(os.path.join(P, dst), "w").write(open(os.path.join(G, src)).read())
 
 
+def r02d():
+    """fourth session of round 2: cluster split-K GEMM (medium batches), grb_bwd with two CTAs per SM, bf16 plain epilogue"""
+    for src, dst, title in (("launches_r02d_b256.csv", "r02d_launch_list_cfg2_B256.txt", "one train step, cfg2 crossattention, B=256, fp32-strict (cluster split-K GEMMs)"),
+                            ("launches_r02d_cfg5.csv", "r02d_launch_list_cfg5_bf16.txt", "one train step, cfg5 RG-ATT, B=4096, bf16")):
+        if os.path.exists(os.path.join(G, src)):
+            tot, agg = launch_list(src, dst, title); print(dst, "total", tot)
+    rep_summary(os.path.join(G, "r02d_tc_csplit.ncu-rep"), "r02d_tc_gemm_csplit_ncu_summary.json",
+                "ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 30 -c 6 python bench.py --batch 256 --steps 2 --warmup 3 --no-graph ...",
+                "cfg2 crossattention B=256, fp32-strict 3xTF32, 128x64 tiles, cluster split-K (1,1,4)",
+                extra_metrics=("launch__cluster_dim_z", "launch__cluster_size", "sm__ctas_launched.sum"))
+    g = rep_summary(os.path.join(G, "r02d_grb.ncu-rep"), "r02d_grb_ncu_summary.json",
+                    "ncu --set full --clock-control none -k regex:grb_ -s 4 -c 4 python bench.py --workload cfg5 --steps 2 --warmup 3 --no-graph ...",
+                    "cfg5 RG-ATT B=4096 bf16: grb_fwd / grb_bwd rows 512 wide, fp32 element-wise")
+    for r in g:
+        print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread")})
+    for src in ("r02d_bench_head.json", "r02d_bench_cfg3a.json", "r02d_bench_cfg4b.json", "r02d_bench_cfg5.json", "r02d_gputest.log", "r02d_csplit_ab.txt"):
+        if os.path.exists(os.path.join(G, src)):
+            open(os.path.join(P, src.replace(".log", ".txt")), "w").write(open(os.path.join(G, src)).read())
+
+
 if __name__ == "__main__":
     if tag == "r02c":
         r02c(); sys.exit(0)
+    if tag == "r02d":
+        r02d(); sys.exit(0)
     tot, agg = launch_list(); print("launch list total", tot)
     for r in attention(): print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum")})
     for r in full(): print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed")})

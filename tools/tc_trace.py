@@ -26,6 +26,7 @@ for i in range(min(nkb, 20)):
 print("MMA warp gap (median): issued(i)->loop top(i+1)", np.median(t[5:, 7] - t[4:-1, 2]), " loop top->barrier passed", np.median(t[5:, 6] - t[5:, 7]), " fence", np.median(t[5:, 1] - t[5:, 6]))
 print("MMA warp per k-block (median): split_seen->all issued+committed", np.median(t[4:, 2] - t[4:, 1]), " ->next split_seen", np.median(t[5:, 1] - t[4:-1, 2]))
 print("entry->setup done", t[1,5]-t[0,5], " setup->first tma issued", t[0,0]-t[1,5], " first tma->first mma issued", t[0,2]-t[0,0], " last mma issued->acc in regs", t[2,5]-t[nkb-1,2], " acc in regs->parked in smem", t[4,5]-t[2,5], " parked->stored", t[3,5]-t[4,5], " total entry->stored", t[3,5]-t[0,5])
-print("epilogue row loop: parked->r1", t[5,5]-t[4,5], " r1->r5", t[6,5]-t[5,5], " r5->r17", t[7,5]-t[6,5], " r17->end", t[3,5]-t[7,5])
+if t[5, 5]:      # cluster split-K kernel: own partial parked -> cluster barrier passed -> partial sums gathered (arrive) -> stored + cluster wait
+    print("cluster epilogue: own tile parked->barrier passed", t[4,5]-t[5,5], " ->sums gathered", t[6,5]-t[4,5], " ->stored + peers done reading", t[3,5]-t[6,5])
 print("median cycles between successive k-blocks at the MMA thread:", np.median(np.diff(t[:, 1])))
 print("median tma_issued -> full/split seen:", np.median(t[:, 1] - t[:, 0]), " mma_issued(i) -> empty_seen(i+S):", np.median(t[S:, 3] - t[:-S, 2]))
