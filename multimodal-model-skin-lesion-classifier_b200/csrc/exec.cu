@@ -234,7 +234,12 @@ static int run_forward(Ctx& c) {
   }
   LaneSync ls; const cudaStream_t main_st = c.st;
   { int rc = ls.begin(c, p.acts.size()); if (rc != FB200_OK) return rc; }
+  // ops up to the last one of the side lane may have a GEMM of the other lane running beside them (cluster split-K hint)
+  int last_side = -1;
+  if (p.two_lanes) for (int i = 0; i < (int)p.ops.size(); ++i) if (p.ops[i].lane == 1) last_side = i;
+  int op_index = -1;
   for (const Op& o : p.ops) {
+    ++op_index;
     c.st = c.lane_st[o.lane];
     for (int b : {o.in0.buf, o.in1.buf, o.in2.buf}) { int rc = ls.wait_for(o.lane, b); if (rc != FB200_OK) return rc; }
     const int mst = c.mega ? 1 + std::max(c.vr(o.in0.buf), std::max(c.vr(o.in1.buf), c.vr(o.in2.buf))) : 0;   // stage of this op in the step kernel
@@ -252,7 +257,7 @@ static int run_forward(Ctx& c) {
           t.B = tc_operand(weight_operand(c, o), o.in0.cols, o.out.cols);
           t.M = B; t.N = o.out.cols; t.K = o.in0.cols;
           t.ep.C = c.value(o.out); t.ep.bias = c.param(o.b_slot, o.w_row0); t.ep.relu = o.relu; t.ep.mask_src.p = nullptr;
-          t.ep.accumulate = 0; t.ep.atomic = 0; t.ep.colsum = nullptr; t.allow_split = 0;
+          t.ep.accumulate = 0; t.ep.atomic = 0; t.ep.colsum = nullptr; t.allow_split = 0; t.alone = op_index > last_side;
           int rc = launch_tc_gemm(t, c.dev.num_sms, c.st);
           if (rc != FB200_OK) return rc;
           break;
@@ -371,6 +376,8 @@ static int run_backward(Ctx& c) {
   // read-modify-writes of the parameter's gradient slice: a weight applied on both lanes must be ordered too)
   const int nbuf = (int)p.acts.size();
   { int rc = ls.begin(c, p.acts.size() + NUM_SLOTS); if (rc != FB200_OK) return rc; }      // after the zero fill of the gradient buffer
+  int last_side_bwd = -1;            // (same hint as in the forward pass: the backward of these ops shares the chip with the side lane)
+  if (p.two_lanes) for (int i = 0; i < (int)p.ops.size(); ++i) if (p.ops[i].lane == 1) last_side_bwd = i;
   for (int oi = (int)p.ops.size() - 1; oi >= 0; --oi) {
     const Op& o = p.ops[oi];
     // the gradient of a view that lives inside a fully written buffer counts as written
@@ -408,7 +415,7 @@ static int run_backward(Ctx& c) {
             h.M = B; h.N = K; h.K = N;
             h.ep.C = c.grad(o.dx_view); h.ep.bias = nullptr; h.ep.relu = 0; h.ep.mask_src.p = nullptr;
             if (p.acts[o.in0.buf].relu_out) h.ep.mask_src = c.value(o.in0);
-            h.ep.accumulate = is_written(o.dx_view); h.ep.atomic = 0; h.ep.colsum = nullptr; h.allow_split = 0;
+            h.ep.accumulate = is_written(o.dx_view); h.ep.atomic = 0; h.ep.colsum = nullptr; h.allow_split = 0; h.alone = oi > last_side_bwd;
             rc = launch_tc_gemm(h, c.dev.num_sms, c.st);
             if (rc != FB200_OK) return rc;
             set_written(o.dx_view);

@@ -802,6 +802,7 @@ struct TcGemmArgs {
   int M, N, K;
   TcEpilogue ep;
   int allow_split;        // weight-gradient GEMMs: split K across CTAs, atomically reduce into pre-zeroed fp32 C
+  int alone;              // hint for cluster split-K: no GEMM of the other lane runs beside this one (it may fill the whole chip)
 };
 
 template <int KIND, int A_MN, int B_MN, int BN>
@@ -848,7 +849,12 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
     static const int cap = [] { const char* e = getenv("FB200_TC_CSPLIT"); return e ? atoi(e) : 8; }();       // 0 / 1: off (A/B runs)
     const int tiles = tiles_m * tiles_n, max_s = BN == 128 ? 8 : 4, min_saved = 4;
     int s = 1;
-    while (s * 2 <= max_s && s * 2 <= cap && tiles * s * 2 <= num_sms / 2 && total_kb / (s * 2) >= 2) s *= 2;
+    // chip share: a GEMM whose lane runs alone may fill the chip; beside the other lane's GEMM two slices may still fill it
+    // (B = 1024: 64 tiles x 2 = 128 CTAs, 0.377 -> 0.358 ms per step), four or more stay within half (B = 512: 32 tiles x 4 =
+    // 128 CTAs measured 0.287 against 0.274 ms with 64).  FB200_TC_CSPLIT_FILL = 1 / 2 forces whole / half for A/B runs.
+    static const int fill_env = [] { const char* e = getenv("FB200_TC_CSPLIT_FILL"); return e ? atoi(e) : 0; }();
+    auto room = [&](int s2) { const int div = fill_env > 0 ? fill_env : ((g.alone || s2 == 2) ? 1 : 2); return tiles * s2 <= num_sms / div; };
+    while (s * 2 <= max_s && s * 2 <= cap && room(s * 2) && total_kb / (s * 2) >= 2) s *= 2;
     for (; s > 1; s >>= 1) { const int per = (total_kb + s - 1) / s; if ((total_kb + per - 1) / per == s) break; }   // no empty slices
     if (s > 1 && total_kb - (total_kb + s - 1) / s >= min_saved) { csplit = s; kb_per = (total_kb + s - 1) / s; }
   }
