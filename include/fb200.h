@@ -174,6 +174,11 @@ int fb200_debug_gemm_replay(const fb200_desc* d, const void* const* params, cons
  * off for every kernel launched afterwards; returns the previous setting. */
 int fb200_debug_set_pdl(int on);
 int fb200_debug_tc_trace(void* device_buf);
+/* debug: grid-wide timeline of the tcgen05 GEMM launches that follow.  Launch l (in host launch order, grouped weight-gradient
+ * launches excluded) writes, for each of its CTAs, int64[8] = {entry, dependency wait passed, tile stored (globaltimer ns), SM id, accumulator in
+ * registers, tensor memory released, accumulator read out by every worker, MMA warp left the k-loop} at device_buf + (l * 1024 + cta) * 8; launches with more than 1024 CTAs are skipped.  max_launches = slots in device_buf; NULL
+ * switches it off.  Returns the number of launches recorded since the previous call. */
+int fb200_debug_tc_timeline(void* device_buf, int max_launches);
 /* debug: clock64 stamps of CTA 0 of the persistent step kernel (>= 2 + 2 * stages int64; NULL disables), and that kernel
  * with `nstages` empty stages (launch + grid-barrier cost alone; ws256: 256 bytes of device memory) */
 int fb200_debug_mega_trace(void* device_buf);

@@ -141,6 +141,16 @@ __device__ __forceinline__ float4 drop_mult4(const DropSpec& d, int64_t row, int
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_release(); }
+// fp32 add into GLOBAL memory, result unused.  A plain atomicAdd through a pointer whose address space the compiler cannot
+// prove (anything loaded from a program struct in memory, as in the persistent step kernel) compiles to a generic atomic:
+// an isspacep test plus a shared-memory compare-and-swap loop beside the RED - 264 such loops in mega_step_kernel (r02e).
+__device__ __forceinline__ void red_add(float* p, float v) {
+#ifdef FB200_NO_RED_ASM
+  atomicAdd(p, v);
+#else
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+#endif
+}
 inline int& pdl_flag() { static int v = -1; return v; }
 inline bool pdl_enabled() {
   int& v = pdl_flag();

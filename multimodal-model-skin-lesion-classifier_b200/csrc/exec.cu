@@ -833,6 +833,12 @@ __global__ void rng_advance_kernel(uint64_t* state, uint64_t inc) { pdl_sync(); 
 /* debug: device buffer of >= 8*k_blocks int64 receiving pipeline time stamps of CTA (0,0,0) of every tcgen05 GEMM launched afterwards; NULL disables */
 int fb200_debug_set_pdl(int on) { const int prev = pdl_enabled() ? 1 : 0; pdl_flag() = on ? 1 : 0; return prev; }
 int fb200_debug_tc_trace(void* device_buf) { tc_trace_buffer() = (long long*)device_buf; return FB200_OK; }
+int fb200_debug_tc_timeline(void* device_buf, int max_launches) {
+  TcTimeline& t = tc_timeline();
+  const int recorded = t.next;
+  t.buf = (long long*)device_buf; t.max_launches = device_buf ? max_launches : 0; t.next = 0;
+  return recorded;
+}
 /* debug: device buffer of >= 2 + 2 * stages int64 receiving clock64 stamps of CTA 0 of the persistent step kernel
  * ([0] entry, [1 + 2s] own tasks of stage s done, [2 + 2s] barrier after stage s passed); NULL disables */
 /* host only (no CUDA call): the program the persistent step kernel would run for `d` - pass 0 forward, 1 backward, 2 fused train

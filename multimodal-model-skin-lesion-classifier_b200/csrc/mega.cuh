@@ -324,7 +324,7 @@ __device__ __forceinline__ void mega_gemm_tn(const MGemm& g, int tile, float* sm
         for (int c = 0; c < 4; ++c)
           if (n + c < g.N) { float o = acc[i][c]; if (g.accumulate) o += __ldcg(dst + c); dst[c] = o; }
       }
-      if (g.colsum && ch == 0 && lane == 0) atomicAdd(g.colsum + m, cs[i]);
+      if (g.colsum && ch == 0 && lane == 0) red_add(g.colsum + m, cs[i]);
     }
     if (more) {
       __syncthreads();                                            // every warp is done reading the current B tile
@@ -507,8 +507,8 @@ __device__ __forceinline__ void ce_rows_body(const CeArgs& a, int bid, int nblk,
   if (threadIdx.x == 0) {
     float n = 0.f;
     for (int w = 0; w < ROW_WARPS; ++w) n += sm[w];
-    atomicAdd(a.loss_out + 1, n);
-    atomicAdd(a.loss_out + 0, n * inv_den);
+    red_add(a.loss_out + 1, n);
+    red_add(a.loss_out + 0, n * inv_den);
     a.loss_out[2] = den_local;                                 // every CTA stores the same value
   }
 }

@@ -118,13 +118,13 @@ __device__ __forceinline__ void cta_colsum_atomic(const Grp<TPR>& G, const float
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < ROW_WARPS; ++w) s += smem[w * 512 + c];
-      atomicAdd(dst + c, s);
+      red_add(dst + c, s);
     }
   } else {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       int c = COL(i);
-      if (c < N) { atomicAdd(dst + c, part[i].x); atomicAdd(dst + c + 1, part[i].y); atomicAdd(dst + c + 2, part[i].z); atomicAdd(dst + c + 3, part[i].w); }
+      if (c < N) { red_add(dst + c, part[i].x); red_add(dst + c + 1, part[i].y); red_add(dst + c + 2, part[i].z); red_add(dst + c + 3, part[i].w); }
     }
   }
 }
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(256) ce_pass1_kernel(const float* __restrict__
     }
   }
   num = warp_sum(num); den = warp_sum(den);
-  if (lane == 0) { atomicAdd(loss_out + 1, num); atomicAdd(loss_out + 2, den); }
+  if (lane == 0) { red_add(loss_out + 1, num); red_add(loss_out + 2, den); }
 }
 __global__ void __launch_bounds__(256) ce_pass2_kernel(const float* __restrict__ denom, int n, float* __restrict__ loss_out,
                                                        float* __restrict__ dlogits) { pdl_sync();
@@ -725,7 +725,10 @@ __device__ __forceinline__ void smalln_bwd_body(const SmallNArgs& a, const int b
       }
     }
   }
-  // warp partials -> CTA totals in shared memory (fast shared atomics) -> one global atomic per element per CTA
+  // warp partials -> CTA totals in shared memory (shared atomics) -> one global atomic per element per CTA.
+  // (r02e, measured and removed: a shared fp32 atomicAdd is a compare-and-swap loop - ATOMS.CAST.SPIN - so the eight warps were
+  // given turns instead, warp 0 storing and the others adding with plain 128-bit read-modify-writes behind a barrier each.
+  // Same-box A/B, whole step: +0.7 % at B = 4096, +1.5 % at B = 32 / 256 - eight barriers cost more than the spinning.)
   const int tot = a.C * a.K + a.C;                        // sm_dw: zeroed below
   for (int i = threadIdx.x; i < tot; i += blockDim.x) sm_dw[i] = 0.f;
   __syncthreads();
@@ -746,12 +749,12 @@ __device__ __forceinline__ void smalln_bwd_body(const SmallNArgs& a, const int b
   __syncthreads();
   for (int i = threadIdx.x; i < tot; i += blockDim.x) {
     const float v = sm_dw[i];
-    if (i < a.C * a.K) atomicAdd(a.dW + i, v); else atomicAdd(a.db + (i - a.C * a.K), v);
+    if (i < a.C * a.K) red_add(a.dW + i, v); else red_add(a.db + (i - a.C * a.K), v);
   }
 }
 template <int MAXC, int CH>
 __global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_kernel(const SmallNArgs a) { pdl_sync();
-  extern __shared__ float smalln_dyn_smem[];
+  extern __shared__ __align__(16) float smalln_dyn_smem[];
   smalln_bwd_body<MAXC, CH>(a, blockIdx.x, gridDim.x, smalln_dyn_smem);
 }
 inline bool smalln_ok(int C, int K) { return C <= 8 && K % 4 == 0 && K <= 512; }
@@ -854,7 +857,7 @@ __global__ void __launch_bounds__(256) aux_loss_kernel(int kind, const float* __
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) atomicAdd(loss_out, acc);
+  if (lane == 0) red_add(loss_out, acc);
 }
 // softmax probabilities + argmax for evaluation (utils/model_metrics.py:57-58, utils/save_predictions.py:93-94)
 __global__ void __launch_bounds__(256) softmax_argmax_kernel(const float* __restrict__ logits, int B, int C, float* __restrict__ probs, int64_t* __restrict__ pred) { pdl_sync();
@@ -969,7 +972,7 @@ __global__ void __launch_bounds__(256) colsum_batch_kernel(const ColsumBatch a) 
     if (active && r_off == 0 && cg < nv) {
       for (int g2 = 1; g2 < groups; ++g2) { const float4 v = red[g2 * lanes + c_lane]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
       float* d = sg.dst + cg * 4;
-      atomicAdd(d, acc.x); atomicAdd(d + 1, acc.y); atomicAdd(d + 2, acc.z); atomicAdd(d + 3, acc.w);
+      red_add(d, acc.x); red_add(d + 1, acc.y); red_add(d + 2, acc.z); red_add(d + 3, acc.w);
     }
   }
 }

@@ -320,7 +320,14 @@ inline cudaError_t launch_simt_gemm(GemmArgs g, int num_sms, cudaStream_t st) {
   } else if (g.split_k != 1 && g.C.fmt == FMT_F32 && !g.bias && !g.relu && !g.mask_src.p) {
     // atomic split-K only where the epilogue is a plain sum into fp32 (weight gradients)
     int want = (2 * num_sms + tiles - 1) / tiles;
-    int maxs = (g.K + 255) / 256;               // keep >= 256 reduction elements per slice
+    // keep >= 32 reduction elements (two k-steps) per slice, at most 32 slices.  (Until r02e: >= 256 per slice - at B = 256 the
+    // deferred text_fc.0 weight gradient ran as 8 CTAs x 16 k-steps = 26 us beside a 23 us grouped tcgen05 launch and set the
+    // length of the step's tail.)
+#ifdef FB200_OLD_SIMT_SPLIT
+    int maxs = (g.K + 255) / 256;
+#else
+    int maxs = g.K / 32; if (maxs < 1) maxs = 1; if (maxs > 32) maxs = 32;
+#endif
     split = want < 1 ? 1 : (want > maxs ? maxs : want);
     if (split < 1) split = 1;
   }

@@ -32,6 +32,12 @@ constexpr int TC_WORKERS = 4 * TC_NH;             // split + promote + epilogue 
 constexpr int TC_GROUPS = 2;                      // fp32-strict: the workers split k-blocks in turn (group g takes i = g mod TC_GROUPS)
 constexpr int TC_GWARPS = TC_WORKERS / TC_GROUPS; // warps of one group: all four lane quarters x TC_NH / TC_GROUPS column parts
 constexpr int TC_THREADS = 64 + 32 * TC_WORKERS;  // + TMA producer warp + MMA warp
+// bf16 kind, two CTAs per SM (r02e): a bf16 tile is mostly prologue + epilogue (8 k-blocks of ~0.25 us inside a ~4.8 us CTA), so a
+// second resident CTA - half the ring each, the same bytes in flight per SM - lets one tile's epilogue overlap the other's k-loop
+#ifndef FB200_BF16_OCC2
+#define FB200_BF16_OCC2 1
+#endif
+template <int KIND> constexpr int tc_min_ctas() { return (KIND == 0 && FB200_BF16_OCC2) ? 2 : 1; }
 
 struct TcEpilogue {
   TRef C;                 // output view (any Fmt)
@@ -43,8 +49,9 @@ struct TcEpilogue {
   float* colsum;          // optional: colsum[n] += sum_m result(m,n)  (unused by the head; reserved)
   int csplit;             // set by the launcher: CTAs of one thread-block cluster (1,1,csplit) that share an output tile, each
                           // reducing a slice of K; the partial tiles meet through distributed shared memory (0 / 1 = none)
-  int dbg;                // debug (timing experiments only, results are wrong): 1 skip B split, 2 skip A split, 16 no tcgen05.st, 32 no A TMA, 64 no B TMA
+  int dbg;                // debug (timing experiments only, results are wrong): 1 skip B split, 2 skip A split, 16 no tcgen05.st, 32 no A TMA, 64 no B TMA, 128 no global stores in the epilogue
   long long* trace;       // debug: per-k-block clock64 stamps of CTA (0,0,0): [i*8 + {issue, full, mma_issued, empty_seen, split_done}]
+  long long* timeline;    // debug: every CTA of this launch writes [cta * 8 + {entry, dependency wait passed, tile stored, SM id, accumulator in registers, tensor memory released, accumulator read by all workers, MMA warp left the k-loop}] (globaltimer ns)
 };
 
 // ----------------------------------------------------------------------------- PTX wrappers
@@ -93,6 +100,7 @@ __device__ __forceinline__ bool elect_one_sync() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // thread-block cluster: rank of this CTA, barrier over every thread of the cluster, peer shared-memory addresses
@@ -233,7 +241,7 @@ struct TcCfg {
   // by bytes in flight (TMA issue -> landed ~3400 cycles under load, over 4 coupled stages = 1080 cycles per k-block
   // with NO split work and one MMA instead of three); 4 A slots + 5 B slots use the same 224 KB better.
   static constexpr int A_PLANES = ATM ? 1 : PLANES;      // smem planes of A
-  static constexpr int STAGES = (KIND == 0) ? (BN <= 128 ? 6 : 4) : (ATM ? 5 : (BN <= 128 ? 3 : 2));   // ring of B (ATM) / of A+B stages
+  static constexpr int STAGES = (KIND == 0) ? (FB200_BF16_OCC2 ? 3 : (BN <= 128 ? 6 : 4)) : (ATM ? 5 : (BN <= 128 ? 3 : 2));   // ring of B (ATM) / of A+B stages
   static constexpr int A_STAGES = ATM ? 4 : STAGES;      // ATM: ring of raw A tiles in smem = ring of split A tiles in TMEM
   static constexpr int A_RING_BYTES = ATM ? A_STAGES * A_BYTES : 0;                 // ATM: A ring first, then the B ring
   static constexpr int B_OFF = ATM ? 0 : A_PLANES * A_BYTES;                         // B tile offset inside a stage
@@ -282,6 +290,12 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (tr && threadIdx.x == 0) tr[5] = clock64();                                     // trace: kernel entry
+  long long* tl = nullptr;
+  if (ep.timeline && threadIdx.x == 0) {
+    tl = ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+    uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tl[0] = global_ns(); tl[3] = smid;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b);
@@ -302,6 +316,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
   // last MMA is issued - measured 1 % slower, with one stream and with two.)
   pdl_sync();
   if (tr && threadIdx.x == 0) tr[13] = clock64();                                    // trace: setup done
+  if (tl) tl[1] = global_ns();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -409,6 +424,18 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
         __syncwarp();
         if (tr && lane == 0) tr[i * 8 + 2] = clock64();
       }
+    }
+    if (ep.timeline && lane == 0) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[7] = global_ns();   // timeline: MMA warp left the k-loop
+    // Release tensor memory as soon as the workers have read the last accumulator chunk(s) out of it (every worker warp arrives
+    // on tmem_empty after its tcgen05.ld + wait::ld), while they transpose and store the tile: tcgen05.dealloc takes ~0.5 us here,
+    // which used to sit between the tile's last store and the CTA's exit (r02e, tools/tc_handover.py).
+    {
+      const int num_chunks = (num_kb + Cfg::CHUNK_KB - 1) / Cfg::CHUNK_KB;
+      for (int ch = num_chunks > Cfg::ACC_BUFS ? num_chunks - Cfg::ACC_BUFS : 0; ch < num_chunks; ++ch)
+        mbar_wait(&tmem_empty[ch & (Cfg::ACC_BUFS - 1)], (ch / Cfg::ACC_BUFS) & 1);
+      if (ep.timeline && lane == 0) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[6] = global_ns();   // timeline: accumulator read out by every worker
+      tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+      if (ep.timeline && lane == 0) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[5] = global_ns();   // timeline: tensor memory released
     }
     if constexpr (CL) { cluster_sync_all(); cluster_sync_all(); }
   } else {
@@ -528,6 +555,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
       }
     }
     for (; next_promote < num_chunks; ++next_promote) promote(next_promote);
+    if (ep.timeline && threadIdx.x == 64) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[4] = global_ns();   // timeline: accumulator in registers
     if (tr && threadIdx.x == 64) tr[21] = clock64();                                 // trace: accumulator in registers
     // Coalesced epilogue.  A thread holds HN columns of one output ROW (TMEM lane) in registers; written as is, a warp
     // store would touch 32 rows x 16 B (measured: 5.5 us per tile, a third of a K=512 GEMM).  The warps transpose
@@ -623,7 +651,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
             const int r = r_begin + u * RPI + rsub;
             v[u].x = fmaxf(v[u].x + bv.x, floor_v); v[u].y = fmaxf(v[u].y + bv.y, floor_v);
             v[u].z = fmaxf(v[u].z + bv.z, floor_v); v[u].w = fmaxf(v[u].w + bv.w, floor_v);
-            if (r < r_end) {
+            if (r < r_end && !(ep.dbg & 128)) {
               if (f32_out) *(float4*)(cp + (int64_t)r * ep.C.ld) = v[u];
               else {
                 const __nv_bfloat162 lo2 = __floats2bfloat162_rn(v[u].x, v[u].y), hi2 = __floats2bfloat162_rn(v[u].z, v[u].w);
@@ -674,7 +702,7 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
               w.z = fmaxf(v[u].z + bv.z, floor_v); w.w = fmaxf(v[u].w + bv.w, floor_v);
               w.x = (mk[u].x > 0.f ? w.x : 0.f) + o[u].x; w.y = (mk[u].y > 0.f ? w.y : 0.f) + o[u].y;
               w.z = (mk[u].z > 0.f ? w.z : 0.f) + o[u].z; w.w = (mk[u].w > 0.f ? w.w : 0.f) + o[u].w;
-              st4(ep.C, row_base + r, n, w);
+              if (!(ep.dbg & 128)) st4(ep.C, row_base + r, n, w);
             }
           }
         }
@@ -688,11 +716,13 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
     if (tr && threadIdx.x == 64) tr[29] = clock64();                                 // trace: tile stored
   }
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+  // timeline: every warp has stored its rows.  (Stamped by a worker: thread 0 - the TMA producer, idle since its last load - was
+  // observed to read the timer right after ARRIVING at this barrier, ~5 us before the workers got there.)
+  if (ep.timeline && threadIdx.x == 64) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[2] = global_ns();
 }
 
 template <int KIND, int A_MN, int B_MN, int BN, bool CL = false>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, tc_min_ctas<KIND>())
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcEpilogue ep, const int M, const int N, const int K, const int kb_per_split) {
   using Cfg = TcCfg<KIND, BN, KIND == 1 ? 1 : 0>;
@@ -714,7 +744,7 @@ struct TcGroupArgs {
   int nprob; int K;
 };
 template <int KIND, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_grouped_tn_kernel(const __grid_constant__ TcGroupArgs g) {
+__global__ void __launch_bounds__(TC_THREADS, tc_min_ctas<KIND>()) tc_gemm_grouped_tn_kernel(const __grid_constant__ TcGroupArgs g) {
   using Cfg = TcCfg<KIND, BN, KIND == 1 ? 1 : 0>;
   int p = 0;
   while (p + 1 < g.nprob && (int)blockIdx.x >= g.tile_begin[p + 1]) ++p;
@@ -722,13 +752,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_grouped_tn_kernel(const
   const int tiles_n = (g.N[p] + BN - 1) / BN;
   TcEpilogue ep;
   ep.C = make_ref(g.C[p], g.ldc[p], FMT_F32); ep.bias = nullptr; ep.relu = 0; ep.mask_src.p = nullptr; ep.accumulate = g.accumulate[p];
-  ep.atomic = 0; ep.colsum = nullptr; ep.trace = nullptr; ep.dbg = 0; ep.csplit = 0;
+  ep.atomic = 0; ep.colsum = nullptr; ep.trace = nullptr; ep.timeline = nullptr; ep.dbg = 0; ep.csplit = 0;
   tc_gemm_tile<KIND, 1, 1, BN>(&g.maps[2 * p], &g.maps[2 * p + 1], ep, g.M[p], g.N[p], (t / tiles_n) * TC_BM, (t % tiles_n) * BN, 0,
                                (g.K + Cfg::BK - 1) / Cfg::BK, nullptr);
 }
 
 // ----------------------------------------------------------------------------- host side
 inline long long*& tc_trace_buffer() { static long long* p = nullptr; return p; }     // debug only (fb200_debug_tc_trace)
+// debug only (fb200_debug_tc_timeline): launch l of the tcgen05 GEMM writes the stamps of its CTAs at buf + l * TC_TL_STRIDE
+constexpr int TC_TL_STRIDE = 8 * 1024;
+struct TcTimeline { long long* buf = nullptr; int max_launches = 0; int next = 0; };
+inline TcTimeline& tc_timeline() { static TcTimeline t; return t; }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -860,6 +894,9 @@ inline int tc_launch_one(const TcGemmArgs& g, int num_sms, cudaStream_t st) {
   }
   ep.csplit = csplit;
   ep.trace = tc_trace_buffer();
+  ep.timeline = nullptr;
+  { TcTimeline& t = tc_timeline();
+    if (t.buf && t.next < t.max_launches && tiles_m * tiles_n * (csplit > 1 ? csplit : split) <= TC_TL_STRIDE / 8) ep.timeline = t.buf + (int64_t)(t.next++) * TC_TL_STRIDE; }
   { static const int dbg = [] { const char* e = getenv("FB200_TC_DBG"); return e ? atoi(e) : 0; }(); ep.dbg = dbg; }
   dim3 grid(tiles_n, tiles_m, csplit > 1 ? csplit : split);
   cudaError_t lrc;

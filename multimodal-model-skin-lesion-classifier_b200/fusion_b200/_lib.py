@@ -88,6 +88,7 @@ def lib():
     sig("fb200_adam_step", i32, i32, pp, pp, pp, pp, C.POINTER(i64), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_float, vp)
     sig("fb200_debug_gemm_replay", i32, dp, pp, vp, vp, vp, vp, vp, vp)
     sig("fb200_debug_tc_trace", i32, vp)
+    sig("fb200_debug_tc_timeline", i32, vp, i32)
     sig("fb200_debug_set_pdl", i32, i32)
     sig("fb200_debug_mega_trace", i32, vp)
     sig("fb200_mega_program_info", i32, dp, i32, C.POINTER(i32))
