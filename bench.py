@@ -596,8 +596,8 @@ def dominant_kernel_roofline(torch, _lib, desc, dev, peaks, dtype, model):
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     traffic, traffic_src = None, None
     try:   # per-launch DRAM bytes of the dominant kernel: a profiler counter, so it comes from the committed ncu --set full
-           # capture of this round (tools/final_r02.sh), not from this run - the file name says which capture
-        traffic_src = "profiles/r02_dominant_kernel_traffic.json"
+           # capture of this round (tools/final_r02e.sh), not from this run - the file name says which capture
+        traffic_src = "profiles/r02e_dominant_kernel_traffic.json"
         traffic = json.load(open(os.path.join(ROOT, traffic_src))).get("dram_bytes_per_launch")
     except Exception:
         traffic_src = None

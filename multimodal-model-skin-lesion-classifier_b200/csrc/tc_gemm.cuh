@@ -37,6 +37,7 @@ constexpr int TC_THREADS = 64 + 32 * TC_WORKERS;  // + TMA producer warp + MMA w
 #ifndef FB200_BF16_OCC2
 #define FB200_BF16_OCC2 1
 #endif
+template <int KIND, bool CL> constexpr bool TC_EARLY_RELEASE = KIND == 0 || CL;     // see the MMA warp in tc_gemm_tile
 template <int KIND> constexpr int tc_min_ctas() { return (KIND == 0 && FB200_BF16_OCC2) ? 2 : 1; }
 
 struct TcEpilogue {
@@ -428,8 +429,10 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
     if (ep.timeline && lane == 0) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[7] = global_ns();   // timeline: MMA warp left the k-loop
     // Release tensor memory as soon as the workers have read the last accumulator chunk(s) out of it (every worker warp arrives
     // on tmem_empty after its tcgen05.ld + wait::ld), while they transpose and store the tile: tcgen05.dealloc takes ~0.5 us here,
-    // which used to sit between the tile's last store and the CTA's exit (r02e, tools/tc_handover.py).
-    {
+    // which otherwise sits between the tile's last store and the CTA's exit (r02e, tools/tc_handover.py).  Same-box A/B of the
+    // whole step: bf16 cfg5 B = 4096 0.531 -> 0.517 ms, fp32 B = 256 (cluster split-K) 0.2192 -> 0.2176, but the fp32 one-wave
+    // GEMMs of the headline batch 0.7292 -> 0.7325 - those keep the release at the end of the CTA.
+    if constexpr (TC_EARLY_RELEASE<KIND, CL>) {
       const int num_chunks = (num_kb + Cfg::CHUNK_KB - 1) / Cfg::CHUNK_KB;
       for (int ch = num_chunks > Cfg::ACC_BUFS ? num_chunks - Cfg::ACC_BUFS : 0; ch < num_chunks; ++ch)
         mbar_wait(&tmem_empty[ch & (Cfg::ACC_BUFS - 1)], (ch / Cfg::ACC_BUFS) & 1);
@@ -719,6 +722,13 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
   // timeline: every warp has stored its rows.  (Stamped by a worker: thread 0 - the TMA producer, idle since its last load - was
   // observed to read the timer right after ARRIVING at this barrier, ~5 us before the workers got there.)
   if (ep.timeline && threadIdx.x == 64) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[2] = global_ns();
+  if constexpr (!TC_EARLY_RELEASE<KIND, CL>) {
+    if (warp == 1) {
+      if (ep.timeline && lane == 0) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[6] = global_ns();
+      tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+      if (ep.timeline && lane == 0) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[5] = global_ns();
+    }
+  }
 }
 
 template <int KIND, int A_MN, int B_MN, int BN, bool CL = false>

@@ -132,7 +132,26 @@ def r02d():
             open(os.path.join(P, src.replace(".log", ".txt")), "w").write(open(os.path.join(G, src)).read())
 
 
+def r02e():
+    """fifth session of round 2: grid-wide GEMM timeline, tensor memory released early (bf16 / cluster kernels), bf16 with two CTAs
+    per SM, finer split of the deferred FFMA weight gradient"""
+    global tag
+    for src, dst, title in (("launches_r02e.csv", "r02e_launch_list_cfg2_B4096.txt", "one train step (forward + CE + backward), cfg2 crossattention, B=4096, fp32-strict"),
+                            ("launches_r02e_cfg5.csv", "r02e_launch_list_cfg5_bf16.txt", "one train step, cfg5 RG-ATT, B=4096, bf16 (two GEMM CTAs per SM)")):
+        if os.path.exists(os.path.join(G, src)):
+            tot, agg = launch_list(src, dst, title); print(dst, "total", tot)
+    if os.path.exists(os.path.join(G, "prof_r02e_tc.ncu-rep")):
+        for r in full(): print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed")})
+    for src in ("r02e_bench_head.json", "r02e_bench_cfg3a.json", "r02e_bench_cfg4b.json", "r02e_bench_cfg5.json", "r02e_bench_2gpu.json", "r02e_gputest.log", "r02e_smoke.log",
+                "r02e_timeline_cfg2_B4096.txt", "r02e_timeline_cfg5_B4096.txt", "r02e_timeline_cfg2_B256.txt", "r02e_handover_gemm.txt", "r02e_handover_micro.txt",
+                "r02e_occ2.txt", "r02e_iso.txt", "r02e_early.txt"):
+        if os.path.exists(os.path.join(G, src)):
+            open(os.path.join(P, src.replace(".log", ".txt")), "w").write(open(os.path.join(G, src)).read())
+
+
 if __name__ == "__main__":
+    if tag == "r02e":
+        r02e(); sys.exit(0)
     if tag == "r02c":
         r02c(); sys.exit(0)
     if tag == "r02d":
