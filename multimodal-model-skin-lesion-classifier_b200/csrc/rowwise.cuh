@@ -763,7 +763,80 @@ inline cudaError_t launch_smalln_fwd(const SmallNArgs& a, int num_sms, cudaStrea
   pdl_launch(smalln_fwd_kernel<8>, grid, ROW_WARPS * 32, 0, st, a);
   return cudaGetLastError();
 }
+// Backward of the small-N Linear for the stand-alone launch (r02e): a THREAD owns one column k of K (KPT columns when K > 256) for
+// every class and walks the CTA's rows, so its C weight-gradient partials never meet another thread's - no shared-memory
+// reduction at all (the warp-per-row body above ends in 48 shared fp32 atomicAdds per lane, compare-and-swap loops that eight
+// warps contend on: 21 us at B = 4096 and 12 us at B = 256 on the critical path where the lanes have joined).  A warp reads and
+// writes 128 contiguous bytes of a row per access; the loads of UR rows are issued before the first use; dX rows are stored as
+// they are formed; one red.global per weight-gradient element per CTA at the end.
+template <int MAXC, int KPT>
+__global__ void __launch_bounds__(ROW_WARPS * 32) smalln_bwd_cols_kernel(const SmallNArgs a, const int rows_per_cta) { pdl_sync();
+  constexpr int NT = ROW_WARPS * 32, UR = 4;
+  const int t = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < (int64_t)a.B ? r0 + rows_per_cta : (int64_t)a.B;
+  float w[MAXC][KPT], dw[MAXC][KPT], dbacc[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    dbacc[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+      const int k = t + NT * j;
+      w[c][j] = (c < a.C && k < a.K) ? __ldg(a.W + (int64_t)c * a.K + k) : 0.f;
+      dw[c][j] = 0.f;
+    }
+  }
+  const bool has_dx = a.dx.p != nullptr, has_mask = has_dx && a.mask_src.p != nullptr, acc_dx = has_dx && a.dx_accumulate != 0;
+  for (int64_t r = r0; r < r1; r += UR) {
+    float x[UR][KPT], mk[UR][KPT], o[UR][KPT], dl[UR][MAXC];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const int64_t row = r + u; const bool ok = row < r1;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) dl[u][c] = (ok && c < a.C) ? __ldcg((const float*)a.dy.p + row * a.dy.ld + c) : 0.f;
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        const int k = t + NT * j; const bool live = ok && k < a.K;
+        x[u][j] = live ? ld1(a.x, row, k) : 0.f;
+        mk[u][j] = (live && has_mask) ? ld1(a.mask_src, row, k) : 1.f;
+        o[u][j] = (live && acc_dx) ? ld1(a.dx, row, k) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const int64_t row = r + u; const bool ok = row < r1;
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        const int k = t + NT * j;
+        float g = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) { g += dl[u][c] * w[c][j]; dw[c][j] += dl[u][c] * x[u][j]; }
+        g = (mk[u][j] > 0.f ? g : 0.f) + o[u][j];
+        if (has_dx && ok && k < a.K) st1(a.dx, row, k, g);
+      }
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) dbacc[c] += dl[u][c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (c < a.C) {
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) { const int k = t + NT * j; if (k < a.K) red_add(a.dW + (int64_t)c * a.K + k, dw[c][j]); }
+      if (t == c) red_add(a.db + c, dbacc[c]);            // every thread saw every row of the CTA: thread c speaks for class c
+    }
+  }
+}
 inline cudaError_t launch_smalln_bwd(const SmallNArgs& a, int num_sms, cudaStream_t st) {
+  static const int legacy = [] { const char* e = getenv("FB200_SMALLN_ROWS"); return e ? atoi(e) : 0; }();      // 1: the warp-per-row kernel (A/B runs)
+  if (!legacy) {
+    // ~2 CTAs per SM at large batches, at least 8 rows (two trips) per CTA: the CTA count is also the number of atomics per address
+    int rows = (a.B + 2 * num_sms - 1) / (2 * num_sms); if (rows < 8) rows = 8;
+    const int grid = (a.B + rows - 1) / rows;
+    if (a.K <= ROW_WARPS * 32) pdl_launch(smalln_bwd_cols_kernel<8, 1>, grid, ROW_WARPS * 32, 0, st, a, rows);
+    else pdl_launch(smalln_bwd_cols_kernel<8, 2>, grid, ROW_WARPS * 32, 0, st, a, rows);
+    return cudaGetLastError();
+  }
   // two rows per warp: each CTA ends with one global atomic per weight-gradient element, so the grid is also the number of
   // atomics every address receives
   int grid = (a.B + ROW_WARPS * 2 - 1) / (ROW_WARPS * 2); if (grid > num_sms * 3) grid = num_sms * 3; if (grid < 1) grid = 1;

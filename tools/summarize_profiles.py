@@ -144,7 +144,7 @@ def r02e():
         for r in full(): print({k: v for k, v in r.items() if k in ("Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed")})
     for src in ("r02e_bench_head.json", "r02e_bench_cfg3a.json", "r02e_bench_cfg4b.json", "r02e_bench_cfg5.json", "r02e_bench_2gpu.json", "r02e_gputest.log", "r02e_smoke.log",
                 "r02e_timeline_cfg2_B4096.txt", "r02e_timeline_cfg5_B4096.txt", "r02e_timeline_cfg2_B256.txt", "r02e_handover_gemm.txt", "r02e_handover_micro.txt",
-                "r02e_occ2.txt", "r02e_iso.txt", "r02e_early.txt"):
+                "r02e_occ2.txt", "r02e_iso.txt", "r02e_early.txt", "r02e_smalln.txt", "r02e_kloop_dbg.txt"):
         if os.path.exists(os.path.join(G, src)):
             open(os.path.join(P, src.replace(".log", ".txt")), "w").write(open(os.path.join(G, src)).read())
 

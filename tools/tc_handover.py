@@ -19,7 +19,7 @@ L.fb200_debug_tc_timeline(buf.data_ptr(), 2); run(); torch.cuda.synchronize(); n
 a = buf.cpu().numpy().reshape(2, 1024, 8)[0]; a = a[a[:, 0] > 0]
 t0 = a[:, 0].min()
 ev = sorted((int(r[3]), (r[0] - t0) / 1e3, (r[1] - t0) / 1e3, (r[2] - t0) / 1e3) for r in a)
-g = np.array([ev[i + 1][1] - ev[i][3] for i in range(len(ev) - 1) if ev[i][0] == ev[i + 1][0]])
+g = np.array([ev[i + 1][1] - ev[i][3] for i in range(len(ev) - 1) if ev[i][0] == ev[i + 1][0]] or [float("nan")])     # (one wave: no pairs)
 life = np.array([e[3] - e[1] for e in ev])
 m = lambda i, j: np.median(a[:, i] - a[:, j]) / 1e3
 print(f"  relative to 'tile stored' (us, median): MMA warp left k-loop {m(7,2):+.2f}; accumulator in registers {m(4,2):+.2f}; dealloc issued {m(6,2):+.2f}; tensor memory released {m(5,2):+.2f}; entry {m(0,2):+.2f}; wait passed {m(1,2):+.2f}")
