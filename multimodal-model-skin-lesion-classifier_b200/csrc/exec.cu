@@ -222,18 +222,34 @@ static int run_forward(Ctx& c) {
   const Plan& p = c.p; const int B = p.d.B;
   if (c.mega) { c.vready.assign(p.acts.size(), 0); }
   if (p.splitk_bytes && !c.gemm_only && !c.mega) CUDA_OK(cudaMemsetAsync(c.ws + p.counters_off, 0, 4096 * sizeof(unsigned), c.st));
-  for (size_t base = 0; base < p.wprep.size(); base += 32) {
-    PrepArgs a{}; a.fmt = p.fmt; a.nseg = 0;
-    for (size_t i = base; i < p.wprep.size() && a.nseg < 32; ++i) {
-      const WPrep& w = p.wprep[i];
-      PrepSeg& sg = a.seg[a.nseg++];
-      sg.src = c.param(w.slot, (int64_t)w.row0 * w.cols); sg.dst = c.ws + w.off; sg.n4 = (int64_t)w.rows * w.cols / 4; sg.plane = (int64_t)w.rows * w.cols;
+  // bf16: operand-format copies of the weights (wprep_kernel), on the caller's stream before the lanes fork.  FB200_WPREP_SIDE=1
+  // makes them on the SIDE lane instead (the main lane starts with the format copy of the image features and only its first
+  // tcgen05 GEMM needs the copies; the side lane starts with the FFMA GEMM of the raw metadata).  Measured mixed on the same box
+  // (r02e, profiles/r02e_wprep.txt: cfg5 B = 4096 0.516 -> 0.511 ms, cfg4b 0.448 -> 0.452, B = 256 +0.3-1.4 %), so it stays off.
+  auto launch_wprep = [&](cudaStream_t st) -> int {
+    for (size_t base = 0; base < p.wprep.size(); base += 32) {
+      PrepArgs a{}; a.fmt = p.fmt; a.nseg = 0;
+      for (size_t i = base; i < p.wprep.size() && a.nseg < 32; ++i) {
+        const WPrep& w = p.wprep[i];
+        PrepSeg& sg = a.seg[a.nseg++];
+        sg.src = c.param(w.slot, (int64_t)w.row0 * w.cols); sg.dst = c.ws + w.off; sg.n4 = (int64_t)w.rows * w.cols / 4; sg.plane = (int64_t)w.rows * w.cols;
+      }
+      if (!c.gemm_only) pdl_launch(wprep_kernel, dim3(64, a.nseg), 256, 0, st, a);
+      CUDA_OK(cudaGetLastError());
     }
-    if (!c.gemm_only) pdl_launch(wprep_kernel, dim3(64, a.nseg), 256, 0, c.st, a);
-    CUDA_OK(cudaGetLastError());
-  }
+    return FB200_OK;
+  };
+  static const bool wprep_side_env = [] { const char* e = getenv("FB200_WPREP_SIDE"); return e && atoi(e) != 0; }();
+  const bool wprep_side = wprep_side_env && p.two_lanes && !p.wprep.empty() && !c.mega;
+  if (!wprep_side) { int rc = launch_wprep(c.st); if (rc != FB200_OK) return rc; }
   LaneSync ls; const cudaStream_t main_st = c.st;
   { int rc = ls.begin(c, p.acts.size()); if (rc != FB200_OK) return rc; }
+  cudaEvent_t wprep_done = nullptr;           // recorded on the side lane; the main lane waits for it before its first tcgen05 GEMM
+  if (wprep_side) {
+    if (!ls.on) return FB200_ECUDA;
+    int rc = launch_wprep(c.lane_st[1]); if (rc != FB200_OK) return rc;
+    rc = ls.record(1, wprep_done); if (rc != FB200_OK) return rc;
+  }
   // ops up to the last one of the side lane may have a GEMM of the other lane running beside them (cluster split-K hint)
   int last_side = -1;
   if (p.two_lanes) for (int i = 0; i < (int)p.ops.size(); ++i) if (p.ops[i].lane == 1) last_side = i;
@@ -242,6 +258,7 @@ static int run_forward(Ctx& c) {
     ++op_index;
     c.st = c.lane_st[o.lane];
     for (int b : {o.in0.buf, o.in1.buf, o.in2.buf}) { int rc = ls.wait_for(o.lane, b); if (rc != FB200_OK) return rc; }
+    if (wprep_done && o.lane == 0 && o.kind == OP_LINEAR && o.engine == 1) { CUDA_OK(cudaStreamWaitEvent(ls.st[0], wprep_done, 0)); wprep_done = nullptr; }
     const int mst = c.mega ? 1 + std::max(c.vr(o.in0.buf), std::max(c.vr(o.in1.buf), c.vr(o.in2.buf))) : 0;   // stage of this op in the step kernel
     int mout = mst;                                                                                            // stage after which its output is complete
     switch (o.kind) {
