@@ -720,7 +720,9 @@ __device__ __forceinline__ void tc_gemm_tile(const CUtensorMap* __restrict__ pma
   }
   __syncthreads();
   // timeline: every warp has stored its rows.  (Stamped by a worker: thread 0 - the TMA producer, idle since its last load - was
-  // observed to read the timer right after ARRIVING at this barrier, ~5 us before the workers got there.)
+  // observed to read the timer right after ARRIVING at this barrier, ~5 us before the workers got there: the SASS is
+  // BAR.SYNC.DEFER_BLOCKING followed by CS2R SR_GLOBALTIMER, and the timer read evidently issues in the barrier's shadow - only
+  // the store of the value waited.  A worker arrives last, so its stamp is right.)
   if (ep.timeline && threadIdx.x == 64) (ep.timeline + 8 * (int64_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)))[2] = global_ns();
   if constexpr (!TC_EARLY_RELEASE<KIND, CL>) {
     if (warp == 1) {
